@@ -1,0 +1,134 @@
+/*
+ * knnsvc_b200.h — C ABI of the B200-native kNN-SVC matcher hot path.
+ *
+ * The reference (SmoothKen/knn-svc) has no FFI layer: its seam is a set of
+ * Python functions.  Each entry point below is the device-side
+ * replacement for one of those functions; the Python mirror in
+ * knn_svc_b200/ (same names and argument meaning as the reference) is a thin
+ * ctypes caller of this library.  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller owns all memory, including workspaces (sizes are queried);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), on the
+ *     current device; nothing synchronises the host;
+ *   - return value 0 = ok, >0 = cudaError_t, <0 = argument error;
+ *     knnsvc_last_error() returns a message for the calling thread;
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef KNNSVC_B200_H
+#define KNNSVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KNNSVC_MAX_K 32          /* ddsp_prematch_dataset.py:1203 takes k=32 */
+#define KNNSVC_GREEDY_K 4        /* ddsp_prematch_dataset.py:1246 keeps 4    */
+
+const char* knnsvc_last_error(void);
+int knnsvc_version(void);
+
+/* ---- K1 pre-pass: row norms + unit-normalised fp16 copy ------------------
+ * Replaces torch.norm(x, p=2, dim=-1) at lib_ongaku_test.py:150-151 /
+ * ddsp_matcher.py:215-216, and prepares the tensor-core operand.
+ *   x        [rows, ld] fp32, first `dim` columns used
+ *   half_out [rows, dim_pad] fp16 = fp16(x * 1024/|x|), zero in the pad columns
+ *   norms    [rows] fp32 = |x|
+ *   bad_rows int counter, incremented per zero-norm / non-finite row (the
+ *            reference NaNs and exits there, lib_ongaku_test.py:166-169)
+ */
+int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld,
+                        void* half_out, int dim_pad, float* norms,
+                        int* bad_rows, void* stream);
+
+/* ---- K1 full matrix (API parity only; never on the fused path) -----------
+ * fast_cosine_dist(source_feats, matching_pool) — lib_ongaku_test.py:148-175,
+ * ddsp_matcher.py:213-221.  out [n_query, n_pool] fp32 = 1 - q.p/(|q||p|).
+ */
+int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t n_pool,
+                       int dim, float* out, void* stream);
+
+/* ---- K1+K2 fused: cosine-distance kNN, k smallest per query row ----------
+ * Replaces the chunk-20 loop fast_cosine_dist + .topk(k, largest=False) at
+ * ddsp_prematch_dataset.py:1196-1206 and ddsp_matcher.py:550-554.
+ * tcgen05 fp16 GEMM (fp32 accumulate in TMEM) filters candidates with a
+ * rigorous error window, survivors are re-scored exactly from the fp32 rows;
+ * rows the window cannot decide go through an exact brute-force kernel.
+ * The [n_query, n_pool] matrix is never written.
+ *   q/p       fp32 rows [n, dim] (ld = dim); qh/ph/qn/pn from knnsvc_prepare_rows
+ *   index_offset  added to every returned index (pool shard offset, C1)
+ *   out_dist  [n_query, k] fp32 ascending;  out_idx [n_query, k] int64
+ *   stats     optional int[8]: {flagged rows, logged candidates (sat.), survivors,
+ *             segments, units, grid, log cap, reserved}
+ */
+size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, int k);
+int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query,
+                      const float* p, const void* ph, const float* pn, int64_t n_pool,
+                      int dim, int dim_pad, int k, int64_t index_offset,
+                      float* out_dist, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, int* stats, void* stream);
+
+/* Exact brute-force kNN on CUDA cores (same outputs as knnsvc_knn_search).
+ * Used for rows the filter flags, and by tests as an independent GPU check. */
+size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k);
+int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query,
+                     const float* p, const float* pn, int64_t n_pool, int dim, int k,
+                     int64_t index_offset, float* out_dist, int64_t* out_idx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- C1: merge per-shard top-k lists (after the NCCL all-gather) ---------
+ * gathered_dist/idx [n_shards, n_query, k]; out [n_query, k]; ties -> lower index,
+ * so the result does not depend on the shard count. */
+int knnsvc_merge_topk(const float* gathered_dist, const int64_t* gathered_idx, int n_shards,
+                      int64_t n_query, int k, float* out_dist, int64_t* out_idx, void* stream);
+
+/* ---- K3: gather + weighted mix -------------------------------------------
+ * out[t,:] = sum_k w[t,k] * pool[idx[t,k],:]  (w == NULL -> mean) —
+ * ddsp_prematch_dataset.py:1348,1358,1364,1435,1444,1446; ddsp_matcher.py:578. */
+int knnsvc_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx,
+                      const float* weights, int64_t n_query, int k, float* out, void* stream);
+
+/* ---- K4: f0-compatibility re-rank ----------------------------------------
+ * sort_by_f0_compatibility — ddsp_prematch_dataset.py:954-997: stable ascending
+ * sort of each row's k candidates by |log2(f0[idx]+1e-5) - log2(expected+1e-5)|. */
+int knnsvc_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx,
+                     int64_t n_query, int k, int64_t* out_idx, void* stream);
+
+/* ---- K5: greedy concatenation-cost re-selection ---------------------------
+ * knn_with_concat_cost — lib_ongaku_test.py:270-369, K = 4 candidates per frame.
+ * Utterance u owns query rows [utt_offsets[u], utt_offsets[u+1]) (host array);
+ * one CTA walks one utterance.  src_f0/pool_f0 NULL selects the no-f0 branch. */
+int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const float* pool,
+                                int64_t n_pool, int dim, const float* shifted_src_f0,
+                                const float* pool_f0, float concat_weight,
+                                const int64_t* utt_offsets_host, int n_utt,
+                                int64_t* out_idx, void* stream);
+
+/* ---- K6: Adam(amsgrad) fit of per-frame softmax mixing weights ------------
+ * compute_wavlm_weight (loss_scale 0.1) — ddsp_prematch_dataset.py:574-680;
+ * compute_extended_weight (loss_scale 1000) — :807-924.
+ *   info (device, optional) double[4]: {stop iteration, best loss, first loss, 0} */
+size_t knnsvc_weight_fit_workspace_bytes(int64_t n_query, int k);
+int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                      int64_t n_query, int k, double loss_scale, int max_iters,
+                      float* out_weights, double* info,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7 / K7': additive harmonic bank -------------------------------------
+ * get_bulk_dsp_choral — ddsp_prematch_dataset.py:165-208 (amp != NULL, H harmonics)
+ * and the single sinusoid of hifigan/ddsp_models_f0.py:344-352 (amp == NULL).
+ *   f0 [batch, frames]; amp [batch, frames, n_harm]; out [batch, frames*hop] fp32
+ *   phase_ws: double[batch*frames] scratch */
+int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames,
+                         int n_harm, int sample_rate, int hop, float* out,
+                         double* phase_ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNNSVC_B200_H */

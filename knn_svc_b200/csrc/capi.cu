@@ -1,0 +1,203 @@
+// extern "C" entry points declared in include/knnsvc_b200.h.
+#include <string.h>
+
+#include "../../include/knnsvc_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct KnnWorkspace {
+  float* log_val;
+  int* log_idx;
+  int* log_cnt;
+  float* seg_top;
+  int64_t* flag_list;
+  int* counters;  // [0] flag count, [1..8] stats
+  void* exact_partial;
+  size_t total;
+};
+
+KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const FilterPlan& pl) {
+  KnnWorkspace w;
+  size_t off = 0;
+  unsigned char* b = reinterpret_cast<unsigned char*>(base);
+  const size_t slots = (size_t)n_query * pl.n_seg;
+  auto take = [&](size_t bytes) {
+    void* p = b ? b + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.log_val = reinterpret_cast<float*>(take(slots * pl.cap * sizeof(float)));
+  w.log_idx = reinterpret_cast<int*>(take(slots * pl.cap * sizeof(int)));
+  w.log_cnt = reinterpret_cast<int*>(take(slots * sizeof(int)));
+  w.seg_top = reinterpret_cast<float*>(take(slots * k * sizeof(float)));
+  w.flag_list = reinterpret_cast<int64_t*>(take(kFlagCap * sizeof(int64_t)));
+  w.counters = reinterpret_cast<int*>(take(16 * sizeof(int)));
+  w.exact_partial = take(exact_partial_bytes(kFlagCap, n_pool, k));
+  w.total = off;
+  return w;
+}
+
+__global__ void write_plan_stats(int* stats, const int* counters, int n_seg, int n_units, int grid, int cap) {
+  stats[0] = counters[1];
+  stats[1] = counters[2];
+  stats[2] = counters[3];
+  stats[3] = n_seg;
+  stats[4] = n_units;
+  stats[5] = grid;
+  stats[6] = cap;
+  stats[7] = counters[0];
+}
+
+}  // namespace
+}  // namespace knnsvc
+
+using namespace knnsvc;
+
+extern "C" {
+
+const char* knnsvc_last_error(void) { return g_err; }
+int knnsvc_version(void) { return 100; }
+
+int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad, float* norms,
+                        int* bad_rows, void* stream) {
+  KNN_CHECK_ARG(rows >= 0 && dim >= 1 && ld >= dim && dim_pad >= dim, -1, "prepare_rows: bad shape");
+  KNN_CHECK_ARG(x && half_out && norms && bad_rows, -1, "prepare_rows: null pointer");
+  return launch_prepare_rows(x, rows, dim, ld, half_out, dim_pad, norms, bad_rows, (cudaStream_t)stream);
+}
+
+int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t n_pool, int dim, float* out,
+                       void* stream) {
+  KNN_CHECK_ARG(n_query >= 0 && n_pool >= 0 && dim >= 1, -1, "cosine_dist: bad shape");
+  return launch_cosine_dist(q, n_query, p, n_pool, dim, out, (cudaStream_t)stream);
+}
+
+size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, int k) {
+  (void)dim_pad;
+  if (n_query <= 0 || n_pool <= 0 || k < 1 || k > kMaxK) return 0;
+  FilterPlan pl = plan_filter(n_query, n_pool, k);
+  return carve(nullptr, n_query, n_pool, k, pl).total;
+}
+
+int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
+                      const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+                      int64_t index_offset, float* out_dist, int64_t* out_idx, void* workspace,
+                      size_t workspace_bytes, int* stats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KNN_CHECK_ARG(n_query >= 0 && n_pool >= 1 && dim >= 1 && dim_pad >= dim, -1, "knn_search: bad shape");
+  KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -1, "knn_search: k=%d outside [1,%d]", k, kMaxK);
+  KNN_CHECK_ARG(k <= n_pool, -1, "knn_search: k=%d exceeds the pool size %lld", k, (long long)n_pool);
+  if (n_query == 0) return 0;
+  KNN_CHECK_ARG(q && qh && qn && p && ph && pn && out_dist && out_idx && workspace, -1, "knn_search: null pointer");
+  FilterPlan pl = plan_filter(n_query, n_pool, k);
+  KnnWorkspace w = carve(workspace, n_query, n_pool, k, pl);
+  KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
+  KNN_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), stream));
+  int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
+                             stream);
+  if (rc) return rc;
+  rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
+                          index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, stream);
+  if (rc) return rc;
+  // rows the error window could not decide: exact brute force, count known only on the device
+  rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, w.flag_list, w.counters, 0, 0, kFlagCap,
+                             index_offset, out_dist, out_idx, w.exact_partial, stream);
+  if (rc) return rc;
+  if (stats) {
+    write_plan_stats<<<1, 1, 0, stream>>>(stats, w.counters, pl.n_seg, pl.n_units, pl.grid, pl.cap);
+    KNN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k) {
+  int64_t slots = n_query < kFlagCap ? n_query : kFlagCap;
+  if (slots < 1) slots = 1;
+  return exact_partial_bytes(slots, n_pool, k) + 256;
+}
+
+int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+                     int64_t n_pool, int dim, int k, int64_t index_offset, float* out_dist, int64_t* out_idx,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  KNN_CHECK_ARG(n_query >= 0 && n_pool >= 1 && dim >= 1, -1, "knn_exact: bad shape");
+  KNN_CHECK_ARG(k >= 1 && k <= kMaxK && k <= n_pool, -1, "knn_exact: bad k=%d", k);
+  KNN_CHECK_ARG(workspace_bytes >= knnsvc_knn_exact_workspace_bytes(n_query, n_pool, k), -2,
+                "knn_exact: workspace too small");
+  const int64_t cap = n_query < kFlagCap ? n_query : kFlagCap;
+  for (int64_t base = 0; base < n_query; base += cap) {
+    const int64_t n = (n_query - base) < cap ? (n_query - base) : cap;
+    int rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, nullptr, nullptr, n, base, cap,
+                                   index_offset, out_dist, out_idx, workspace, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int knnsvc_merge_topk(const float* gathered_dist, const int64_t* gathered_idx, int n_shards, int64_t n_query, int k,
+                      float* out_dist, int64_t* out_idx, void* stream) {
+  KNN_CHECK_ARG(gathered_dist && gathered_idx && out_dist && out_idx, -1, "merge_topk: null pointer");
+  return launch_merge_topk(gathered_dist, gathered_idx, n_shards, n_query, k, out_dist, out_idx, (cudaStream_t)stream);
+}
+
+int knnsvc_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,
+                      int64_t n_query, int k, float* out, void* stream) {
+  KNN_CHECK_ARG(pool && idx && out && n_pool >= 1 && k >= 1, -1, "gather_mix: bad arguments");
+  return launch_gather_mix(pool, n_pool, dim, idx, weights, n_query, k, out, (cudaStream_t)stream);
+}
+
+int knnsvc_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx, int64_t n_query, int k,
+                     int64_t* out_idx, void* stream) {
+  KNN_CHECK_ARG(expected_f0 && pool_f0 && idx && out_idx, -1, "f0_rerank: null pointer");
+  return launch_f0_rerank(expected_f0, pool_f0, idx, n_query, k, out_idx, (cudaStream_t)stream);
+}
+
+int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+                                const float* shifted_src_f0, const float* pool_f0, float concat_weight,
+                                const int64_t* utt_offsets_host, int n_utt, int64_t* out_idx, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KNN_CHECK_ARG(idx && src && pool && out_idx && utt_offsets_host && n_utt >= 0, -1, "concat_cost: bad arguments");
+  KNN_CHECK_ARG((shifted_src_f0 == nullptr) == (pool_f0 == nullptr), -1,
+                "concat_cost: shifted_src_f0 and pool_f0 must be given together");
+  if (n_utt == 0) return 0;
+  int64_t* d_off = nullptr;
+  KNN_CUDA(cudaMallocAsync(&d_off, (size_t)(n_utt + 1) * sizeof(int64_t), stream));
+  KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           stream));
+  int rc = launch_concat_cost(idx, src, pool, n_pool, dim, shifted_src_f0, pool_f0, concat_weight, d_off, n_utt,
+                              out_idx, stream);
+  cudaFreeAsync(d_off, stream);
+  return rc;
+}
+
+size_t knnsvc_weight_fit_workspace_bytes(int64_t n_query, int k) { return weight_fit_workspace_bytes(n_query, k); }
+
+int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
+                      double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  KNN_CHECK_ARG(idx && synth && out_weights && workspace, -1, "weight_fit: null pointer");
+  KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(n_query, k), -2, "weight_fit: workspace too small");
+  return launch_weight_fit(idx, synth, n_pool, dim, n_query, k, loss_scale, max_iters, out_weights, info, workspace,
+                           (cudaStream_t)stream);
+}
+
+int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,
+                         int hop, float* out, double* phase_ws, void* stream) {
+  KNN_CHECK_ARG(f0 && out && phase_ws && batch >= 0 && frames >= 0, -1, "harmonic_bank: bad arguments");
+  return launch_harmonic_bank(f0, amp, batch, frames, n_harm, sample_rate, hop, out, phase_ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Internal launcher declarations shared by the .cu files and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace knnsvc {
+
+// ---- rows.cu
+int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
+                        float* norms, int* bad_rows, cudaStream_t stream);
+int launch_cosine_dist(const float* q, int64_t nq, const float* p, int64_t np_, int dim, float* out,
+                       cudaStream_t stream);
+int exact_chunks(int64_t n_pool);
+size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k);
+int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+                          int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
+                          int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
+                          float* out_dist, int64_t* out_idx, void* partial, cudaStream_t stream);
+
+// ---- knn_filter_sm100.cu
+struct FilterPlan {
+  int n_qtiles, n_ptiles, n_seg, n_units, grid, cap;
+};
+FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
+int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
+                      const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
+                      cudaStream_t stream);
+
+// ---- knn_select.cu
+constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb
+int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+                       int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
+                       const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
+                       float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
+                       cudaStream_t stream);
+int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
+                      int64_t* out_idx, cudaStream_t stream);
+
+// ---- post.cu
+int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,
+                      int64_t n_query, int k, float* out, cudaStream_t stream);
+int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx, int64_t n_query, int k,
+                     int64_t* out_idx, cudaStream_t stream);
+int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+                       const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
+                       int n_utt, int64_t* out_idx, cudaStream_t stream);
+
+// ---- weight_fit.cu
+size_t weight_fit_workspace_bytes(int64_t n_query, int k);
+int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
+                      double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
+                      cudaStream_t stream);
+
+// ---- harmonic.cu
+int launch_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,
+                         int hop, float* out, double* phase_ws, cudaStream_t stream);
+
+}  // namespace knnsvc

@@ -1,0 +1,431 @@
+// K1+K2 fused: cosine-similarity GEMM on the 5th-gen tensor cores with a
+// streaming candidate filter in the epilogue.  Replaces the reference's chunk-20
+// loop  fast_cosine_dist(...) ; dists.topk(k=32, largest=False)
+// (ddsp_prematch_dataset.py:1196-1206, lib_ongaku_test.py:148-175) without ever
+// writing the [T, Np] distance matrix.
+//
+// Shape of the computation (per CTA, persistent over work units):
+//   A = 128 query rows   x 64 fp16  (TMA, SWIZZLE_128B, K-major)   -> UMMA M = 128
+//   B = 256 pool rows    x 64 fp16  (TMA, SWIZZLE_128B, K-major)   -> UMMA N = 256
+//   D = 128 lanes x 256 fp32 columns in TMEM, double buffered (512 columns)
+//   warp 0 : TMA producer      warp 1 : tcgen05.mma issuer + TMEM owner
+//   warps 2-5 : epilogue, one thread per query row (TMEM lane), tcgen05.ld 32x32b
+//
+// A work unit is (query tile, pool segment): the CTA keeps its 128 rows and walks
+// the segment's pool tiles, so each epilogue thread carries one row's running
+// threshold in a register across the whole segment.
+//
+// Filter rule (rigorous, DESIGN.md "exact top-k from an fp16 GEMM"): operands are
+// unit-normalised rows cast to fp16, so the accumulator is the cosine similarity
+// s~ with |s~ - s| <= eps.  The thread tracks tau_k = k-th largest s~ seen so far
+// and LOGS every column with s~ > tau_k - 2*eps.  Every true top-k member is in
+// the log; knn_rescore re-scores the log exactly from the fp32 rows.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct SmemLayout {
+  // operand ring first: SWIZZLE_128B wants 1024-byte aligned stage bases
+  static constexpr int ring = 0;
+  static constexpr int topv = ring + STAGES * STAGE_BYTES;              // float [kMaxK][BM]
+  static constexpr int bars = topv + kMaxK * BM * 4;                    // mbarriers
+  static constexpr int full_bar = bars;                                 // [STAGES]
+  static constexpr int empty_bar = full_bar + STAGES * 8;               // [STAGES]
+  static constexpr int tmem_full_bar = empty_bar + STAGES * 8;          // [2]
+  static constexpr int tmem_empty_bar = tmem_full_bar + 2 * 8;          // [2]
+  static constexpr int tmem_ptr = tmem_empty_bar + 2 * 8;               // uint32
+  static constexpr int total = tmem_ptr + 16;
+};
+constexpr int SMEM_BYTES = SmemLayout::total + 1024;  // slack for manual 1024 B alignment
+
+// ----------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row core groups of
+// 1024 B (SBO), version 1 (Blackwell), layout type 2 (128-byte swizzle).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128.
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct RowState {
+  float tau_lo;  // scaled: log everything strictly above this
+  int cnt;       // entries in this row's log (cap+1 = overflowed)
+};
+
+// Rare path: one accumulator value passed the register threshold.  Logs it and,
+// if it also beats the running k-th best, updates the sorted top-k values kept
+// in shared memory ([slot][row] so the 32 rows of a warp hit 32 banks).
+__device__ __noinline__ RowState filter_insert(RowState st, float v, int col, float* __restrict__ topv_row, int k,
+                                               float* __restrict__ log_val, int* __restrict__ log_idx, int cap,
+                                               float window_scaled) {
+  if (st.cnt == cap) {
+    // compact in place: entries below the current threshold can never be needed (tau only rises)
+    int n = 0;
+    for (int e = 0; e < cap; ++e) {
+      float lv = log_val[e];
+      if (lv * kDotScale > st.tau_lo) {
+        int li = log_idx[e];
+        log_val[n] = lv;
+        log_idx[n] = li;
+        ++n;
+      }
+    }
+    st.cnt = n;
+  }
+  if (st.cnt < cap) {
+    log_val[st.cnt] = v * kDotUnscale;
+    log_idx[st.cnt] = col;
+    ++st.cnt;
+  } else {
+    st.cnt = cap + 1;  // genuine overflow: more than `cap` candidates inside the window
+  }
+  float kth = topv_row[(k - 1) * BM];
+  if (v > kth) {
+    int j = k - 1;
+    while (j > 0) {
+      float up = topv_row[(j - 1) * BM];
+      if (!(up < v)) break;
+      topv_row[j * BM] = up;
+      --j;
+    }
+    topv_row[j * BM] = v;
+    kth = topv_row[(k - 1) * BM];
+    st.tau_lo = kth - window_scaled;  // -inf until k values have been seen
+  }
+  return st;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
+                  int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
+                  int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
+                  float* __restrict__ seg_top) {
+  extern __shared__ unsigned char smem_raw_unaligned[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
+                                                         ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_units = n_qtiles * n_seg;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_p) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(sbase + SmemLayout::full_bar + s * 8, 1);
+      mbar_init(sbase + SmemLayout::empty_bar + s * 8, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sbase + SmemLayout::tmem_full_bar + b * 8, 1);
+      mbar_init(sbase + SmemLayout::tmem_empty_bar + b * 8, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SmemLayout::tmem_ptr),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::tmem_ptr);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int seg = u / n_qtiles, qt = u % n_qtiles;
+        const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
+        for (int pt = t0; pt < t1; ++pt) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(sbase + SmemLayout::empty_bar + stage * 8, phase ^ 1);
+            const uint32_t full = sbase + SmemLayout::full_bar + stage * 8;
+            mbar_expect_tx(full, STAGE_BYTES);
+            const uint32_t a_dst = sbase + SmemLayout::ring + stage * STAGE_BYTES;
+            tma_load_2d(a_dst, &map_q, full, kb * BK, qt * BM);
+            tma_load_2d(a_dst + A_BYTES, &map_p, full, kb * BK, pt * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_n = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int seg = u / n_qtiles;
+        const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
+        for (int pt = t0; pt < t1; ++pt, ++tile_n) {
+          const uint32_t buf = tile_n & 1;
+          const uint32_t buf_phase = (tile_n >> 1) & 1;
+          mbar_wait(sbase + SmemLayout::tmem_empty_bar + buf * 8, buf_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(sbase + SmemLayout::full_bar + stage * 8, phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = sbase + SmemLayout::ring + stage * STAGE_BYTES;
+            const uint64_t da = make_smem_desc(a_addr);
+            const uint64_t db = make_smem_desc(a_addr + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              // advancing 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), kInstrDesc, (kb | kk) != 0);
+            }
+            tcgen05_commit(sbase + SmemLayout::empty_bar + stage * 8);  // smem slot free once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tcgen05_commit(sbase + SmemLayout::tmem_full_bar + buf * 8);  // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: streaming candidate filter =====================
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
+    const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside the tile
+    float* topv_row = reinterpret_cast<float*>(smem + SmemLayout::topv) + row_in_tile;
+    const float window_scaled = 2.0f * kFilterEps * kDotScale;
+    uint32_t tile_n = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int seg = u / n_qtiles, qt = u % n_qtiles;
+      const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
+      const int64_t row = (int64_t)qt * BM + row_in_tile;
+      const bool row_ok = row < n_query;
+      for (int j = 0; j < k; ++j) topv_row[j * BM] = -INFINITY;
+      RowState st;
+      st.tau_lo = row_ok ? -INFINITY : INFINITY;
+      st.cnt = 0;
+      const int64_t slot = row * n_seg + seg;
+      float* lv = log_val + (row_ok ? slot * cap : 0);
+      int* li = log_idx + (row_ok ? slot * cap : 0);
+      for (int pt = t0; pt < t1; ++pt, ++tile_n) {
+        const uint32_t buf = tile_n & 1;
+        const uint32_t buf_phase = (tile_n >> 1) & 1;
+        mbar_wait(sbase + SmemLayout::tmem_full_bar + buf * 8, buf_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+        const int col0 = pt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          if (mx > st.tau_lo) {
+            const int cbase = col0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
+                st = filter_insert(st, v, cbase + j, topv_row, k, lv, li, cap, window_scaled);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + SmemLayout::tmem_empty_bar + buf * 8);
+      }
+      if (row_ok) {
+        log_cnt[slot] = st.cnt;
+        for (int j = 0; j < k; ++j) seg_top[slot * k + j] = topv_row[j * BM] * kDotUnscale;
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_half_map(CUtensorMap* map, const void* base, int64_t rows, int dim_pad, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  KNN_CHECK_ARG(fn != nullptr, -10, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)dim_pad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KNN_CHECK_ARG(r == CUDA_SUCCESS, -11, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
+  FilterPlan pl;
+  pl.n_qtiles = (int)ceil_div64(n_query, BM);
+  pl.n_ptiles = (int)ceil_div64(n_pool, BN);
+  int num_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
+  }
+  // choose the number of pool segments: minimise waves*tiles_per_unit, with a
+  // small penalty per segment (each one restarts the running threshold -> more log traffic)
+  int best_s = 1;
+  double best_cost = 1e300;
+  const int max_s = pl.n_ptiles < 16 ? pl.n_ptiles : 16;
+  for (int s = 1; s <= max_s; ++s) {
+    double waves = (double)ceil_div64((int64_t)pl.n_qtiles * s, num_sms);
+    double tiles = (double)ceil_div64(pl.n_ptiles, s) + 1.0;  // +1: pipeline fill per unit
+    double cost = waves * tiles * (1.0 + 0.004 * s);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_s = s;
+    }
+  }
+  pl.n_seg = best_s;
+  pl.n_units = pl.n_qtiles * pl.n_seg;
+  pl.grid = pl.n_units < num_sms ? pl.n_units : num_sms;
+  pl.cap = 64 * k < 256 ? 256 : 64 * k;
+  return pl;
+}
+
+int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
+                      const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
+                      cudaStream_t stream) {
+  KNN_CHECK_ARG(dim_pad % BK == 0 && dim_pad > 0, -3, "dim_pad %d must be a positive multiple of %d", dim_pad, BK);
+  KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -3, "k=%d outside [1,%d]", k, kMaxK);
+  KNN_CHECK_ARG(n_pool < (int64_t)1 << 31, -3, "pool shard of %lld rows exceeds int32 column indices", (long long)n_pool);
+  CUtensorMap map_q, map_p;
+  int rc = make_half_map(&map_q, qh, n_query, dim_pad, BM);
+  if (rc) return rc;
+  rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  knn_filter_kernel<<<pl.grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_q, map_p, n_query, n_pool, dim_pad / BK, k,
+                                                                  pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val,
+                                                                  log_idx, log_cnt, seg_top);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace knnsvc

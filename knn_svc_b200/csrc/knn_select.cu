@@ -1,0 +1,203 @@
+// Exact re-scoring of the tensor-core filter's candidate log, and the top-k
+// merge used after the NCCL all-gather of per-shard results (C1).
+//
+// knn_rescore: one CTA per query row.
+//   1. tau* = k-th largest approximate similarity over the row's per-segment
+//      top-k lists; every true top-k member has s~ >= tau* - 2*eps.
+//   2. survivors = logged candidates with s~ >= tau* - 2*eps.
+//   3. each survivor is re-scored from the fp32 rows with fp64 accumulation:
+//      dist = 1 - q.p/(|q||p|)   (lib_ongaku_test.py:162-165).
+//   4. survivors are ranked by (dist, index) and the first k written, ascending —
+//      the order dists.topk(k, largest=False) returns (ddsp_prematch_dataset.py:1203).
+// Rows whose log overflowed, or with more than RS_MAXSURV survivors (massive
+// ties), are appended to the flag list for the exact brute-force kernel.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+constexpr int RS_THREADS = 128;
+constexpr int RS_MAXSURV = 512;
+constexpr int RS_MAXTOP = 16 * kMaxK;  // n_seg <= 16
+
+__global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
+    const float* __restrict__ q, const float* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
+    const float* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
+    const float* __restrict__ log_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
+    const float* __restrict__ seg_top, int64_t index_offset, float* __restrict__ out_dist,
+    int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list, int* __restrict__ flag_count,
+    int* __restrict__ stats) {
+  extern __shared__ __align__(16) float s_q[];  // [dim]
+  __shared__ float s_top[RS_MAXTOP];
+  __shared__ int s_surv_idx[RS_MAXSURV];
+  __shared__ double s_surv_d[RS_MAXSURV];
+  __shared__ int s_nsurv, s_overflow, s_logged;
+  __shared__ float s_thr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int64_t row = blockIdx.x; row < n_query; row += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      s_nsurv = 0;
+      s_overflow = 0;
+      s_logged = 0;
+      s_thr = -INFINITY;
+    }
+    const int n_top = n_seg * k;
+    for (int e = tid; e < n_top; e += RS_THREADS) s_top[e] = seg_top[row * n_top + e];
+    for (int c = tid; c < dim; c += RS_THREADS) s_q[c] = __ldg(q + row * dim + c);
+    __syncthreads();
+    // k-th largest of the union of the segment lists (rank counting, ties by position)
+    for (int e = tid; e < n_top; e += RS_THREADS) {
+      const float v = s_top[e];
+      int rank = 0;
+      for (int j = 0; j < n_top; ++j) {
+        const float o = s_top[j];
+        rank += (o > v) || (o == v && j < e);
+      }
+      if (rank == k - 1) s_thr = v - 2.0f * kFilterEps;
+    }
+    for (int s = tid; s < n_seg; s += RS_THREADS) {
+      const int c = log_cnt[row * n_seg + s];
+      if (c > cap) s_overflow = 1;
+      atomicAdd(&s_logged, c > cap ? cap : c);
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t slot = row * n_seg + s;
+      int c = log_cnt[slot];
+      c = c > cap ? cap : c;
+      for (int e = tid; e < c; e += RS_THREADS) {
+        if (log_val[slot * cap + e] >= thr) {
+          const int pos = atomicAdd(&s_nsurv, 1);
+          if (pos < RS_MAXSURV) s_surv_idx[pos] = log_idx[slot * cap + e];
+        }
+      }
+    }
+    __syncthreads();
+    const int nsurv = s_nsurv;
+    if (tid == 0 && stats) {
+      atomicAdd(stats + 1, s_logged);
+      atomicAdd(stats + 2, nsurv);
+    }
+    if (s_overflow || nsurv > RS_MAXSURV) {
+      if (tid == 0) {
+        const int pos = atomicAdd(flag_count, 1);
+        if (pos < kFlagCap) flag_list[pos] = row;
+        if (stats) atomicAdd(stats + 0, 1);
+      }
+      continue;
+    }
+    const double qnorm = (double)qn[row];
+    for (int e = warp; e < nsurv; e += RS_THREADS / 32) {
+      const int64_t pr = s_surv_idx[e];
+      const float* prow = p + pr * dim;
+      double acc = 0.0;
+      if ((dim & 3) == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(prow);
+        const float4* q4 = reinterpret_cast<const float4*>(s_q);
+        for (int c = lane; c < dim / 4; c += 32) {
+          const float4 a = __ldg(p4 + c);
+          const float4 b = q4[c];
+          acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+        }
+      } else {
+        for (int c = lane; c < dim; c += 32) acc += (double)__ldg(prow + c) * (double)s_q[c];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_surv_d[e] = 1.0 - acc / (qnorm * (double)pn[pr]);
+    }
+    __syncthreads();
+    for (int e = tid; e < nsurv; e += RS_THREADS) {
+      const double d = s_surv_d[e];
+      const int i = s_surv_idx[e];
+      int rank = 0;
+      for (int j = 0; j < nsurv; ++j) {
+        const double dj = s_surv_d[j];
+        rank += (dj < d) || (dj == d && s_surv_idx[j] < i);
+      }
+      if (rank < k) {
+        out_dist[row * k + rank] = (float)d;
+        out_idx[row * k + rank] = (int64_t)i + index_offset;
+      }
+    }
+    for (int o = nsurv + tid; o < k; o += RS_THREADS) {  // pool smaller than k
+      out_dist[row * k + o] = INFINITY;
+      out_idx[row * k + o] = -1;
+    }
+  }
+}
+
+int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+                       int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
+                       const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
+                       float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
+                       cudaStream_t stream) {
+  if (n_query == 0) return 0;
+  KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
+  int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
+  size_t smem = (size_t)dim * sizeof(float);
+  KNN_CHECK_ARG(smem <= 40 * 1024, -3, "dim %d too large for the rescoring kernel", dim);
+  knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
+                                                                   pl.cap, log_val, log_idx, log_cnt, seg_top,
+                                                                   index_offset, out_dist, out_idx, flag_list,
+                                                                   flag_count, stats);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- merge_topk (C1)
+// One warp per query row; n_shards*k <= 512 entries staged in shared memory and
+// ranked by (dist, idx).  Exact ties resolve to the lower global index, so the
+// result is independent of how the pool was sharded.
+constexpr int MG_WARPS = 4;
+constexpr int MG_MAX = 512;
+
+__global__ void __launch_bounds__(MG_WARPS * 32) merge_topk_kernel(const float* __restrict__ gd,
+                                                                   const int64_t* __restrict__ gi, int n_shards,
+                                                                   int64_t n_query, int k, float* __restrict__ out_dist,
+                                                                   int64_t* __restrict__ out_idx) {
+  __shared__ float sd[MG_WARPS][MG_MAX];
+  __shared__ int64_t si[MG_WARPS][MG_MAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = n_shards * k;
+  for (int64_t row = (int64_t)blockIdx.x * MG_WARPS + warp; row < n_query; row += (int64_t)gridDim.x * MG_WARPS) {
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const int s = e / k, j = e % k;
+      sd[warp][e] = gd[((int64_t)s * n_query + row) * k + j];
+      si[warp][e] = gi[((int64_t)s * n_query + row) * k + j];
+    }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const float d = sd[warp][e];
+      const int64_t i = si[warp][e];
+      if (i < 0) continue;  // padding of a shard smaller than k
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float dj = sd[warp][j];
+        const int64_t ij = si[warp][j];
+        rank += (ij >= 0) && ((dj < d) || (dj == d && ij < i));
+      }
+      if (rank < k) {
+        out_dist[row * k + rank] = d;
+        out_idx[row * k + rank] = i;
+      }
+    }
+  }
+}
+
+int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
+                      int64_t* out_idx, cudaStream_t stream) {
+  if (n_query == 0) return 0;
+  KNN_CHECK_ARG(n_shards >= 1 && n_shards * k <= MG_MAX, -3, "merge_topk: n_shards*k=%d exceeds %d", n_shards * k,
+                MG_MAX);
+  int64_t grid = ceil_div64(n_query, MG_WARPS);
+  if (grid > 148 * 16) grid = 148 * 16;
+  merge_topk_kernel<<<(unsigned)grid, MG_WARPS * 32, 0, stream>>>(gd, gi, n_shards, n_query, k, out_dist, out_idx);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace knnsvc

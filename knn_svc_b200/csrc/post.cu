@@ -1,0 +1,270 @@
+// K3 gather + weighted mix, K4 f0 re-rank, K5 greedy concatenation-cost re-selection.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+// ------------------------------------------------------------------ K3 gather_mix
+// out[t,:] = sum_k w[t,k] * pool[idx[t,k],:]   (w == nullptr -> 1/K each)
+// ddsp_prematch_dataset.py:1348,1358,1364 (features), :1435,1444,1446 (harmonics),
+// ddsp_matcher.py:578.  HBM-bound: K row reads + one row write per query frame.
+// One thread per 4 output columns (float4) when the row length allows it, K
+// independent 16-byte loads in flight per thread.
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_mix_kernel(const float* __restrict__ pool, int64_t n_pool, int dim,
+                                                         const int64_t* __restrict__ idx,
+                                                         const float* __restrict__ weights, int64_t n_query, int k,
+                                                         float* __restrict__ out) {
+  const int per_row = VEC ? dim / 4 : dim;
+  const int64_t total = n_query * per_row;
+  const float uniform = 1.0f / (float)k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = e / per_row;
+    const int c = (int)(e % per_row);
+    if (VEC) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < k; ++j) {
+        int64_t r = __ldg(idx + t * k + j);
+        r = r < 0 ? 0 : (r >= n_pool ? n_pool - 1 : r);
+        const float w = weights ? __ldg(weights + t * k + j) : uniform;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pool + r * dim) + c);
+        acc.x = fmaf(w, v.x, acc.x);
+        acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z);
+        acc.w = fmaf(w, v.w, acc.w);
+      }
+      reinterpret_cast<float4*>(out + t * dim)[c] = acc;
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) {
+        int64_t r = __ldg(idx + t * k + j);
+        r = r < 0 ? 0 : (r >= n_pool ? n_pool - 1 : r);
+        const float w = weights ? __ldg(weights + t * k + j) : uniform;
+        acc = fmaf(w, __ldg(pool + r * dim + c), acc);
+      }
+      out[t * dim + c] = acc;
+    }
+  }
+}
+
+int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,
+                      int64_t n_query, int k, float* out, cudaStream_t stream) {
+  if (n_query == 0 || dim == 0) return 0;
+  const bool vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(pool) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int64_t total = n_query * (vec ? dim / 4 : dim);
+  int64_t grid = ceil_div64(total, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  if (vec)
+    gather_mix_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(pool, n_pool, dim, idx, weights, n_query, k, out);
+  else
+    gather_mix_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(pool, n_pool, dim, idx, weights, n_query, k, out);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ K4 f0 re-rank
+// sort_by_f0_compatibility (ddsp_prematch_dataset.py:954-997): key =
+// |log2(f0[idx]+1e-5) - log2(expected+1e-5)| in fp32, stable ascending sort of the
+// k <= 32 candidates of a row.  One warp per row, one candidate per lane; the
+// stable rank is a count over the warp (a 32-wide sorting network by shuffles).
+__global__ void __launch_bounds__(256) f0_rerank_kernel(const float* __restrict__ expected_f0,
+                                                        const float* __restrict__ pool_f0,
+                                                        const int64_t* __restrict__ idx, int64_t n_query, int k,
+                                                        int64_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = warp; t < n_query; t += nwarps) {
+    const float e = log2f(__ldg(expected_f0 + t) + 1e-5f);
+    int64_t my = -1;
+    float key = INFINITY;
+    if (lane < k) {
+      my = __ldg(idx + t * k + lane);
+      key = fabsf(log2f(__ldg(pool_f0 + my) + 1e-5f) - e);
+    }
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float kj = __shfl_sync(0xffffffffu, key, j);
+      rank += (j < k) && ((kj < key) || (kj == key && j < lane));
+    }
+    if (lane < k) out_idx[t * k + rank] = my;
+  }
+}
+
+int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx, int64_t n_query, int k,
+                     int64_t* out_idx, cudaStream_t stream) {
+  if (n_query == 0) return 0;
+  KNN_CHECK_ARG(k >= 1 && k <= 32, -3, "f0_rerank: k=%d outside [1,32]", k);
+  int64_t grid = ceil_div64(n_query, 8);
+  if (grid > 148 * 16) grid = 148 * 16;
+  f0_rerank_kernel<<<(unsigned)grid, 256, 0, stream>>>(expected_f0, pool_f0, idx, n_query, k, out_idx);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ K5 greedy re-selection
+// knn_with_concat_cost (lib_ongaku_test.py:270-369), K = 4.  The recurrence is
+// serial in the frame index (frame i's candidates include "previous selection + 1"),
+// so one CTA walks one utterance; parallelism is inside a step — 8 warps, one
+// candidate row each, 5 direct-form cosine distances per candidate plus the
+// frame-to-frame baseline — and across utterances (one CTA each).
+//
+// Distances follow the reference's small-matrix path: cdist evaluates
+// sum((x-y)^2) directly, dot = (-d2 + |x|^2 + |y|^2)/2,
+// dist = 1 - dot/(|x||y|); accumulated in fp64.
+constexpr int CC_K = 4;
+constexpr int CC_C = 2 * CC_K;
+
+struct Dist3 {
+  double d2, nx, ny;
+};
+
+__device__ __forceinline__ double cosd_from(double d2, double nx2, double ny2) {
+  const double dot = (-d2 + nx2 + ny2) * 0.5;
+  return 1.0 - dot / (sqrt(nx2) * sqrt(ny2));
+}
+
+__global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
+    const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
+    int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
+    const int64_t* __restrict__ utt_offsets, int64_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
+  if (f_end <= f_begin) return;
+  const bool use_f0 = src_f0 != nullptr;
+
+  __shared__ int64_t s_prev[CC_K];
+  __shared__ int64_t s_cand[CC_C];
+  __shared__ double s_match[CC_C];
+  __shared__ double s_concat[CC_K][CC_C];
+  __shared__ double s_base;
+  __shared__ double s_w;
+
+  if (threadIdx.x < CC_K) {
+    const int64_t v = idx[f_begin * CC_K + threadIdx.x];
+    s_prev[threadIdx.x] = v;
+    out_idx[f_begin * CC_K + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) s_w = (double)concat_weight;
+  __syncthreads();
+
+  for (int64_t i = f_begin + 1; i < f_end; ++i) {
+    if (threadIdx.x < CC_C) {
+      int64_t c;
+      if (threadIdx.x < CC_K) {
+        c = idx[i * CC_K + threadIdx.x];
+      } else {
+        c = s_prev[threadIdx.x - CC_K] + 1;
+        if (c >= n_pool) c = n_pool - 1;
+      }
+      s_cand[threadIdx.x] = c;
+    }
+    __syncthreads();
+    {
+      // warp w scores candidate w against the query frame and the 4 previous selections
+      const float* crow = pool + s_cand[warp] * dim;
+      const float* srow = src + i * dim;
+      const float* p0 = pool + s_prev[0] * dim;
+      const float* p1 = pool + s_prev[1] * dim;
+      const float* p2 = pool + s_prev[2] * dim;
+      const float* p3 = pool + s_prev[3] * dim;
+      double nc = 0, ns = 0, dm = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+      for (int c = lane; c < dim; c += 32) {
+        const double cv = (double)__ldg(crow + c);
+        const double sv = (double)__ldg(srow + c);
+        const double a0 = (double)__ldg(p0 + c), a1 = (double)__ldg(p1 + c);
+        const double a2 = (double)__ldg(p2 + c), a3 = (double)__ldg(p3 + c);
+        nc += cv * cv;
+        ns += sv * sv;
+        dm += (sv - cv) * (sv - cv);
+        n0 += a0 * a0; d0 += (a0 - cv) * (a0 - cv);
+        n1 += a1 * a1; d1 += (a1 - cv) * (a1 - cv);
+        n2 += a2 * a2; d2 += (a2 - cv) * (a2 - cv);
+        n3 += a3 * a3; d3 += (a3 - cv) * (a3 - cv);
+      }
+      nc = warp_sum(nc); ns = warp_sum(ns); dm = warp_sum(dm);
+      n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2); n3 = warp_sum(n3);
+      d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+      if (lane == 0) {
+        s_match[warp] = cosd_from(dm, ns, nc);
+        s_concat[0][warp] = cosd_from(d0, n0, nc);
+        s_concat[1][warp] = cosd_from(d1, n1, nc);
+        s_concat[2][warp] = cosd_from(d2, n2, nc);
+        s_concat[3][warp] = cosd_from(d3, n3, nc);
+      }
+      if (warp == 0) {
+        // src_concat_baseline = 2 * dist(src[i-1], src[i])   (lib_ongaku_test.py:310)
+        const float* prow = src + (i - 1) * dim;
+        double na = 0, nb = 0, dd = 0;
+        for (int c = lane; c < dim; c += 32) {
+          const double a = (double)__ldg(prow + c), b = (double)__ldg(srow + c);
+          na += a * a;
+          nb += b * b;
+          dd += (a - b) * (a - b);
+        }
+        na = warp_sum(na); nb = warp_sum(nb); dd = warp_sum(dd);
+        if (lane == 0) s_base = 2.0 * cosd_from(dd, na, nb);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double base = s_base;
+      double w = s_w;
+      if (use_f0 && !(base < 0.08)) w = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
+      double total = INFINITY;
+      if (lane < CC_C) {
+        double cc[CC_K];
+#pragma unroll
+        for (int j = 0; j < CC_K; ++j) cc[j] = s_concat[j][lane];
+        if (use_f0) {
+          if (base < 0.08) {
+#pragma unroll
+            for (int j = 0; j < CC_K; ++j)
+              if (cc[j] < 5.0 * base) cc[j] = 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CC_K; ++j)
+            if (cc[j] > base) cc[j] = 1.5 * cc[j] - base;
+        }
+        // lower median of 4 = second smallest (torch.median, lib_ongaku_test.py:337,342)
+        double lo01 = fmin(cc[0], cc[1]), hi01 = fmax(cc[0], cc[1]);
+        double lo23 = fmin(cc[2], cc[3]), hi23 = fmax(cc[2], cc[3]);
+        double med = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+        total = w * med + s_match[lane];
+        if (use_f0) {
+          const double lc = log2((double)__ldg(pool_f0 + s_cand[lane]) + 1e-5);
+          const double ls = log2((double)__ldg(src_f0 + i) + 1e-5);
+          total += fabs(lc - ls);
+        }
+      }
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < CC_C; ++j) {
+        const double tj = __shfl_sync(0xffffffffu, total, j);
+        rank += (tj < total) || (tj == total && j < lane);
+      }
+      if (lane < CC_C && rank < CC_K) {
+        const int64_t sel = s_cand[lane];
+        out_idx[i * CC_K + rank] = sel;
+        s_prev[rank] = sel;
+      }
+      if (lane == 0) s_w = w;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+                       const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
+                       int n_utt, int64_t* out_idx, cudaStream_t stream) {
+  if (n_utt == 0) return 0;
+  concat_cost_kernel<<<n_utt, CC_C * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
+                                                      utt_offsets_dev, out_idx);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace knnsvc

@@ -1,0 +1,298 @@
+// K6: Adam(amsgrad) fit of per-frame softmax mixing weights —
+// compute_wavlm_weight (ddsp_prematch_dataset.py:574-680, loss scale 0.1) and
+// compute_extended_weight (:807-924, loss scale 1000; its scaling_factors are inert).
+//
+// The reference re-gathers 3x[T,4,D] rows and runs autograd every iteration.
+// The loss is quadratic in the softmax weights w:
+//   L = c/((T-1)D) * sum_t u_t' G_t u_t,   u_t = (w[t+1,:], -w[t,:])  in R^8,
+//   G_t = Gram{S_-1[t+1,k], S_0[t,k]} + Gram{S_0[t+1,k], S_+1[t,k]},  S_i = synth[clamp(idx+i)]
+// so the 8x8 Gram blocks are built ONCE (fp64, HBM-bound gather: 3*K*D*4 bytes
+// per frame) and the whole optimisation loop then runs inside one persistent
+// CTA on [T,4] state with the analytic gradient.  Logits and Adam moments are
+// fp32 and the update is torch.optim.Adam(amsgrad=True)'s single-tensor form;
+// the loss and dL/dw are fp64 and cast to fp32 at w, as on the reference's real
+// (float64) path.  Stop rules: ddsp_prematch_dataset.py:644-663.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+constexpr int WF_K = 4;
+constexpr int WF_V = 2 * WF_K;         // vectors per Gram block
+constexpr int WF_THREADS = 1024;
+constexpr int WF_SMEM_FRAMES = 10240;  // frames whose weights fit in shared memory
+
+// ---- Gram build: one CTA per frame pair t (frames t, t+1); warp i owns row i of both blocks
+__global__ void __launch_bounds__(WF_V * 32) weight_gram_kernel(const int64_t* __restrict__ idx,
+                                                                const float* __restrict__ synth, int64_t n_pool,
+                                                                int dim, int64_t n_query, double* __restrict__ gram) {
+  const int64_t t = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int64_t rows[2][WF_V];
+  if (threadIdx.x < WF_V) {
+    const int j = threadIdx.x;
+    const int64_t base = (j < WF_K) ? idx[(t + 1) * WF_K + j] : idx[t * WF_K + (j - WF_K)];
+    // block 0: (S_-1[t+1], S_0[t]); block 1: (S_0[t+1], S_+1[t])
+    int64_t r0 = base + ((j < WF_K) ? -1 : 0);
+    int64_t r1 = base + ((j < WF_K) ? 0 : 1);
+    r0 = r0 < 0 ? 0 : (r0 >= n_pool ? n_pool - 1 : r0);
+    r1 = r1 < 0 ? 0 : (r1 >= n_pool ? n_pool - 1 : r1);
+    rows[0][j] = r0;
+    rows[1][j] = r1;
+  }
+  __syncthreads();
+  double acc[WF_V];
+#pragma unroll
+  for (int j = 0; j < WF_V; ++j) acc[j] = 0.0;
+  for (int b = 0; b < 2; ++b) {
+    const float* mine = synth + rows[b][warp] * dim;
+    for (int c = lane; c < dim; c += 32) {
+      const double a = (double)__ldg(mine + c);
+#pragma unroll
+      for (int j = 0; j < WF_V; ++j) acc[j] += a * (double)__ldg(synth + rows[b][j] * dim + c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < WF_V; ++j) {
+    const double v = warp_sum(acc[j]);
+    if (lane == 0) gram[(t * WF_V + warp) * WF_V + j] = v;
+  }
+}
+
+struct WfState {
+  float* theta;
+  float* m;
+  float* v;
+  float* vmax;
+  float* best;
+  float* wglob;  // [T,4] softmax weights when they do not fit in shared memory
+};
+
+__device__ __forceinline__ void softmax4(const float* th, float* w) {
+  const float mx = fmaxf(fmaxf(th[0], th[1]), fmaxf(th[2], th[3]));
+  float e[4], s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e[k] = expf(th[k] - mx);
+    s += e[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = e[k] / s;
+}
+
+__global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double* __restrict__ gram, int64_t n_query,
+                                                                   int dim, double loss_scale, int max_iters,
+                                                                   WfState st, int use_smem,
+                                                                   float* __restrict__ out_weights,
+                                                                   double* __restrict__ info) {
+  extern __shared__ __align__(16) float s_w_dyn[];
+  __shared__ double s_red[WF_THREADS / 32];
+  __shared__ double s_loss;
+  __shared__ int s_ctl;  // bit0: stop, bit1: snapshot
+  volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t T = n_query;
+  const double norm = loss_scale / ((double)(T - 1) * (double)dim);
+  const float lr = 0.1f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+
+  for (int64_t t = tid; t < T; t += WF_THREADS)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st.theta[t * 4 + k] = 0.f;
+      st.m[t * 4 + k] = 0.f;
+      st.v[t * 4 + k] = 0.f;
+      st.vmax[t * 4 + k] = 0.f;
+      st.best[t * 4 + k] = 0.f;
+    }
+  double min_loss = 20000.0, converge_min_loss = 20000.0, first_loss = 0.0;
+  int since_improve = 0, stop_iter = max_iters;
+  __syncthreads();
+
+  for (int it = 0; it < max_iters; ++it) {
+    // ---- w = softmax(theta)
+    for (int64_t t = tid; t < T; t += WF_THREADS) {
+      float th[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) th[k] = st.theta[t * 4 + k];
+      softmax4(th, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wbuf[t * 4 + k] = w[k];
+    }
+    __syncthreads();
+    // ---- loss and dL/dw from the Gram blocks (kept in registers until the step)
+    double part = 0.0;
+    for (int64_t t = tid; t < T; t += WF_THREADS) {
+      double wt[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wt[k] = (double)wbuf[t * 4 + k];
+      double g[4] = {0.0, 0.0, 0.0, 0.0};
+      if (t >= 1) {  // pair t-1: this frame is the "t+1" member, rows 0..3 of G u
+        const double* G = gram + (t - 1) * WF_V * WF_V;
+        double u[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          u[k] = wt[k];
+          u[4 + k] = -(double)wbuf[(t - 1) * 4 + k];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          double y = 0.0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y += G[r * 8 + c] * u[c];
+          part += wt[r] * y;
+          g[r] += y;
+        }
+      }
+      if (t + 1 < T) {  // pair t: this frame is the "t" member, rows 4..7 of G u
+        const double* G = gram + t * WF_V * WF_V;
+        double u[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          u[k] = (double)wbuf[(t + 1) * 4 + k];
+          u[4 + k] = -wt[k];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          double y = 0.0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y += G[(4 + r) * 8 + c] * u[c];
+          part -= wt[r] * y;
+          g[r] -= y;
+        }
+      }
+      // gradient wrt w, cast to fp32 where the fp64 graph meets the fp32 softmax output
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st.best[T * 4 + t * 4 + k] = (float)(2.0 * norm * g[k]);  // scratch after best[T*4]
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < WF_THREADS / 32; ++w) s += s_red[w];
+      const double loss = s * norm;
+      if (it == 0) first_loss = loss;
+      int ctl = 0;
+      if (it % 100 == 1) {
+        if (fabs(min_loss - converge_min_loss) < 1e-5) ctl |= 1;
+        else converge_min_loss = min_loss;
+      }
+      if (!(ctl & 1)) {
+        if (loss < min_loss) {
+          min_loss = loss;
+          ctl |= 2;
+          since_improve = 0;
+        } else {
+          ++since_improve;
+        }
+        if (since_improve >= 1000) ctl |= 1;
+      }
+      if (ctl & 1) stop_iter = it;
+      s_ctl = ctl;
+      s_loss = loss;
+    }
+    __syncthreads();
+    const int ctl = s_ctl;
+    if (ctl & 2)
+      for (int64_t t = tid; t < T; t += WF_THREADS)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st.best[t * 4 + k] = st.theta[t * 4 + k];
+    if (ctl & 1) break;
+    // ---- Adam (amsgrad) step on the logits
+    const int step = it + 1;
+    const double bc1 = 1.0 - pow((double)0.9, (double)step);
+    const double bc2 = 1.0 - pow((double)0.999, (double)step);
+    const float step_size = (float)((double)0.1 / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    (void)lr;
+    for (int64_t t = tid; t < T; t += WF_THREADS) {
+      float w[4], gw[4];
+      float dotgw = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = wbuf[t * 4 + k];
+        gw[k] = st.best[T * 4 + t * 4 + k];
+        dotgw += gw[k] * w[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gth = w[k] * (gw[k] - dotgw);  // softmax backward
+        float m = st.m[t * 4 + k], v = st.v[t * 4 + k], vm = st.vmax[t * 4 + k];
+        m = m + (gth - m) * (1.0f - b1);
+        v = v * b2 + (1.0f - b2) * gth * gth;
+        vm = fmaxf(vm, v);
+        const float denom = sqrtf(vm) / bc2_sqrt + eps;
+        st.theta[t * 4 + k] = st.theta[t * 4 + k] - step_size * (m / denom);
+        st.m[t * 4 + k] = m;
+        st.v[t * 4 + k] = v;
+        st.vmax[t * 4 + k] = vm;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int64_t t = tid; t < T; t += WF_THREADS) {
+    float th[4], w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) th[k] = st.best[t * 4 + k];
+    softmax4(th, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out_weights[t * 4 + k] = w[k];
+  }
+  if (tid == 0 && info) {
+    info[0] = (double)stop_iter;
+    info[1] = min_loss;
+    info[2] = first_loss;
+    info[3] = s_loss;
+  }
+}
+
+__global__ void uniform_weights_kernel(float* w, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = v;
+}
+
+size_t weight_fit_workspace_bytes(int64_t n_query, int k) {
+  if (n_query < 2) return 256;
+  size_t gram = (size_t)(n_query - 1) * WF_V * WF_V * sizeof(double);
+  size_t state = (size_t)n_query * k * sizeof(float) * 7;  // theta, m, v, vmax, best, grad scratch, wglob
+  return gram + state + 1024;
+}
+
+int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
+                      double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
+                      cudaStream_t stream) {
+  KNN_CHECK_ARG(k == WF_K, -3, "weight_fit: k=%d, only k=%d is on the reference path", k, WF_K);
+  if (n_query == 0) return 0;
+  if (n_query < 2) {
+    uniform_weights_kernel<<<1, 32, 0, stream>>>(out_weights, n_query * k, 1.0f / k);
+    KNN_LAUNCH_CHECK();
+    return 0;
+  }
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  double* gram = reinterpret_cast<double*>(ws);
+  float* f = reinterpret_cast<float*>(ws + (size_t)(n_query - 1) * WF_V * WF_V * sizeof(double));
+  WfState st;
+  const size_t n4 = (size_t)n_query * 4;
+  st.theta = f;
+  st.m = f + n4;
+  st.v = f + 2 * n4;
+  st.vmax = f + 3 * n4;
+  st.best = f + 4 * n4;  // followed by the gradient scratch at best + n4
+  st.wglob = f + 6 * n4;
+  weight_gram_kernel<<<(unsigned)(n_query - 1), WF_V * 32, 0, stream>>>(idx, synth, n_pool, dim, n_query, gram);
+  KNN_LAUNCH_CHECK();
+  const int use_smem = n_query <= WF_SMEM_FRAMES;
+  const size_t smem = use_smem ? n4 * sizeof(float) : 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
+    attr_done = true;
+  }
+  weight_fit_kernel<<<1, WF_THREADS, smem, stream>>>(gram, n_query, dim, loss_scale, max_iters, st, use_smem,
+                                                     out_weights, info);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace knnsvc

@@ -1,0 +1,272 @@
+"""Tensor-level ops: torch tensors in, C-ABI call on the current CUDA stream,
+torch tensors out.  PyTorch is used for device memory and streams only; all
+arithmetic happens in libknnsvc_b200.so.  Every op requires CUDA tensors and
+raises otherwise — there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+MAX_K = 32
+_HALF_ALIGN = 64   # the tcgen05 filter consumes the feature dimension in 64-element slabs
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: knn_svc_b200 has no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 contiguous view/copy.  float64 inputs (the reference's real inference
+    path) hold fp32-representable values, so the cast is lossless there."""
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def _i64c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class PreparedRows:
+    """A [n, dim] fp32 row set with its norms and the fp16 tensor-core operand."""
+    rows: torch.Tensor      # [n, dim] fp32
+    half: torch.Tensor      # [n, dim_pad] fp16 = fp16(rows * 1024/|row|)
+    norms: torch.Tensor     # [n] fp32
+
+    @property
+    def n(self) -> int:
+        return self.rows.shape[0]
+
+    @property
+    def dim(self) -> int:
+        return self.rows.shape[1]
+
+    @property
+    def dim_pad(self) -> int:
+        return self.half.shape[1]
+
+
+def prepare_rows(x: torch.Tensor, check: bool = True) -> PreparedRows:
+    """Row norms + unit-normalised fp16 copy (replaces torch.norm at
+    lib_ongaku_test.py:150-151).  A zero-norm or non-finite row is an error: the
+    reference produces NaN distances there and exits (lib_ongaku_test.py:166-169)."""
+    _dev(x, "rows")
+    if x.dim() != 2:
+        raise ValueError(f"expected [n, dim] rows, got shape {tuple(x.shape)}")
+    x = _f32c(x)
+    n, dim = x.shape
+    dim_pad = (dim + _HALF_ALIGN - 1) // _HALF_ALIGN * _HALF_ALIGN
+    half = torch.empty((n, dim_pad), dtype=torch.float16, device=x.device)
+    norms = torch.empty((n,), dtype=torch.float32, device=x.device)
+    bad = torch.zeros((1,), dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.knnsvc_prepare_rows(x.data_ptr(), n, dim, dim, half.data_ptr(), dim_pad, norms.data_ptr(),
+                                           bad.data_ptr(), _stream()), "prepare_rows")
+    if check and n > 0 and int(bad.item()) != 0:
+        raise ValueError(f"{int(bad.item())} zero-norm or non-finite feature rows: cosine distance undefined "
+                         "(the reference exits with 'containing nan')")
+    return PreparedRows(x, half, norms)
+
+
+def cosine_dist(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """Full [T, Np] cosine-distance matrix (fast_cosine_dist's return value)."""
+    _dev(q, "source_feats"); _dev(p, "matching_pool")
+    q, p = _f32c(q), _f32c(p)
+    if q.shape[1] != p.shape[1]:
+        raise ValueError("feature dimensions differ")
+    out = torch.empty((q.shape[0], p.shape[0]), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        _lib.check(lib.knnsvc_cosine_dist(q.data_ptr(), q.shape[0], p.data_ptr(), p.shape[0], q.shape[1],
+                                          out.data_ptr(), _stream()), "cosine_dist")
+    return out
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (the library never allocates)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0,
+               return_stats: bool = False):
+    """k smallest cosine distances per query row, ascending, with int64 pool
+    indices — the fused replacement of fast_cosine_dist + topk
+    (ddsp_prematch_dataset.py:1196-1206, ddsp_matcher.py:550-554)."""
+    if not (1 <= k <= MAX_K):
+        raise ValueError(f"k={k} outside [1,{MAX_K}]")
+    if k > pool.n:
+        raise ValueError(f"k={k} exceeds the pool size {pool.n}")
+    if query.dim != pool.dim:
+        raise ValueError("feature dimensions differ")
+    dev = query.rows.device
+    T = query.n
+    dist = torch.empty((T, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((T, k), dtype=torch.int64, device=dev)
+    stats = torch.zeros((8,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    if T > 0:
+        with torch.cuda.device(dev):
+            nbytes = lib.knnsvc_knn_workspace_bytes(T, pool.n, query.dim_pad, k)
+            ws = _workspace(nbytes, dev)
+            _lib.check(lib.knnsvc_knn_search(query.rows.data_ptr(), query.half.data_ptr(), query.norms.data_ptr(), T,
+                                             pool.rows.data_ptr(), pool.half.data_ptr(), pool.norms.data_ptr(),
+                                             pool.n, query.dim, query.dim_pad, k, index_offset, dist.data_ptr(),
+                                             idx.data_ptr(), ws.data_ptr(), ws.numel(), stats.data_ptr(), _stream()),
+                       "knn_search")
+    if return_stats:
+        return dist, idx, stats
+    return dist, idx
+
+
+def knn_exact(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0):
+    """Exact CUDA-core kNN (fp64 accumulation); the decision procedure behind
+    knn_search for undecidable rows, exposed for tests."""
+    dev = query.rows.device
+    T = query.n
+    dist = torch.empty((T, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((T, k), dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    if T > 0:
+        with torch.cuda.device(dev):
+            nbytes = lib.knnsvc_knn_exact_workspace_bytes(T, pool.n, k)
+            ws = _workspace(nbytes, dev)
+            _lib.check(lib.knnsvc_knn_exact(query.rows.data_ptr(), query.norms.data_ptr(), T, pool.rows.data_ptr(),
+                                            pool.norms.data_ptr(), pool.n, query.dim, k, index_offset,
+                                            dist.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                       "knn_exact")
+    return dist, idx
+
+
+def merge_topk(gathered_dist: torch.Tensor, gathered_idx: torch.Tensor):
+    """[R, T, k] per-shard results -> [T, k] merged by (dist, idx) (C1)."""
+    _dev(gathered_dist, "gathered_dist")
+    R, T, k = gathered_dist.shape
+    gd, gi = _f32c(gathered_dist), _i64c(gathered_idx)
+    dist = torch.empty((T, k), dtype=torch.float32, device=gd.device)
+    idx = torch.empty((T, k), dtype=torch.int64, device=gd.device)
+    lib = _lib.load()
+    with torch.cuda.device(gd.device):
+        _lib.check(lib.knnsvc_merge_topk(gd.data_ptr(), gi.data_ptr(), R, T, k, dist.data_ptr(), idx.data_ptr(),
+                                         _stream()), "merge_topk")
+    return dist, idx
+
+
+def gather_mix(pool: torch.Tensor, idx: torch.Tensor, weights: torch.Tensor | None = None) -> torch.Tensor:
+    """out[t] = sum_k w[t,k] * pool[idx[t,k]]  (weights None -> mean)."""
+    _dev(pool, "pool"); _dev(idx, "indices")
+    pool, idx = _f32c(pool), _i64c(idx)
+    T, k = idx.shape
+    w = None if weights is None else _f32c(weights.to(pool.device))
+    out = torch.empty((T, pool.shape[1]), dtype=torch.float32, device=pool.device)
+    lib = _lib.load()
+    with torch.cuda.device(pool.device):
+        _lib.check(lib.knnsvc_gather_mix(pool.data_ptr(), pool.shape[0], pool.shape[1], idx.data_ptr(), _ptr(w), T, k,
+                                         out.data_ptr(), _stream()), "gather_mix")
+    return out
+
+
+def f0_rerank(expected_f0: torch.Tensor, pool_f0: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _dev(idx, "indices")
+    dev = idx.device
+    e, f, idx = _f32c(expected_f0.to(dev)), _f32c(pool_f0.to(dev)), _i64c(idx)
+    T, k = idx.shape
+    if e.shape[0] != T:
+        raise ValueError("expected_f0 and indices disagree on the number of frames")
+    out = torch.empty_like(idx)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.knnsvc_f0_rerank(e.data_ptr(), f.data_ptr(), idx.data_ptr(), T, k, out.data_ptr(), _stream()),
+                   "f0_rerank")
+    return out
+
+
+def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tensor,
+                         shifted_src_f0: torch.Tensor | None = None, pool_f0: torch.Tensor | None = None,
+                         concat_weight: float = 0.2, utt_offsets=None) -> torch.Tensor:
+    _dev(src, "src_elements"); _dev(pool, "tgt_elements")
+    dev = src.device
+    idx, src, pool = _i64c(idx.to(dev)), _f32c(src), _f32c(pool)
+    T, k = idx.shape
+    if k != 4:
+        raise ValueError("knn_with_concat_cost: the reference path keeps 4 candidates per frame")
+    if len(src) != T:
+        raise ValueError("indices and src_elements disagree on the number of frames")
+    sf = None if shifted_src_f0 is None else _f32c(shifted_src_f0.to(dev))
+    pf = None if pool_f0 is None else _f32c(pool_f0.to(dev))
+    offs = [0, T] if utt_offsets is None else [int(v) for v in utt_offsets]
+    import ctypes
+    arr = (ctypes.c_int64 * len(offs))(*offs)
+    out = torch.empty_like(idx)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.knnsvc_concat_cost_reselect(idx.data_ptr(), src.data_ptr(), pool.data_ptr(), pool.shape[0],
+                                                   pool.shape[1], _ptr(sf), _ptr(pf), float(concat_weight),
+                                                   ctypes.cast(arr, ctypes.c_void_p), len(offs) - 1, out.data_ptr(),
+                                                   _stream()), "concat_cost_reselect")
+    return out
+
+
+def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_iters: int = 100000,
+               return_info: bool = False):
+    _dev(synth, "synth_set")
+    dev = synth.device
+    idx, synth = _i64c(idx.to(dev)), _f32c(synth)
+    T, k = idx.shape
+    out = torch.empty((T, k), dtype=torch.float32, device=dev)
+    info = torch.zeros((4,), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    if T > 0:
+        with torch.cuda.device(dev):
+            nbytes = lib.knnsvc_weight_fit_workspace_bytes(T, k)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            _lib.check(lib.knnsvc_weight_fit(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1], T, k,
+                                             float(loss_scale), int(max_iters), out.data_ptr(), info.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()), "weight_fit")
+    if return_info:
+        return out, info
+    return out
+
+
+def harmonic_bank(f0: torch.Tensor, amp: torch.Tensor | None, sample_rate: int = 16000, hop: int = 320) -> torch.Tensor:
+    """f0 [B,T], amp [B,T,H] or None -> [B, T*hop] fp32."""
+    _dev(f0, "f0")
+    f0 = _f32c(f0)
+    B, T = f0.shape
+    H = 1
+    if amp is not None:
+        amp = _f32c(amp.to(f0.device))
+        if amp.shape[:2] != f0.shape:
+            raise ValueError("f0 and amp disagree on [batch, frames]")
+        H = amp.shape[2]
+    out = torch.empty((B, T * hop), dtype=torch.float32, device=f0.device)
+    ws = torch.empty((max(B * T, 1),), dtype=torch.float64, device=f0.device)
+    lib = _lib.load()
+    with torch.cuda.device(f0.device):
+        _lib.check(lib.knnsvc_harmonic_bank(f0.data_ptr(), _ptr(amp), B, T, H, int(sample_rate), int(hop),
+                                            out.data_ptr(), ws.data_ptr(), _stream()), "harmonic_bank")
+    return out

@@ -1,0 +1,106 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol,
+the host logic of the sharded exchange works over gloo with world_size 2, and
+the product refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from knn_svc_b200 import _lib
+    header = (ROOT / "include" / "knnsvc_b200.h").read_text()
+    declared = set(re.findall(r"\b(knnsvc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.knnsvc_version() >= 100
+    # pure host-side query, no GPU needed
+    assert lib.knnsvc_weight_fit_workspace_bytes(100, 4) > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    from knn_svc_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.prepare_rows(torch.randn(4, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.cosine_dist(torch.randn(4, 64), torch.randn(5, 64))
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "knn_svc_b200").glob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_shard_bounds_cover_pool():
+    from knn_svc_b200.sharded import shard_bounds
+    for n, w in ((10_000_000, 8), (1001, 3), (7, 8)):
+        edges = [shard_bounds(n, w, r) for r in range(w)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+
+
+def test_merge_rule_host_is_shard_invariant():
+    from knn_svc_b200.sharded import merge_topk_host, shard_bounds
+    rs = np.random.RandomState(0)
+    d = rs.rand(17, 400).astype(np.float32)
+    d[:, 100:120] = d[:, 50:51]            # exact ties across what will be different shards
+    full = torch.from_numpy(d)
+    k = 8
+    order = torch.argsort(full, dim=1, stable=True)[:, :k]
+    for world in (1, 2, 3, 8):
+        gd, gi = [], []
+        for r in range(world):
+            lo, hi = shard_bounds(400, world, r)
+            o = torch.argsort(full[:, lo:hi], dim=1, stable=True)[:, :k]
+            gd.append(torch.gather(full[:, lo:hi], 1, o)); gi.append(o + lo)
+        md, mi = merge_topk_host(torch.stack(gd), torch.stack(gi))
+        assert torch.equal(mi, order)
+        assert torch.equal(md, torch.gather(full, 1, order))
+
+
+WORKER = r"""
+import os, sys, torch, numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from knn_svc_b200.sharded import all_gather_topk, merge_topk_host, shard_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rs = np.random.RandomState(0)
+full = torch.from_numpy(rs.rand(23, 501).astype(np.float32))
+k = 4
+lo, hi = shard_bounds(501, world, rank)
+o = torch.argsort(full[:, lo:hi], dim=1, stable=True)[:, :k]
+ld, li = torch.gather(full[:, lo:hi], 1, o), o + lo
+gd, gi = all_gather_topk(ld, li)
+md, mi = merge_topk_host(gd, gi)
+want = torch.argsort(full, dim=1, stable=True)[:, :k]
+assert torch.equal(mi, want), (rank, mi[0], want[0])
+assert torch.equal(md, torch.gather(full, 1, want))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_exchange_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, REPO_ROOT=str(ROOT), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
