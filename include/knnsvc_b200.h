@@ -73,6 +73,16 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
                       float* out_dist, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, int* stats, void* stream);
 
+/* Measurement hooks used by bench.py (no effect on results).
+ *   knnsvc_launch_count            kernels this library has launched in this process
+ *   knnsvc_filter_timing(1/0)      bracket the tcgen05 filter launch of every later
+ *                                  knnsvc_knn_search with CUDA events on its stream
+ *   knnsvc_filter_timing_collect   host float[max_n] <- per-call filter durations (ms)
+ *                                  since the last collect; returns the count */
+long long knnsvc_launch_count(void);
+int knnsvc_filter_timing(int enable);
+int knnsvc_filter_timing_collect(float* ms_host, int max_n);
+
 /* Exact brute-force kNN on CUDA cores (same outputs as knnsvc_knn_search).
  * Used for rows the filter flags, and by tests as an independent GPU check. */
 size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k);

@@ -23,6 +23,9 @@ SIGNATURES = {
     "knnsvc_cosine_dist": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "knnsvc_knn_workspace_bytes": (sz, [i64, i64, i32, i32]),
     "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, sz, vp, vp]),
+    "knnsvc_launch_count": (C.c_longlong, []),
+    "knnsvc_filter_timing": (i32, [i32]),
+    "knnsvc_filter_timing_collect": (i32, [vp, i32]),
     "knnsvc_knn_exact_workspace_bytes": (sz, [i64, i64, i32]),
     "knnsvc_knn_exact": (i32, [vp, vp, i64, vp, vp, i64, i32, i32, i64, vp, vp, vp, sz, vp]),
     "knnsvc_merge_topk": (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),

@@ -1,6 +1,8 @@
 // extern "C" entry points declared in include/knnsvc_b200.h.
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/knnsvc_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
@@ -15,6 +17,17 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Optional device-side timing of the dominant kernel (the tcgen05 filter): when
+// enabled, knn_search brackets that one launch with CUDA events on its stream.
+constexpr int kTimingSlots = 256;
+static bool g_timing = false;
+static cudaEvent_t g_ev[kTimingSlots][2];
+static bool g_ev_made = false;
+static int g_ev_n = 0;
 
 namespace {
 
@@ -107,9 +120,15 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
   KnnWorkspace w = carve(workspace, n_query, n_pool, k, pl);
   KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
   KNN_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), stream));
+  const bool timed = g_timing && g_ev_n < kTimingSlots;
+  if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
                              stream);
   if (rc) return rc;
+  if (timed) {
+    KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));
+    ++g_ev_n;
+  }
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
                           index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, stream);
   if (rc) return rc;
@@ -122,6 +141,29 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
     KNN_LAUNCH_CHECK();
   }
   return 0;
+}
+
+long long knnsvc_launch_count(void) { return g_launches.load(); }
+
+int knnsvc_filter_timing(int enable) {
+  if (enable && !g_ev_made) {
+    for (int i = 0; i < kTimingSlots; ++i)
+      for (int j = 0; j < 2; ++j) KNN_CUDA(cudaEventCreate(&g_ev[i][j]));
+    g_ev_made = true;
+  }
+  g_timing = enable != 0;
+  g_ev_n = 0;
+  return 0;
+}
+
+int knnsvc_filter_timing_collect(float* ms_host, int max_n) {
+  int n = g_ev_n < max_n ? g_ev_n : max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(ms_host + i, g_ev[i][0], g_ev[i][1]) != cudaSuccess) return -1;
+  }
+  g_ev_n = 0;
+  return n;
 }
 
 size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k) {

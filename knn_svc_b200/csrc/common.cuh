@@ -28,7 +28,12 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
-#define KNN_LAUNCH_CHECK() KNN_CUDA(cudaGetLastError())
+void count_launch();
+#define KNN_LAUNCH_CHECK()            \
+  do {                                \
+    ::knnsvc::count_launch();         \
+    KNN_CUDA(cudaGetLastError());     \
+  } while (0)
 
 // fp16 operand scaling: unit-norm rows are multiplied by 2^10 before the fp16
 // cast so that small components stay out of the subnormal range; a dot product

@@ -1,0 +1,47 @@
+"""CPU baseline for bench.py: the reference's matcher loop re-stated with the
+SAME library calls the reference makes (torch on the host cores), timed on a
+bounded sample.  TEST/MEASUREMENT INFRASTRUCTURE ONLY — never on a product path.
+
+Follows ddsp_prematch_dataset.py:1196-1206 (chunk-20 fast_cosine_dist + topk(32),
+lib_ongaku_test.py:148-175), then `[:, :4]` and the gather-mean (:1246, :1348, :1364).
+kind = "port": /root/reference is not present on the GPU box, so the reference's
+own file cannot be imported there.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+
+def _cosine_dist_chunk(src, pool, pool_norms):
+    src_norms = torch.linalg.vector_norm(src, dim=-1)
+    d = torch.cdist(src[None], pool[None], p=2)[0]
+    dot = (-(d * d) + src_norms[:, None] ** 2 + pool_norms[None] ** 2) / 2
+    return 1 - dot / (src_norms[:, None] * pool_norms[None])
+
+
+def match_sample(query: torch.Tensor, pool: torch.Tensor, k_search: int = 32, k_mix: int = 4, increment: int = 20):
+    """One pass of the reference's matcher over `query` (CPU tensors)."""
+    pool_norms = torch.linalg.vector_norm(pool, dim=-1)
+    nbrs = []
+    for a in range(0, len(query), increment):
+        dists = _cosine_dist_chunk(query[a:a + increment], pool, pool_norms)
+        nbrs.append(dists.topk(k=min(k_search, pool.shape[0]), dim=-1, largest=False).indices)
+    nbrs = torch.cat(nbrs, dim=0)
+    idx = nbrs[:, :k_mix]
+    out = pool[idx.reshape(-1)].reshape(idx.shape[0], idx.shape[1], pool.shape[1]).mean(1)
+    return nbrs, out
+
+
+def time_sample(n_query: int, n_pool: int, dim: int, steps: int = 1, warmup: int = 0, seed: int = 0):
+    """Returns (seconds per pass, threads used)."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn((n_query, dim), generator=g)
+    p = torch.randn((n_pool, dim), generator=g)
+    for _ in range(warmup):
+        match_sample(q, p)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        match_sample(q, p)
+    return (time.perf_counter() - t0) / max(steps, 1), torch.get_num_threads()

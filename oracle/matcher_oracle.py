@@ -158,7 +158,8 @@ def knn_with_concat_cost(idx, src, tgt, shifted_src_f0=None, tgt_f0=None, concat
     distance (the calls see <= 8 rows).  In the f0 branch the
     assignment `concat_weight = 0` sticks for all later frames (SURVEY D6,
     lib_ongaku_test.py:332).  With `return_costs` also returns the sorted total
-    costs [T,2K] (row 0 zeros) so tests can mask legitimately tied rows.
+    costs [T,2K] and the candidates in that order (row 0 zeros) so tests can
+    mask legitimately tied rows (duplicate candidates tie harmlessly).
     """
     idx = np.asarray(idx, dtype=np.int64)
     src = np.asarray(src, dtype=np.float64)
@@ -174,6 +175,7 @@ def knn_with_concat_cost(idx, src, tgt, shifted_src_f0=None, tgt_f0=None, concat
     out = np.empty_like(idx)
     out[0] = idx[0]
     costs = np.zeros((t_len, 2 * k))
+    cands = np.zeros((t_len, 2 * k), dtype=np.int64)
     for i in range(1, t_len):
         prev = out[i - 1]
         extra = np.minimum(prev + 1, n_pool - 1)
@@ -196,8 +198,9 @@ def knn_with_concat_cost(idx, src, tgt, shifted_src_f0=None, tgt_f0=None, concat
         order = np.argsort(total[0], kind="stable")
         out[i] = cand[order[:k]]
         costs[i] = total[0][order]
+        cands[i] = cand[order]
     if return_costs:
-        return out, costs
+        return out, costs, cands
     return out
 
 
