@@ -80,6 +80,10 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
  *   knnsvc_filter_timing_collect   host float[max_n] <- per-call filter durations (ms)
  *                                  since the last collect; returns the count */
 long long knnsvc_launch_count(void);
+/* tuning / experiment switches: "cta_group" = 1|2 (CTAs per tcgen05.mma),
+ * "bf16_operands" = 0|1 (bf16 instead of fp16 tensor-core operands; measurement only,
+ * the error window is sized for fp16). */
+int knnsvc_set_option(const char* name, int value);
 int knnsvc_filter_timing(int enable);
 int knnsvc_filter_timing_collect(float* ms_host, int max_n);
 

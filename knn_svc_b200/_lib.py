@@ -24,6 +24,7 @@ SIGNATURES = {
     "knnsvc_knn_workspace_bytes": (sz, [i64, i64, i32, i32]),
     "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, sz, vp, vp]),
     "knnsvc_launch_count": (C.c_longlong, []),
+    "knnsvc_set_option": (i32, [C.c_char_p, i32]),
     "knnsvc_filter_timing": (i32, [i32]),
     "knnsvc_filter_timing_collect": (i32, [vp, i32]),
     "knnsvc_knn_exact_workspace_bytes": (sz, [i64, i64, i32]),

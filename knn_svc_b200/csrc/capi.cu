@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/knnsvc_b200.h.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -17,6 +18,17 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static int g_opt_cta_group = 0;  // 0 = unset -> env KNNSVC_CTA_GROUP or default
+static int g_opt_bf16 = 0;
+int opt_cta_group() {
+  if (g_opt_cta_group == 0) {
+    const char* e = getenv("KNNSVC_CTA_GROUP");
+    g_opt_cta_group = (e && e[0] == '2') ? 2 : 1;
+  }
+  return g_opt_cta_group;
+}
+int opt_bf16() { return g_opt_bf16; }
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -144,6 +156,20 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
 }
 
 long long knnsvc_launch_count(void) { return g_launches.load(); }
+
+int knnsvc_set_option(const char* name, int value) {
+  KNN_CHECK_ARG(name != nullptr, -1, "set_option: null name");
+  if (strcmp(name, "cta_group") == 0) {
+    KNN_CHECK_ARG(value == 1 || value == 2, -1, "set_option: cta_group must be 1 or 2");
+    g_opt_cta_group = value;
+    return 0;
+  }
+  if (strcmp(name, "bf16_operands") == 0) {
+    g_opt_bf16 = value != 0;
+    return 0;
+  }
+  KNN_CHECK_ARG(false, -1, "set_option: unknown option '%s'", name);
+}
 
 int knnsvc_filter_timing(int enable) {
   if (enable && !g_ev_made) {

@@ -5,6 +5,10 @@
 
 namespace knnsvc {
 
+// ---- tuning options (capi.cu): diagnostic switches, see knnsvc_set_option
+int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
+int opt_bf16();        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
+
 // ---- rows.cu
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
                         float* norms, int* bad_rows, cudaStream_t stream);
@@ -19,7 +23,7 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
 
 // ---- knn_filter_sm100.cu
 struct FilterPlan {
-  int n_qtiles, n_ptiles, n_seg, n_units, grid, cap;
+  int ctas, n_qtiles, n_ptiles, n_seg, n_units, grid, cap;
 };
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,

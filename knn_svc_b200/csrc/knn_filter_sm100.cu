@@ -4,12 +4,17 @@
 // (ddsp_prematch_dataset.py:1196-1206, lib_ongaku_test.py:148-175) without ever
 // writing the [T, Np] distance matrix.
 //
-// Shape of the computation (per CTA, persistent over work units):
-//   A = 128 query rows   x 64 fp16  (TMA, SWIZZLE_128B, K-major)   -> UMMA M = 128
-//   B = 256 pool rows    x 64 fp16  (TMA, SWIZZLE_128B, K-major)   -> UMMA N = 256
-//   D = 128 lanes x 256 fp32 columns in TMEM, double buffered (512 columns)
+// Shape of the computation (persistent over work units), two variants:
+//   CTAS = 2 (default): a CTA PAIR on one TPC runs tcgen05.mma.cta_group::2 with
+//     UMMA M = 256 (128 query rows per CTA), N = 256.  Each CTA stages its own
+//     A = 128 query rows x 64 fp16 and HALF of B = 128 pool rows x 64 fp16 per
+//     pipeline stage (32 KB, 6 stages), so shared-memory fill and L2->SM traffic
+//     per FLOP are 2/3 of the single-CTA shape.  The leader CTA issues the MMAs.
+//   CTAS = 1: one CTA, UMMA M = 128, N = 256, A 16 KB + B 32 KB per stage, 4 stages.
+//   D = 128 lanes x 256 fp32 columns per CTA in TMEM, double buffered (512 columns)
 //   warp 0 : TMA producer      warp 1 : tcgen05.mma issuer + TMEM owner
 //   warps 2-5 : epilogue, one thread per query row (TMEM lane), tcgen05.ld 32x32b
+//   Operands: TMA, SWIZZLE_128B, K-major.
 //
 // A work unit is (query tile, pool segment): the CTA keeps its 128 rows and walks
 // the segment's pool tiles, so each epilogue thread carries one row's running
@@ -21,6 +26,7 @@
 // and LOGS every column with s~ > tau_k - 2*eps.  Every true top-k member is in
 // the log; knn_rescore re-scores the log exactly from the fp32 rows.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -29,34 +35,50 @@ namespace knnsvc {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
-constexpr int BK = 64;
+constexpr int BM = 128;   // query rows per CTA (TMEM lanes)
+constexpr int BN = 256;   // pool rows per MMA tile (TMEM columns)
+constexpr int BK = 64;    // fp16 elements per pipeline stage along the feature dimension
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
-struct SmemLayout {
+template <int CTAS>
+struct Cfg {
+  static constexpr int B_ROWS = BN / CTAS;             // pool rows this CTA stages per tile
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
   // operand ring first: SWIZZLE_128B wants 1024-byte aligned stage bases
   static constexpr int ring = 0;
   static constexpr int topv = ring + STAGES * STAGE_BYTES;              // float [kMaxK][BM]
-  static constexpr int bars = topv + kMaxK * BM * 4;                    // mbarriers
-  static constexpr int full_bar = bars;                                 // [STAGES]
+  static constexpr int full_bar = topv + kMaxK * BM * 4;                // [STAGES]
   static constexpr int empty_bar = full_bar + STAGES * 8;               // [STAGES]
   static constexpr int tmem_full_bar = empty_bar + STAGES * 8;          // [2]
   static constexpr int tmem_empty_bar = tmem_full_bar + 2 * 8;          // [2]
   static constexpr int tmem_ptr = tmem_empty_bar + 2 * 8;               // uint32
   static constexpr int total = tmem_ptr + 16;
+  static constexpr int SMEM_BYTES = total + 1024;  // slack for manual 1024 B alignment
 };
-constexpr int SMEM_BYTES = SmemLayout::total + 1024;  // slack for manual 1024 B alignment
 
 // ----------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -65,6 +87,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (shared::cluster address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -79,26 +105,57 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// TMA tile load; with CTAS == 2 the completion bytes are credited to `bar`, a shared::cluster
+// address that names the LEADER CTA's barrier, whichever CTA of the pair issues the copy.
+template <int CTAS>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if constexpr (CTAS == 2) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// completion of all prior MMAs of this thread -> one arrival on `bar` (in both CTAs of the pair when CTAS == 2)
+template <int CTAS>
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CTAS == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  }
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
+  if constexpr (CTAS == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  }
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -126,17 +183,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128.
-constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128*CTAS.
+template <int CTAS>
+struct InstrDesc {
+  static constexpr uint32_t value = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
+};
 
 struct RowState {
   float tau_lo;  // scaled: log everything strictly above this
+  float kth;     // scaled: k-th largest value seen (min of the list), -inf until k values seen
+  int kpos;      // slot of `kth` in the list
   int cnt;       // entries in this row's log (cap+1 = overflowed)
 };
 
 // Rare path: one accumulator value passed the register threshold.  Logs it and,
-// if it also beats the running k-th best, updates the sorted top-k values kept
-// in shared memory ([slot][row] so the 32 rows of a warp hit 32 banks).
+// if it also beats the running k-th best, replaces that entry of the row's
+// UNSORTED top-k list in shared memory ([slot][row]: the 32 rows of a warp hit
+// 32 banks) and rescans the k slots for the new minimum — k independent loads
+// instead of an insertion sort's dependent chain.
 __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, float* __restrict__ topv_row, int k,
                                                float* __restrict__ log_val, int* __restrict__ log_idx, int cap,
                                                float window_scaled) {
@@ -161,18 +225,20 @@ __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, fl
   } else {
     st.cnt = cap + 1;  // genuine overflow: more than `cap` candidates inside the window
   }
-  float kth = topv_row[(k - 1) * BM];
-  if (v > kth) {
-    int j = k - 1;
-    while (j > 0) {
-      float up = topv_row[(j - 1) * BM];
-      if (!(up < v)) break;
-      topv_row[j * BM] = up;
-      --j;
+  if (v > st.kth) {
+    topv_row[st.kpos * BM] = v;
+    float mn = topv_row[0];
+    int mp = 0;
+    for (int j = 1; j < k; ++j) {
+      const float t = topv_row[j * BM];
+      if (t < mn) {
+        mn = t;
+        mp = j;
+      }
     }
-    topv_row[j * BM] = v;
-    kth = topv_row[(k - 1) * BM];
-    st.tau_lo = kth - window_scaled;  // -inf until k values have been seen
+    st.kth = mn;
+    st.kpos = mp;
+    st.tau_lo = mn - window_scaled;  // -inf until k values have been seen
   }
   return st;
 }
@@ -180,11 +246,13 @@ __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, fl
 }  // namespace
 
 // ----------------------------------------------------------------------------- kernel
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
                   int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
-                  float* __restrict__ seg_top) {
+                  float* __restrict__ seg_top, uint32_t idesc) {
+  using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
                                                          ~(uintptr_t)1023);
@@ -192,49 +260,69 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_units = n_qtiles * n_seg;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int worker = blockIdx.x / CTAS;        // index of this CTA (pair) among the persistent workers
+  const int n_workers = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_p) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(sbase + SmemLayout::full_bar + s * 8, 1);
-      mbar_init(sbase + SmemLayout::empty_bar + s * 8, 1);
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(sbase + L::full_bar + s * 8, 1);
+      mbar_init(sbase + L::empty_bar + s * 8, 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(sbase + SmemLayout::tmem_full_bar + b * 8, 1);
-      mbar_init(sbase + SmemLayout::tmem_empty_bar + b * 8, 4);  // one arrive per epilogue warp
+      mbar_init(sbase + L::tmem_full_bar + b * 8, 1);
+      mbar_init(sbase + L::tmem_empty_bar + b * 8, 4 * CTAS);  // one arrive per epilogue warp of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SmemLayout::tmem_ptr),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L::tmem_ptr),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L::tmem_ptr),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::tmem_ptr);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::tmem_ptr);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA; each stages its own A rows and its part of B) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = worker; u < n_units; u += n_workers) {
         const int seg = u / n_qtiles, qt = u % n_qtiles;
         const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
+        const int q_row = (qt * CTAS + (int)cta_rank) * BM;
         for (int pt = t0; pt < t1; ++pt) {
+          const int p_row = pt * BN + (int)cta_rank * L::B_ROWS;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(sbase + SmemLayout::empty_bar + stage * 8, phase ^ 1);
-            const uint32_t full = sbase + SmemLayout::full_bar + stage * 8;
-            mbar_expect_tx(full, STAGE_BYTES);
-            const uint32_t a_dst = sbase + SmemLayout::ring + stage * STAGE_BYTES;
-            tma_load_2d(a_dst, &map_q, full, kb * BK, qt * BM);
-            tma_load_2d(a_dst + A_BYTES, &map_p, full, kb * BK, pt * BN);
-            if (++stage == STAGES) {
+            mbar_wait(sbase + L::empty_bar + stage * 8, phase ^ 1);
+            const uint32_t full_local = sbase + L::full_bar + stage * 8;
+            uint32_t full = full_local;
+            if constexpr (CTAS == 2) {
+              full = mapa(full_local, 0);                                  // the leader's barrier collects both CTAs' bytes
+              if (leader) mbar_expect_tx(full_local, 2 * L::STAGE_BYTES);
+            } else {
+              mbar_expect_tx(full_local, L::STAGE_BYTES);
+            }
+            const uint32_t a_dst = sbase + L::ring + stage * L::STAGE_BYTES;
+            tma_load_2d<CTAS>(a_dst, &map_q, full, kb * BK, q_row);
+            tma_load_2d<CTAS>(a_dst + A_BYTES, &map_p, full, kb * BK, p_row);
+            if (++stage == L::STAGES) {
               stage = 0;
               phase ^= 1;
             }
@@ -243,56 +331,58 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_n = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = worker; u < n_units; u += n_workers) {
         const int seg = u / n_qtiles;
         const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
         for (int pt = t0; pt < t1; ++pt, ++tile_n) {
           const uint32_t buf = tile_n & 1;
           const uint32_t buf_phase = (tile_n >> 1) & 1;
-          mbar_wait(sbase + SmemLayout::tmem_empty_bar + buf * 8, buf_phase ^ 1);
+          mbar_wait(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(sbase + SmemLayout::full_bar + stage * 8, phase);
+            mbar_wait(sbase + L::full_bar + stage * 8, phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = sbase + SmemLayout::ring + stage * STAGE_BYTES;
+            const uint32_t a_addr = sbase + L::ring + stage * L::STAGE_BYTES;
             const uint64_t da = make_smem_desc(a_addr);
             const uint64_t db = make_smem_desc(a_addr + A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; ++kk) {
               // advancing 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), kInstrDesc, (kb | kk) != 0);
+              umma_f16<CTAS>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
             }
-            tcgen05_commit(sbase + SmemLayout::empty_bar + stage * 8);  // smem slot free once these MMAs retire
-            if (++stage == STAGES) {
+            tcgen05_commit<CTAS>(sbase + L::empty_bar + stage * 8);  // smem slot free once these MMAs retire
+            if (++stage == L::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tcgen05_commit(sbase + SmemLayout::tmem_full_bar + buf * 8);  // accumulator ready for the epilogue
+          tcgen05_commit<CTAS>(sbase + L::tmem_full_bar + buf * 8);  // accumulator ready for the epilogue(s)
         }
       }
     }
   } else {
     // ===================== epilogue: streaming candidate filter =====================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
-    const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside the tile
-    float* topv_row = reinterpret_cast<float*>(smem + SmemLayout::topv) + row_in_tile;
+    const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside this CTA's tile
+    float* topv_row = reinterpret_cast<float*>(smem + L::topv) + row_in_tile;
     const float window_scaled = 2.0f * kFilterEps * kDotScale;
     uint32_t tile_n = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int u = worker; u < n_units; u += n_workers) {
       const int seg = u / n_qtiles, qt = u % n_qtiles;
       const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
-      const int64_t row = (int64_t)qt * BM + row_in_tile;
+      const int64_t row = (int64_t)(qt * CTAS + (int)cta_rank) * BM + row_in_tile;
       const bool row_ok = row < n_query;
       for (int j = 0; j < k; ++j) topv_row[j * BM] = -INFINITY;
       RowState st;
       st.tau_lo = row_ok ? -INFINITY : INFINITY;
+      st.kth = -INFINITY;
+      st.kpos = 0;
       st.cnt = 0;
       const int64_t slot = row * n_seg + seg;
       float* lv = log_val + (row_ok ? slot * cap : 0);
@@ -300,7 +390,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int pt = t0; pt < t1; ++pt, ++tile_n) {
         const uint32_t buf = tile_n & 1;
         const uint32_t buf_phase = (tile_n >> 1) & 1;
-        mbar_wait(sbase + SmemLayout::tmem_full_bar + buf * 8, buf_phase);
+        mbar_wait(sbase + L::tmem_full_bar + buf * 8, buf_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
         const int col0 = pt * BN;
@@ -324,7 +414,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(sbase + SmemLayout::tmem_empty_bar + buf * 8);
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(mapa(sbase + L::tmem_empty_bar + buf * 8, 0));
+          else mbar_arrive(sbase + L::tmem_empty_bar + buf * 8);
+        }
       }
       if (row_ok) {
         log_cnt[slot] = st.cnt;
@@ -333,9 +426,18 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   }
 
-  __syncthreads();
+  // the pair must stay resident until both CTAs are done with each other's shared memory and TMEM
+  __syncwarp();
+  tcgen05_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
+  tcgen05_fence_after();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    __syncwarp();
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -372,25 +474,34 @@ int make_half_map(CUtensorMap* map, const void* base, int64_t rows, int dim_pad,
   return 0;
 }
 
+int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      cached = v;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
 }  // namespace
 
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   FilterPlan pl;
-  pl.n_qtiles = (int)ceil_div64(n_query, BM);
+  pl.ctas = opt_cta_group();
+  pl.n_qtiles = (int)ceil_div64(n_query, BM * pl.ctas);
   pl.n_ptiles = (int)ceil_div64(n_pool, BN);
-  int num_sms = 148;
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
-  }
+  const int workers = num_sms() / pl.ctas;
   // choose the number of pool segments: minimise waves*tiles_per_unit, with a
   // small penalty per segment (each one restarts the running threshold -> more log traffic)
   int best_s = 1;
   double best_cost = 1e300;
   const int max_s = pl.n_ptiles < 16 ? pl.n_ptiles : 16;
   for (int s = 1; s <= max_s; ++s) {
-    double waves = (double)ceil_div64((int64_t)pl.n_qtiles * s, num_sms);
+    double waves = (double)ceil_div64((int64_t)pl.n_qtiles * s, workers);
     double tiles = (double)ceil_div64(pl.n_ptiles, s) + 1.0;  // +1: pipeline fill per unit
     double cost = waves * tiles * (1.0 + 0.004 * s);
     if (cost < best_cost) {
@@ -400,9 +511,39 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   }
   pl.n_seg = best_s;
   pl.n_units = pl.n_qtiles * pl.n_seg;
-  pl.grid = pl.n_units < num_sms ? pl.n_units : num_sms;
+  pl.grid = (pl.n_units < workers ? pl.n_units : workers) * pl.ctas;
   pl.cap = 64 * k < 256 ? 256 : 64 * k;
   return pl;
+}
+
+template <int CTAS>
+static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
+                          int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
+                          float* seg_top, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<CTAS>::SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
+  const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
+  KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS>, map_q, map_p, n_query, n_pool, k_blocks, k, pl.n_qtiles,
+                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, idesc));
+  return 0;
 }
 
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
@@ -414,18 +555,13 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   CUtensorMap map_q, map_p;
   int rc = make_half_map(&map_q, qh, n_query, dim_pad, BM);
   if (rc) return rc;
-  rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN);
+  rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN / pl.ctas);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
-  knn_filter_kernel<<<pl.grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_q, map_p, n_query, n_pool, dim_pad / BK, k,
-                                                                  pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val,
-                                                                  log_idx, log_cnt, seg_top);
-  KNN_LAUNCH_CHECK();
-  return 0;
+  if (pl.ctas == 2)
+    return launch_variant<2>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
+                             stream);
+  return launch_variant<1>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
+                           stream);
 }
 
 }  // namespace knnsvc

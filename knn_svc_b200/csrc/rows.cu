@@ -8,6 +8,8 @@
 //  knn_exact      : CUDA-core exact kNN, fp64 accumulation.  It is the decision
 //                   procedure for rows the tensor-core filter cannot decide
 //                   (massive ties) and an independent GPU check in the tests.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -17,7 +19,7 @@ namespace knnsvc {
 // One warp per row; HBM-bound: reads dim*4 B, writes dim_pad*2 + 4 B per row.
 __global__ void __launch_bounds__(256) prepare_rows_kernel(
     const float* __restrict__ x, int64_t rows, int dim, int64_t ld,
-    __half* __restrict__ hout, int dim_pad, float* __restrict__ norms, int* __restrict__ bad_rows) {
+    __half* __restrict__ hout, int dim_pad, float* __restrict__ norms, int* __restrict__ bad_rows, int bf16) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -52,17 +54,25 @@ __global__ void __launch_bounds__(256) prepare_rows_kernel(
       uint2* h4 = reinterpret_cast<uint2*>(hr);
       for (int c = lane; c < dim_pad / 4; c += 32) {
         float4 v = (c < dim / 4) ? __ldg(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        __half2 a = __floats2half2_rn(v.x * sc, v.y * sc);
-        __half2 b = __floats2half2_rn(v.z * sc, v.w * sc);
         uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&a);
-        o.y = *reinterpret_cast<uint32_t*>(&b);
+        if (bf16) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(v.x * sc, v.y * sc);
+          __nv_bfloat162 b = __floats2bfloat162_rn(v.z * sc, v.w * sc);
+          o.x = *reinterpret_cast<uint32_t*>(&a);
+          o.y = *reinterpret_cast<uint32_t*>(&b);
+        } else {
+          __half2 a = __floats2half2_rn(v.x * sc, v.y * sc);
+          __half2 b = __floats2half2_rn(v.z * sc, v.w * sc);
+          o.x = *reinterpret_cast<uint32_t*>(&a);
+          o.y = *reinterpret_cast<uint32_t*>(&b);
+        }
         h4[c] = o;
       }
     } else {
       for (int c = lane; c < dim_pad; c += 32) {
         float v = (c < dim) ? __ldg(xr + c) * sc : 0.0f;
-        hr[c] = __float2half_rn(v);
+        if (bf16) reinterpret_cast<__nv_bfloat16*>(hr)[c] = __float2bfloat16_rn(v);
+        else hr[c] = __float2half_rn(v);
       }
     }
   }
@@ -74,7 +84,7 @@ int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void*
   int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   prepare_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, dim, ld, (__half*)half_out, dim_pad,
-                                                            norms, bad_rows);
+                                                            norms, bad_rows, opt_bf16());
   KNN_LAUNCH_CHECK();
   return 0;
 }
