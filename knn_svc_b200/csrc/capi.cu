@@ -70,7 +70,7 @@ KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const Fil
   w.log_idx = reinterpret_cast<int*>(take(slots * pl.cap * sizeof(int)));
   w.log_cnt = reinterpret_cast<int*>(take(slots * sizeof(int)));
   w.seg_top = reinterpret_cast<float*>(take(slots * k * sizeof(float)));
-  w.flag_list = reinterpret_cast<int64_t*>(take(kFlagCap * sizeof(int64_t)));
+  w.flag_list = reinterpret_cast<int64_t*>(take((size_t)n_query * sizeof(int64_t)));
   w.counters = reinterpret_cast<int*>(take(16 * sizeof(int)));
   w.exact_partial = take(exact_partial_bytes(kFlagCap, n_pool, k));
   w.total = off;
@@ -241,13 +241,18 @@ int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const floa
   KNN_CHECK_ARG((shifted_src_f0 == nullptr) == (pool_f0 == nullptr), -1,
                 "concat_cost: shifted_src_f0 and pool_f0 must be given together");
   if (n_utt == 0) return 0;
-  int64_t* d_off = nullptr;
-  KNN_CUDA(cudaMallocAsync(&d_off, (size_t)(n_utt + 1) * sizeof(int64_t), stream));
+  const int64_t n_frames = utt_offsets_host[n_utt];
+  KNN_CHECK_ARG(utt_offsets_host[0] == 0 && n_frames >= 0, -1, "concat_cost: utterance offsets must start at 0");
+  // stream-ordered scratch: utterance offsets + per-frame baseline and |src|^2 (fp64)
+  unsigned char* d_ws = nullptr;
+  const size_t off_bytes = ((size_t)(n_utt + 1) * sizeof(int64_t) + 255) / 256 * 256;
+  KNN_CUDA(cudaMallocAsync(&d_ws, off_bytes + (size_t)2 * (n_frames + 1) * sizeof(double), stream));
+  int64_t* d_off = reinterpret_cast<int64_t*>(d_ws);
   KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            stream));
   int rc = launch_concat_cost(idx, src, pool, n_pool, dim, shifted_src_f0, pool_f0, concat_weight, d_off, n_utt,
-                              out_idx, stream);
-  cudaFreeAsync(d_off, stream);
+                              n_frames, reinterpret_cast<double*>(d_ws + off_bytes), out_idx, stream);
+  cudaFreeAsync(d_ws, stream);
   return rc;
 }
 

@@ -47,7 +47,7 @@ int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
                      int64_t* out_idx, cudaStream_t stream);
 int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
-                       int n_utt, int64_t* out_idx, cudaStream_t stream);
+                       int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream);
 
 // ---- weight_fit.cu
 size_t weight_fit_workspace_bytes(int64_t n_query, int k);

@@ -9,16 +9,24 @@
 //      dist = 1 - q.p/(|q||p|)   (lib_ongaku_test.py:162-165).
 //   4. survivors are ranked by (dist, index) and the first k written, ascending —
 //      the order dists.topk(k, largest=False) returns (ddsp_prematch_dataset.py:1203).
-// Rows whose log overflowed, or with more than RS_MAXSURV survivors (massive
-// ties), are appended to the flag list for the exact brute-force kernel.
+// Survivors are streamed (no cap): each warp re-scores its share and keeps a
+// sorted exact top-k; the warps' lists are merged at the end.  Rows whose log
+// overflowed in some segment (more than `cap` candidates inside the window:
+// massive ties) are appended to the flag list for the exact brute-force kernel.
+#include <limits.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace knnsvc {
 
 constexpr int RS_THREADS = 128;
-constexpr int RS_MAXSURV = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAXTOP = 16 * kMaxK;  // n_seg <= 16
+
+__device__ __forceinline__ bool rs_less(double da, int ia, double db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
 
 __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ q, const float* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
@@ -29,23 +37,28 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     int* __restrict__ stats) {
   extern __shared__ __align__(16) float s_q[];  // [dim]
   __shared__ float s_top[RS_MAXTOP];
-  __shared__ int s_surv_idx[RS_MAXSURV];
-  __shared__ double s_surv_d[RS_MAXSURV];
-  __shared__ int s_nsurv, s_overflow, s_logged;
+  __shared__ double s_d[RS_WARPS][kMaxK];   // per-warp exact top-k, ascending by (dist, idx)
+  __shared__ int s_i[RS_WARPS][kMaxK];
+  __shared__ int s_nsurv[RS_WARPS];
+  __shared__ int s_overflow, s_logged;
   __shared__ float s_thr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int64_t row = blockIdx.x; row < n_query; row += gridDim.x) {
     __syncthreads();
     if (tid == 0) {
-      s_nsurv = 0;
       s_overflow = 0;
       s_logged = 0;
       s_thr = -INFINITY;
     }
+    if (tid < RS_WARPS) s_nsurv[tid] = 0;
     const int n_top = n_seg * k;
     for (int e = tid; e < n_top; e += RS_THREADS) s_top[e] = seg_top[row * n_top + e];
     for (int c = tid; c < dim; c += RS_THREADS) s_q[c] = __ldg(q + row * dim + c);
+    for (int e = tid; e < RS_WARPS * kMaxK; e += RS_THREADS) {
+      s_d[e / kMaxK][e % kMaxK] = INFINITY;
+      s_i[e / kMaxK][e % kMaxK] = INT_MAX;
+    }
     __syncthreads();
     // k-th largest of the union of the segment lists (rank counting, ties by position)
     for (int e = tid; e < n_top; e += RS_THREADS) {
@@ -63,68 +76,87 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
       atomicAdd(&s_logged, c > cap ? cap : c);
     }
     __syncthreads();
-    const float thr = s_thr;
-    for (int s = 0; s < n_seg; ++s) {
-      const int64_t slot = row * n_seg + s;
-      int c = log_cnt[slot];
-      c = c > cap ? cap : c;
-      for (int e = tid; e < c; e += RS_THREADS) {
-        if (log_val[slot * cap + e] >= thr) {
-          const int pos = atomicAdd(&s_nsurv, 1);
-          if (pos < RS_MAXSURV) s_surv_idx[pos] = log_idx[slot * cap + e];
-        }
-      }
-    }
-    __syncthreads();
-    const int nsurv = s_nsurv;
-    if (tid == 0 && stats) {
-      atomicAdd(stats + 1, s_logged);
-      atomicAdd(stats + 2, nsurv);
-    }
-    if (s_overflow || nsurv > RS_MAXSURV) {
+    if (s_overflow) {
+      // more than `cap` candidates inside the error window of one segment: exact brute force decides
       if (tid == 0) {
         const int pos = atomicAdd(flag_count, 1);
-        if (pos < kFlagCap) flag_list[pos] = row;
+        flag_list[pos] = row;
         if (stats) atomicAdd(stats + 0, 1);
       }
       continue;
     }
+    const float thr = s_thr;
     const double qnorm = (double)qn[row];
-    for (int e = warp; e < nsurv; e += RS_THREADS / 32) {
-      const int64_t pr = s_surv_idx[e];
-      const float* prow = p + pr * dim;
-      double acc = 0.0;
-      if ((dim & 3) == 0) {
-        const float4* p4 = reinterpret_cast<const float4*>(prow);
-        const float4* q4 = reinterpret_cast<const float4*>(s_q);
-        for (int c = lane; c < dim / 4; c += 32) {
-          const float4 a = __ldg(p4 + c);
-          const float4 b = q4[c];
-          acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+    int my_surv = 0;
+    double kth_d = INFINITY;   // warp-uniform copy of this warp's current k-th best
+    int kth_i = INT_MAX;
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t slot = row * n_seg + s;
+      const int c = log_cnt[slot];
+      for (int base = warp * 32; base < c; base += RS_THREADS) {
+        const int e = base + lane;
+        int cand = -1;
+        if (e < c && log_val[slot * cap + e] >= thr) cand = log_idx[slot * cap + e];
+        unsigned mask = __ballot_sync(0xffffffffu, cand >= 0);
+        while (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int pr = __shfl_sync(0xffffffffu, cand, b);
+          const float* prow = p + (int64_t)pr * dim;
+          double acc = 0.0;
+          if ((dim & 3) == 0) {
+            const float4* p4 = reinterpret_cast<const float4*>(prow);
+            const float4* q4 = reinterpret_cast<const float4*>(s_q);
+            for (int cc = lane; cc < dim / 4; cc += 32) {
+              const float4 a = __ldg(p4 + cc);
+              const float4 bq = q4[cc];
+              acc += (double)a.x * bq.x + (double)a.y * bq.y + (double)a.z * bq.z + (double)a.w * bq.w;
+            }
+          } else {
+            for (int cc = lane; cc < dim; cc += 32) acc += (double)__ldg(prow + cc) * (double)s_q[cc];
+          }
+          acc = warp_sum(acc);
+          const double d = 1.0 - acc / (qnorm * (double)pn[pr]);
+          ++my_surv;
+          if (rs_less(d, pr, kth_d, kth_i)) {
+            if (lane == 0) {
+              int j = k - 1;
+              while (j > 0 && rs_less(d, pr, s_d[warp][j - 1], s_i[warp][j - 1])) {
+                s_d[warp][j] = s_d[warp][j - 1];
+                s_i[warp][j] = s_i[warp][j - 1];
+                --j;
+              }
+              s_d[warp][j] = d;
+              s_i[warp][j] = pr;
+            }
+            __syncwarp();
+            kth_d = s_d[warp][k - 1];
+            kth_i = s_i[warp][k - 1];
+          }
         }
-      } else {
-        for (int c = lane; c < dim; c += 32) acc += (double)__ldg(prow + c) * (double)s_q[c];
       }
-      acc = warp_sum(acc);
-      if (lane == 0) s_surv_d[e] = 1.0 - acc / (qnorm * (double)pn[pr]);
     }
+    if (lane == 0) s_nsurv[warp] = my_surv;
     __syncthreads();
-    for (int e = tid; e < nsurv; e += RS_THREADS) {
-      const double d = s_surv_d[e];
-      const int i = s_surv_idx[e];
+    // merge the RS_WARPS sorted lists: rank of each entry among all RS_WARPS*k by (dist, idx)
+    for (int e = tid; e < RS_WARPS * k; e += RS_THREADS) {
+      const int w = e / k, j = e % k;
+      const double d = s_d[w][j];
+      const int i = s_i[w][j];
+      if (i == INT_MAX) continue;
       int rank = 0;
-      for (int j = 0; j < nsurv; ++j) {
-        const double dj = s_surv_d[j];
-        rank += (dj < d) || (dj == d && s_surv_idx[j] < i);
-      }
+      for (int w2 = 0; w2 < RS_WARPS; ++w2)
+        for (int j2 = 0; j2 < k; ++j2) rank += rs_less(s_d[w2][j2], s_i[w2][j2], d, i);
       if (rank < k) {
         out_dist[row * k + rank] = (float)d;
         out_idx[row * k + rank] = (int64_t)i + index_offset;
       }
     }
-    for (int o = nsurv + tid; o < k; o += RS_THREADS) {  // pool smaller than k
-      out_dist[row * k + o] = INFINITY;
-      out_idx[row * k + o] = -1;
+    if (tid == 0 && stats) {
+      int ns = 0;
+      for (int w = 0; w < RS_WARPS; ++w) ns += s_nsurv[w];
+      atomicAdd(stats + 1, s_logged);
+      atomicAdd(stats + 2, ns);
     }
   }
 }
@@ -138,7 +170,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
   KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
   size_t smem = (size_t)dim * sizeof(float);
-  KNN_CHECK_ARG(smem <= 40 * 1024, -3, "dim %d too large for the rescoring kernel", dim);
+  KNN_CHECK_ARG(smem <= 32 * 1024, -3, "dim %d too large for the rescoring kernel", dim);
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, log_val, log_idx, log_cnt, seg_top,
                                                                    index_offset, out_dist, out_idx, flag_list,

@@ -108,38 +108,66 @@ int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
 // knn_with_concat_cost (lib_ongaku_test.py:270-369), K = 4.  The recurrence is
 // serial in the frame index (frame i's candidates include "previous selection + 1"),
 // so one CTA walks one utterance; parallelism is inside a step — 8 warps, one
-// candidate row each, 5 direct-form cosine distances per candidate plus the
-// frame-to-frame baseline — and across utterances (one CTA each).
+// candidate row each, 5 direct-form cosine distances per candidate — and across
+// utterances (one CTA each).  Everything that does NOT depend on the recurrence
+// is hoisted into a fully parallel pre-pass: the frame-to-frame baseline
+// 2*dist(src[i-1], src[i]) (:310) and |src[i]|^2.  Norms of the previous
+// selections are carried from the step in which they were candidates.
 //
 // Distances follow the reference's small-matrix path: cdist evaluates
 // sum((x-y)^2) directly, dot = (-d2 + |x|^2 + |y|^2)/2,
-// dist = 1 - dot/(|x||y|); accumulated in fp64.
+// dist = 1 - dot/(|x||y|).  Differences and squares are fp32 (the operands are
+// fp32), four-term partials are summed in fp64.
 constexpr int CC_K = 4;
 constexpr int CC_C = 2 * CC_K;
-
-struct Dist3 {
-  double d2, nx, ny;
-};
 
 __device__ __forceinline__ double cosd_from(double d2, double nx2, double ny2) {
   const double dot = (-d2 + nx2 + ny2) * 0.5;
   return 1.0 - dot / (sqrt(nx2) * sqrt(ny2));
 }
 
+// one warp per frame: base[i] = 2*cosd(src[i-1], src[i]) (i >= 1), n2[i] = |src[i]|^2
+__global__ void __launch_bounds__(256) frame_baseline_kernel(const float* __restrict__ src, int dim, int64_t n_frames,
+                                                             double* __restrict__ base, double* __restrict__ n2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp; i < n_frames; i += nwarps) {
+    const float* b = src + i * dim;
+    const float* a = src + (i > 0 ? i - 1 : 0) * dim;
+    double na = 0, nb = 0, dd = 0;
+    for (int c = lane; c < dim; c += 32) {
+      const float av = __ldg(a + c), bv = __ldg(b + c);
+      na += (double)(av * av);
+      nb += (double)(bv * bv);
+      dd += (double)((av - bv) * (av - bv));
+    }
+    na = warp_sum(na); nb = warp_sum(nb); dd = warp_sum(dd);
+    if (lane == 0) {
+      n2[i] = nb;
+      base[i] = (i > 0) ? 2.0 * cosd_from(dd, na, nb) : 0.0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
     const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
     int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
-    const int64_t* __restrict__ utt_offsets, int64_t* __restrict__ out_idx) {
+    const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
+    int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
   if (f_end <= f_begin) return;
   const bool use_f0 = src_f0 != nullptr;
+  const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(pool) & 15) == 0);
 
   __shared__ int64_t s_prev[CC_K];
+  __shared__ double s_prev_n2[CC_K];
   __shared__ int64_t s_cand[CC_C];
+  __shared__ double s_cand_n2[CC_C];
   __shared__ double s_match[CC_C];
   __shared__ double s_concat[CC_K][CC_C];
-  __shared__ double s_base;
   __shared__ double s_w;
 
   if (threadIdx.x < CC_K) {
@@ -148,6 +176,17 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
     out_idx[f_begin * CC_K + threadIdx.x] = v;
   }
   if (threadIdx.x == 0) s_w = (double)concat_weight;
+  __syncthreads();
+  if (warp < CC_K) {  // |row|^2 of the four initial selections
+    const float* r = pool + s_prev[warp] * dim;
+    double n = 0;
+    for (int c = lane; c < dim; c += 32) {
+      const float v = __ldg(r + c);
+      n += (double)(v * v);
+    }
+    n = warp_sum(n);
+    if (lane == 0) s_prev_n2[warp] = n;
+  }
   __syncthreads();
 
   for (int64_t i = f_begin + 1; i < f_end; ++i) {
@@ -170,47 +209,77 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
       const float* p1 = pool + s_prev[1] * dim;
       const float* p2 = pool + s_prev[2] * dim;
       const float* p3 = pool + s_prev[3] * dim;
-      double nc = 0, ns = 0, dm = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-      for (int c = lane; c < dim; c += 32) {
-        const double cv = (double)__ldg(crow + c);
-        const double sv = (double)__ldg(srow + c);
-        const double a0 = (double)__ldg(p0 + c), a1 = (double)__ldg(p1 + c);
-        const double a2 = (double)__ldg(p2 + c), a3 = (double)__ldg(p3 + c);
-        nc += cv * cv;
-        ns += sv * sv;
-        dm += (sv - cv) * (sv - cv);
-        n0 += a0 * a0; d0 += (a0 - cv) * (a0 - cv);
-        n1 += a1 * a1; d1 += (a1 - cv) * (a1 - cv);
-        n2 += a2 * a2; d2 += (a2 - cv) * (a2 - cv);
-        n3 += a3 * a3; d3 += (a3 - cv) * (a3 - cv);
+      double nc = 0, dm = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+      if (vec4) {
+        const float4* c4 = reinterpret_cast<const float4*>(crow);
+        const float4* s4 = reinterpret_cast<const float4*>(srow);
+        const float4* q0 = reinterpret_cast<const float4*>(p0);
+        const float4* q1 = reinterpret_cast<const float4*>(p1);
+        const float4* q2 = reinterpret_cast<const float4*>(p2);
+        const float4* q3 = reinterpret_cast<const float4*>(p3);
+        const int n4 = dim / 4;
+        constexpr int U = 4;  // 6 rows x U float4 loads issued before any use: ~one L2 round trip per batch
+        for (int c0 = lane; c0 < n4; c0 += 32 * U) {
+          float4 cv[U], sv[U], a0[U], a1[U], a2[U], a3[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+            const bool ok = c < n4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[u] = ok ? __ldg(c4 + c) : z;
+            sv[u] = ok ? __ldg(s4 + c) : z;
+            a0[u] = ok ? __ldg(q0 + c) : z;
+            a1[u] = ok ? __ldg(q1 + c) : z;
+            a2[u] = ok ? __ldg(q2 + c) : z;
+            a3[u] = ok ? __ldg(q3 + c) : z;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float e;
+            float t_nc = cv[u].x * cv[u].x;
+            t_nc = fmaf(cv[u].y, cv[u].y, t_nc);
+            t_nc = fmaf(cv[u].z, cv[u].z, t_nc);
+            t_nc = fmaf(cv[u].w, cv[u].w, t_nc);
+#define KNN_D2(acc, a)                                                  \
+            {                                                           \
+              float t;                                                  \
+              e = a.x - cv[u].x; t = e * e;                             \
+              e = a.y - cv[u].y; t = fmaf(e, e, t);                     \
+              e = a.z - cv[u].z; t = fmaf(e, e, t);                     \
+              e = a.w - cv[u].w; t = fmaf(e, e, t);                     \
+              acc += (double)t;                                         \
+            }
+            nc += (double)t_nc;
+            KNN_D2(dm, sv[u]) KNN_D2(d0, a0[u]) KNN_D2(d1, a1[u]) KNN_D2(d2, a2[u]) KNN_D2(d3, a3[u])
+#undef KNN_D2
+          }
+        }
+      } else {
+        for (int c = lane; c < dim; c += 32) {
+          const float cv = __ldg(crow + c), sv = __ldg(srow + c);
+          const float a0 = __ldg(p0 + c), a1 = __ldg(p1 + c), a2 = __ldg(p2 + c), a3 = __ldg(p3 + c);
+          nc += (double)(cv * cv);
+          dm += (double)((sv - cv) * (sv - cv));
+          d0 += (double)((a0 - cv) * (a0 - cv));
+          d1 += (double)((a1 - cv) * (a1 - cv));
+          d2 += (double)((a2 - cv) * (a2 - cv));
+          d3 += (double)((a3 - cv) * (a3 - cv));
+        }
       }
-      nc = warp_sum(nc); ns = warp_sum(ns); dm = warp_sum(dm);
-      n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2); n3 = warp_sum(n3);
+      nc = warp_sum(nc); dm = warp_sum(dm);
       d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
       if (lane == 0) {
-        s_match[warp] = cosd_from(dm, ns, nc);
-        s_concat[0][warp] = cosd_from(d0, n0, nc);
-        s_concat[1][warp] = cosd_from(d1, n1, nc);
-        s_concat[2][warp] = cosd_from(d2, n2, nc);
-        s_concat[3][warp] = cosd_from(d3, n3, nc);
-      }
-      if (warp == 0) {
-        // src_concat_baseline = 2 * dist(src[i-1], src[i])   (lib_ongaku_test.py:310)
-        const float* prow = src + (i - 1) * dim;
-        double na = 0, nb = 0, dd = 0;
-        for (int c = lane; c < dim; c += 32) {
-          const double a = (double)__ldg(prow + c), b = (double)__ldg(srow + c);
-          na += a * a;
-          nb += b * b;
-          dd += (a - b) * (a - b);
-        }
-        na = warp_sum(na); nb = warp_sum(nb); dd = warp_sum(dd);
-        if (lane == 0) s_base = 2.0 * cosd_from(dd, na, nb);
+        s_cand_n2[warp] = nc;
+        s_match[warp] = cosd_from(dm, src_n2[i], nc);
+        s_concat[0][warp] = cosd_from(d0, s_prev_n2[0], nc);
+        s_concat[1][warp] = cosd_from(d1, s_prev_n2[1], nc);
+        s_concat[2][warp] = cosd_from(d2, s_prev_n2[2], nc);
+        s_concat[3][warp] = cosd_from(d3, s_prev_n2[3], nc);
       }
     }
     __syncthreads();
     if (warp == 0) {
-      const double base = s_base;
+      const double base = base_all[i];  // 2 * dist(src[i-1], src[i])   (lib_ongaku_test.py:310)
       double w = s_w;
       if (use_f0 && !(base < 0.08)) w = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
       double total = INFINITY;
@@ -250,6 +319,7 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
         const int64_t sel = s_cand[lane];
         out_idx[i * CC_K + rank] = sel;
         s_prev[rank] = sel;
+        s_prev_n2[rank] = s_cand_n2[lane];
       }
       if (lane == 0) s_w = w;
     }
@@ -259,10 +329,16 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
 
 int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
-                       int n_utt, int64_t* out_idx, cudaStream_t stream) {
-  if (n_utt == 0) return 0;
+                       int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream) {
+  if (n_utt == 0 || n_frames == 0) return 0;
+  double* base = frame_ws;
+  double* n2 = frame_ws + n_frames;
+  int64_t grid = ceil_div64(n_frames, 8);
+  if (grid > 148 * 16) grid = 148 * 16;
+  frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
+  KNN_LAUNCH_CHECK();
   concat_cost_kernel<<<n_utt, CC_C * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
-                                                      utt_offsets_dev, out_idx);
+                                                      utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
   return 0;
 }

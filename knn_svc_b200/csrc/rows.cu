@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
     const float* __restrict__ q, const float* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const float* __restrict__ pn, int64_t n_pool, int dim, int k, const int64_t* __restrict__ row_list,
     const int* __restrict__ row_count_dev, int64_t row_count_host, int64_t slot_base, int64_t slot_cap,
-    double* __restrict__ part_d, int64_t* __restrict__ part_i) {
+    double* __restrict__ part_d, int64_t* __restrict__ part_i, int direct, int64_t index_offset,
+    float* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);                       // [EX_Q][dim]
   double* ld = reinterpret_cast<double*>(sq + (size_t)EX_Q * dim);      // [EX_WARPS][EX_Q][k]
@@ -191,7 +192,16 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_chunks = gridDim.x;
-  const int64_t total = row_count_dev ? (int64_t)min((int64_t)*row_count_dev, slot_cap) : row_count_host;
+  // Device-side row lists run in one of two regimes, chosen by the count the host cannot see:
+  //   chunked (direct == 0): <= slot_cap rows, the pool is split over gridDim.x CTAs per row group
+  //                          and per-chunk partial lists are merged by knn_exact_merge_kernel;
+  //   direct  (direct == 1): > slot_cap rows, one CTA scans the whole pool for a row group and
+  //                          writes the final lists (parallelism comes from the many groups).
+  int64_t total = row_count_host;
+  if (row_count_dev) {
+    total = (int64_t)*row_count_dev;
+    if ((total > slot_cap) != (direct != 0)) return;
+  }
   const int64_t chunk_rows = ceil_div64(n_pool, n_chunks);
   const int64_t c0 = (int64_t)blockIdx.x * chunk_rows;
   const int64_t c1 = min(n_pool, c0 + chunk_rows);
@@ -256,8 +266,9 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
       const int qi = warp;
       if (rows_s[qi] >= 0) {
         int64_t slot = g * EX_Q + qi;
-        double* od = part_d + ((slot * n_chunks) + blockIdx.x) * k;
-        int64_t* oi = part_i + ((slot * n_chunks) + blockIdx.x) * k;
+        double* od = direct ? nullptr : part_d + ((slot * n_chunks) + blockIdx.x) * k;
+        int64_t* oi = direct ? nullptr : part_i + ((slot * n_chunks) + blockIdx.x) * k;
+        const int64_t orow = rows_s[qi];
         int head = 0;  // lanes 0..EX_WARPS-1: cursor into list of warp `lane`
         for (int o = 0; o < k; ++o) {
           double cd = INFINITY;
@@ -279,8 +290,13 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
           }
           if (lane < EX_WARPS && head < k && cd == bd && ci == bi && bi != INT64_MAX) ++head;
           if (lane == 0) {
-            od[o] = bd;
-            oi[o] = bi;
+            if (direct) {
+              out_dist[orow * k + o] = (float)bd;
+              out_idx[orow * k + o] = (bi == INT64_MAX) ? -1 : bi + index_offset;
+            } else {
+              od[o] = bd;
+              oi[o] = bi;
+            }
           }
         }
       }
@@ -293,7 +309,11 @@ __global__ void __launch_bounds__(256) knn_exact_merge_kernel(
     const int64_t* __restrict__ row_list, const int* __restrict__ row_count_dev, int64_t row_count_host,
     int64_t slot_base, int64_t slot_cap, int64_t index_offset, float* __restrict__ out_dist,
     int64_t* __restrict__ out_idx) {
-  const int64_t total = row_count_dev ? (int64_t)min((int64_t)*row_count_dev, slot_cap) : row_count_host;
+  int64_t total = row_count_host;
+  if (row_count_dev) {
+    total = (int64_t)*row_count_dev;
+    if (total > slot_cap) return;   // the direct regime already wrote these rows
+  }
   __shared__ double sd[256];
   __shared__ int64_t si[256];
   for (int64_t slot = blockIdx.x; slot < total; slot += gridDim.x) {
@@ -370,8 +390,16 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
   dim3 grid(n_chunks, gy);
   knn_exact_partial_kernel<<<grid, EX_WARPS * 32, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, row_list,
                                                                    row_count_dev, row_count_host, slot_base,
-                                                                   slot_cap, part_d, part_i);
+                                                                   slot_cap, part_d, part_i, 0, index_offset, out_dist,
+                                                                   out_idx);
   KNN_LAUNCH_CHECK();
+  if (row_count_dev) {
+    // many-rows regime (exits immediately unless the device-side count exceeds slot_cap)
+    knn_exact_partial_kernel<<<dim3(1, 148 * 2), EX_WARPS * 32, smem, stream>>>(
+        q, qn, n_query, p, pn, n_pool, dim, k, row_list, row_count_dev, row_count_host, slot_base, slot_cap, part_d,
+        part_i, 1, index_offset, out_dist, out_idx);
+    KNN_LAUNCH_CHECK();
+  }
   int64_t mg = row_count_dev ? slot_cap : row_count_host;
   if (mg > 148 * 8) mg = 148 * 8;
   if (mg < 1) mg = 1;

@@ -124,6 +124,23 @@ def test_knn_search_ties_and_duplicates(ops):
     assert np.array_equal(np.sort(idx2.cpu().numpy()[rows], 1), np.sort(o2_idx[rows, :4], 1))
 
 
+def test_knn_search_many_undecidable_rows(ops):
+    """> 1024 rows whose error window holds more candidates than the log: the device-side row list
+    exceeds the chunked fallback's capacity and the direct regime of the exact kernel takes over."""
+    base = synth.ar1_frames(3000, seed=35)
+    p = np.concatenate([base, base, base])                        # 9000 rows
+    p[100:6100] = p[5]                                            # 6001 identical pool rows
+    rs = np.random.RandomState(1)
+    q = (p[5][None, :] + 0.05 * rs.standard_normal((1300, 1024))).astype(np.float32)
+    qp, pp = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p))
+    dist, idx, stats = ops.knn_search(qp, pp, 4, return_stats=True)
+    assert int(stats[0]) > 1024, stats.tolist()
+    e_dist, e_idx = ops.knn_exact(qp, pp, 4)
+    assert torch.equal(idx, e_idx)
+    assert torch.allclose(dist, e_dist, atol=2e-7, rtol=0)
+    assert idx.min() >= 0 and idx.max() < 9000
+
+
 def test_knn_search_index_offset_and_merge(ops):
     """two pool shards searched separately and merged == one search (C1 merge rule)"""
     from knn_svc_b200 import sharded
