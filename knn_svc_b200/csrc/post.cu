@@ -150,7 +150,13 @@ __global__ void __launch_bounds__(256) frame_baseline_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
+// 16 warps: warp w scores candidate (w >> 1) over half (w & 1) of the feature dimension, so one
+// batch of 6 rows x 4 float4 loads per lane covers a 1024-dim row and a step costs about one
+// L2 round trip plus ~600 instructions per warp.
+constexpr int CC_WARPS = 2 * CC_C;
+constexpr int CC_ACC = 6;  // |c|^2, d2(src,c), d2(prev_j,c) j=0..3
+
+__global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
     const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
     int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
     const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
@@ -159,15 +165,13 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
   const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
   if (f_end <= f_begin) return;
   const bool use_f0 = src_f0 != nullptr;
-  const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+  const bool vec4 = (dim % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(pool) & 15) == 0);
 
   __shared__ int64_t s_prev[CC_K];
   __shared__ double s_prev_n2[CC_K];
   __shared__ int64_t s_cand[CC_C];
-  __shared__ double s_cand_n2[CC_C];
-  __shared__ double s_match[CC_C];
-  __shared__ double s_concat[CC_K][CC_C];
+  __shared__ double s_part[CC_WARPS][CC_ACC];
   __shared__ double s_w;
 
   if (threadIdx.x < CC_K) {
@@ -187,13 +191,26 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
     n = warp_sum(n);
     if (lane == 0) s_prev_n2[warp] = n;
   }
+  // values that do not depend on the recurrence are fetched one step ahead
+  int64_t next_idx = 0;
+  double next_base = 0.0, next_n2 = 0.0, next_lsrc = 0.0;
+  if (f_begin + 1 < f_end) {
+    if (threadIdx.x < CC_K) next_idx = idx[(f_begin + 1) * CC_K + threadIdx.x];
+    if (threadIdx.x < CC_C) {
+      next_base = base_all[f_begin + 1];
+      next_n2 = src_n2[f_begin + 1];
+      if (use_f0) next_lsrc = log2((double)__ldg(src_f0 + f_begin + 1) + 1e-5);
+    }
+  }
   __syncthreads();
 
+  const int cand_id = warp >> 1, half = warp & 1;
   for (int64_t i = f_begin + 1; i < f_end; ++i) {
+    const double base = next_base, sn2 = next_n2, lsrc = next_lsrc;   // meaningful on threads < CC_C
     if (threadIdx.x < CC_C) {
       int64_t c;
       if (threadIdx.x < CC_K) {
-        c = idx[i * CC_K + threadIdx.x];
+        c = next_idx;
       } else {
         c = s_prev[threadIdx.x - CC_K] + 1;
         if (c >= n_pool) c = n_pool - 1;
@@ -201,9 +218,18 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
       s_cand[threadIdx.x] = c;
     }
     __syncthreads();
+    if (i + 1 < f_end) {  // issue next step's independent loads now; they land while this step computes
+      if (threadIdx.x < CC_K) next_idx = idx[(i + 1) * CC_K + threadIdx.x];
+      if (threadIdx.x < CC_C) {
+        next_base = base_all[i + 1];
+        next_n2 = src_n2[i + 1];
+        if (use_f0) next_lsrc = log2((double)__ldg(src_f0 + i + 1) + 1e-5);
+      }
+    }
+    double lcand = 0.0;
+    if (use_f0 && threadIdx.x < CC_C) lcand = log2((double)__ldg(pool_f0 + s_cand[threadIdx.x]) + 1e-5);
     {
-      // warp w scores candidate w against the query frame and the 4 previous selections
-      const float* crow = pool + s_cand[warp] * dim;
+      const float* crow = pool + s_cand[cand_id] * dim;
       const float* srow = src + i * dim;
       const float* p0 = pool + s_prev[0] * dim;
       const float* p1 = pool + s_prev[1] * dim;
@@ -211,20 +237,21 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
       const float* p3 = pool + s_prev[3] * dim;
       double nc = 0, dm = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
       if (vec4) {
-        const float4* c4 = reinterpret_cast<const float4*>(crow);
-        const float4* s4 = reinterpret_cast<const float4*>(srow);
-        const float4* q0 = reinterpret_cast<const float4*>(p0);
-        const float4* q1 = reinterpret_cast<const float4*>(p1);
-        const float4* q2 = reinterpret_cast<const float4*>(p2);
-        const float4* q3 = reinterpret_cast<const float4*>(p3);
-        const int n4 = dim / 4;
-        constexpr int U = 4;  // 6 rows x U float4 loads issued before any use: ~one L2 round trip per batch
-        for (int c0 = lane; c0 < n4; c0 += 32 * U) {
+        const int n4h = dim / 8;                 // float4s in this warp's half of the row
+        const int off = half * n4h;
+        const float4* c4 = reinterpret_cast<const float4*>(crow) + off;
+        const float4* s4 = reinterpret_cast<const float4*>(srow) + off;
+        const float4* q0 = reinterpret_cast<const float4*>(p0) + off;
+        const float4* q1 = reinterpret_cast<const float4*>(p1) + off;
+        const float4* q2 = reinterpret_cast<const float4*>(p2) + off;
+        const float4* q3 = reinterpret_cast<const float4*>(p3) + off;
+        constexpr int U = 4;  // 6 rows x U float4 loads issued before any use
+        for (int c0 = lane; c0 < n4h; c0 += 32 * U) {
           float4 cv[U], sv[U], a0[U], a1[U], a2[U], a3[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int c = c0 + 32 * u;
-            const bool ok = c < n4;
+            const bool ok = c < n4h;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             cv[u] = ok ? __ldg(c4 + c) : z;
             sv[u] = ok ? __ldg(s4 + c) : z;
@@ -255,7 +282,8 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
           }
         }
       } else {
-        for (int c = lane; c < dim; c += 32) {
+        const int h0 = half * ((dim + 1) / 2), h1 = half ? dim : (dim + 1) / 2;
+        for (int c = h0 + lane; c < h1; c += 32) {
           const float cv = __ldg(crow + c), sv = __ldg(srow + c);
           const float a0 = __ldg(p0 + c), a1 = __ldg(p1 + c), a2 = __ldg(p2 + c), a3 = __ldg(p3 + c);
           nc += (double)(cv * cv);
@@ -269,24 +297,24 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
       nc = warp_sum(nc); dm = warp_sum(dm);
       d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
       if (lane == 0) {
-        s_cand_n2[warp] = nc;
-        s_match[warp] = cosd_from(dm, src_n2[i], nc);
-        s_concat[0][warp] = cosd_from(d0, s_prev_n2[0], nc);
-        s_concat[1][warp] = cosd_from(d1, s_prev_n2[1], nc);
-        s_concat[2][warp] = cosd_from(d2, s_prev_n2[2], nc);
-        s_concat[3][warp] = cosd_from(d3, s_prev_n2[3], nc);
+        s_part[warp][0] = nc; s_part[warp][1] = dm;
+        s_part[warp][2] = d0; s_part[warp][3] = d1; s_part[warp][4] = d2; s_part[warp][5] = d3;
       }
     }
     __syncthreads();
     if (warp == 0) {
-      const double base = base_all[i];  // 2 * dist(src[i-1], src[i])   (lib_ongaku_test.py:310)
       double w = s_w;
       if (use_f0 && !(base < 0.08)) w = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
-      double total = INFINITY;
+      double total = INFINITY, my_n2 = 0.0;
       if (lane < CC_C) {
+        double v[CC_ACC];
+#pragma unroll
+        for (int a = 0; a < CC_ACC; ++a) v[a] = s_part[2 * lane][a] + s_part[2 * lane + 1][a];
+        my_n2 = v[0];
+        const double match = cosd_from(v[1], sn2, my_n2);
         double cc[CC_K];
 #pragma unroll
-        for (int j = 0; j < CC_K; ++j) cc[j] = s_concat[j][lane];
+        for (int j = 0; j < CC_K; ++j) cc[j] = cosd_from(v[2 + j], s_prev_n2[j], my_n2);
         if (use_f0) {
           if (base < 0.08) {
 #pragma unroll
@@ -302,12 +330,8 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
         double lo01 = fmin(cc[0], cc[1]), hi01 = fmax(cc[0], cc[1]);
         double lo23 = fmin(cc[2], cc[3]), hi23 = fmax(cc[2], cc[3]);
         double med = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
-        total = w * med + s_match[lane];
-        if (use_f0) {
-          const double lc = log2((double)__ldg(pool_f0 + s_cand[lane]) + 1e-5);
-          const double ls = log2((double)__ldg(src_f0 + i) + 1e-5);
-          total += fabs(lc - ls);
-        }
+        total = w * med + match;
+        if (use_f0) total += fabs(lcand - lsrc);
       }
       int rank = 0;
 #pragma unroll
@@ -315,11 +339,12 @@ __global__ void __launch_bounds__(CC_C * 32) concat_cost_kernel(
         const double tj = __shfl_sync(0xffffffffu, total, j);
         rank += (tj < total) || (tj == total && j < lane);
       }
+      __syncwarp();  // every lane has read s_prev_n2 before it is overwritten
       if (lane < CC_C && rank < CC_K) {
         const int64_t sel = s_cand[lane];
         out_idx[i * CC_K + rank] = sel;
         s_prev[rank] = sel;
-        s_prev_n2[rank] = s_cand_n2[lane];
+        s_prev_n2[rank] = my_n2;
       }
       if (lane == 0) s_w = w;
     }
@@ -337,7 +362,7 @@ int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, 
   if (grid > 148 * 16) grid = 148 * 16;
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
-  concat_cost_kernel<<<n_utt, CC_C * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
+  concat_cost_kernel<<<n_utt, CC_WARPS * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
                                                       utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
   return 0;

@@ -19,7 +19,15 @@ namespace knnsvc {
 
 constexpr int WF_K = 4;
 constexpr int WF_V = 2 * WF_K;         // vectors per Gram block
-constexpr int WF_THREADS = 1024;
+// The 8x8 Gram block [[A, B], [B', C]] is symmetric: 10 + 16 + 10 = 36 unique entries, stored
+// ENTRY-MAJOR (gram[e * n_pairs + t]) so that consecutive threads (frames) read consecutive
+// addresses in the optimisation loop.
+constexpr int WF_E = 36;
+__host__ __device__ constexpr int wf_tri(int i, int j) { return i * 4 - i * (i - 1) / 2 + (j - i); }  // i <= j < 4
+__host__ __device__ constexpr int wf_a(int i, int j) { return i <= j ? wf_tri(i, j) : wf_tri(j, i); }
+__host__ __device__ constexpr int wf_b(int i, int j) { return 10 + i * 4 + j; }                        // A-row i, C-col j
+__host__ __device__ constexpr int wf_c(int i, int j) { return 26 + (i <= j ? wf_tri(i, j) : wf_tri(j, i)); }
+constexpr int WF_THREADS = 512;
 constexpr int WF_SMEM_FRAMES = 10240;  // frames whose weights fit in shared memory
 
 // ---- Gram build: one CTA per frame pair t (frames t, t+1); warp i owns row i of both blocks
@@ -52,10 +60,18 @@ __global__ void __launch_bounds__(WF_V * 32) weight_gram_kernel(const int64_t* _
       for (int j = 0; j < WF_V; ++j) acc[j] += a * (double)__ldg(synth + rows[b][j] * dim + c);
     }
   }
+  const int64_t n_pairs = n_query - 1;
 #pragma unroll
   for (int j = 0; j < WF_V; ++j) {
     const double v = warp_sum(acc[j]);
-    if (lane == 0) gram[(t * WF_V + warp) * WF_V + j] = v;
+    if (lane == 0) {
+      const int i = warp;
+      int e = -1;
+      if (i < 4 && j < 4 && j >= i) e = wf_tri(i, j);
+      else if (i < 4 && j >= 4) e = wf_b(i, j - 4);
+      else if (i >= 4 && j >= i) e = 26 + wf_tri(i - 4, j - 4);
+      if (e >= 0) gram[(int64_t)e * n_pairs + t] = v;
+    }
   }
 }
 
@@ -89,6 +105,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
   __shared__ double s_red[WF_THREADS / 32];
   __shared__ double s_loss;
   __shared__ int s_ctl;  // bit0: stop, bit1: snapshot
+  __shared__ float s_step_size, s_bc2_sqrt;
   volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t T = n_query;
@@ -119,43 +136,38 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       for (int k = 0; k < 4; ++k) wbuf[t * 4 + k] = w[k];
     }
     __syncthreads();
-    // ---- loss and dL/dw from the Gram blocks (kept in registers until the step)
+    // ---- loss and dL/dw from the Gram blocks
+    const int64_t NP = T - 1;
     double part = 0.0;
     for (int64_t t = tid; t < T; t += WF_THREADS) {
       double wt[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) wt[k] = (double)wbuf[t * 4 + k];
       double g[4] = {0.0, 0.0, 0.0, 0.0};
-      if (t >= 1) {  // pair t-1: this frame is the "t+1" member, rows 0..3 of G u
-        const double* G = gram + (t - 1) * WF_V * WF_V;
-        double u[8];
+      if (t >= 1) {  // pair t-1: this frame is the "t+1" member -> rows 0..3 of G u = A w[t] - B w[t-1]
+        const double* G = gram + (t - 1);
+        double wp[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          u[k] = wt[k];
-          u[4 + k] = -(double)wbuf[(t - 1) * 4 + k];
-        }
+        for (int k = 0; k < 4; ++k) wp[k] = (double)wbuf[(t - 1) * 4 + k];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double y = 0.0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) y += G[r * 8 + c] * u[c];
+          for (int c = 0; c < 4; ++c) y += G[(int64_t)wf_a(r, c) * NP] * wt[c] - G[(int64_t)wf_b(r, c) * NP] * wp[c];
           part += wt[r] * y;
           g[r] += y;
         }
       }
-      if (t + 1 < T) {  // pair t: this frame is the "t" member, rows 4..7 of G u
-        const double* G = gram + t * WF_V * WF_V;
-        double u[8];
+      if (t + 1 < T) {  // pair t: this frame is the "t" member -> rows 4..7 of G u = B' w[t+1] - C w[t]
+        const double* G = gram + t;
+        double wn[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          u[k] = (double)wbuf[(t + 1) * 4 + k];
-          u[4 + k] = -wt[k];
-        }
+        for (int k = 0; k < 4; ++k) wn[k] = (double)wbuf[(t + 1) * 4 + k];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double y = 0.0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) y += G[(4 + r) * 8 + c] * u[c];
+          for (int c = 0; c < 4; ++c) y += G[(int64_t)wf_b(c, r) * NP] * wn[c] - G[(int64_t)wf_c(r, c) * NP] * wt[c];
           part -= wt[r] * y;
           g[r] -= y;
         }
@@ -190,6 +202,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       if (ctl & 1) stop_iter = it;
       s_ctl = ctl;
       s_loss = loss;
+      const int step = it + 1;
+      s_step_size = (float)((double)0.1 / (1.0 - pow((double)0.9, (double)step)));
+      s_bc2_sqrt = (float)sqrt(1.0 - pow((double)0.999, (double)step));
     }
     __syncthreads();
     const int ctl = s_ctl;
@@ -199,11 +214,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
         for (int k = 0; k < 4; ++k) st.best[t * 4 + k] = st.theta[t * 4 + k];
     if (ctl & 1) break;
     // ---- Adam (amsgrad) step on the logits
-    const int step = it + 1;
-    const double bc1 = 1.0 - pow((double)0.9, (double)step);
-    const double bc2 = 1.0 - pow((double)0.999, (double)step);
-    const float step_size = (float)((double)0.1 / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     (void)lr;
     for (int64_t t = tid; t < T; t += WF_THREADS) {
       float w[4], gw[4];
@@ -253,7 +264,7 @@ __global__ void uniform_weights_kernel(float* w, int64_t n, float v) {
 
 size_t weight_fit_workspace_bytes(int64_t n_query, int k) {
   if (n_query < 2) return 256;
-  size_t gram = (size_t)(n_query - 1) * WF_V * WF_V * sizeof(double);
+  size_t gram = (size_t)(n_query - 1) * WF_E * sizeof(double);
   size_t state = (size_t)n_query * k * sizeof(float) * 7;  // theta, m, v, vmax, best, grad scratch, wglob
   return gram + state + 1024;
 }
@@ -270,7 +281,7 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   }
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   double* gram = reinterpret_cast<double*>(ws);
-  float* f = reinterpret_cast<float*>(ws + (size_t)(n_query - 1) * WF_V * WF_V * sizeof(double));
+  float* f = reinterpret_cast<float*>(ws + (size_t)(n_query - 1) * WF_E * sizeof(double));
   WfState st;
   const size_t n4 = (size_t)n_query * 4;
   st.theta = f;
