@@ -29,6 +29,8 @@ int opt_cta_group() {
   return g_opt_cta_group;
 }
 int opt_bf16() { return g_opt_bf16; }
+static int g_opt_spin_ns = 0;
+int opt_spin_ns() { return g_opt_spin_ns; }
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -162,6 +164,11 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "cta_group") == 0) {
     KNN_CHECK_ARG(value == 1 || value == 2, -1, "set_option: cta_group must be 1 or 2");
     g_opt_cta_group = value;
+    return 0;
+  }
+  if (strcmp(name, "spin_sleep_ns") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= 100000, -1, "set_option: spin_sleep_ns out of range");
+    g_opt_spin_ns = value;
     return 0;
   }
   if (strcmp(name, "bf16_operands") == 0) {

@@ -7,7 +7,8 @@ namespace knnsvc {
 
 // ---- tuning options (capi.cu): diagnostic switches, see knnsvc_set_option
 int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
-int opt_bf16();        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
+int opt_bf16();
+int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
 
 // ---- rows.cu
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,

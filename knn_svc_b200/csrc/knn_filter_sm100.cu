@@ -26,6 +26,7 @@
 // and LOGS every column with s~ > tau_k - 2*eps.  Every true top-k member is in
 // the log; knn_rescore re-scores the log exactly from the fp32 rows.
 #include <cuda.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -104,6 +105,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// wait used by the single-lane producer / MMA loops: optional nanosleep between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  if (sleep_ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(sleep_ns);
+  }
 }
 // TMA tile load; with CTAS == 2 the completion bytes are credited to `bar`, a shared::cluster
 // address that names the LEADER CTA's barrier, whichever CTA of the pair issues the copy.
@@ -191,29 +213,49 @@ struct InstrDesc {
 
 struct RowState {
   float tau_lo;  // scaled: log everything strictly above this
-  float kth;     // scaled: k-th largest value seen (min of the list), -inf until k values seen
-  int kpos;      // slot of `kth` in the list
+  float kth;     // scaled lower bound of the k-th largest value seen (kEmpty until k values seen)
+  int kpos;      // slot holding `kth`
   int cnt;       // entries in this row's log (cap+1 = overflowed)
 };
+
+constexpr float kEmpty = -3.0e38f;   // "no value yet" (finite, so the packed key decodes cleanly)
+constexpr int kSlots = kMaxK;        // list slots scanned per update (slots >= k hold INT_MAX)
+
+// Order-preserving map between fp32 bit patterns and signed ints (an involution).
+__device__ __forceinline__ int mono(int b) { return b ^ ((b >> 31) & 0x7fffffff); }
+// Key of a list entry: the value rounded DOWN to 27 significant bits with the slot id in the low
+// 5 bits, so one min-reduction over the keys yields both the k-th value and where it lives.
+// Rounding down keeps the tracked k-th value a lower bound of the true one (the filter stays a
+// superset); the loss is < 4e-6 of the value, against an error window of 2.4e-3.
+__device__ __forceinline__ int pack_key(float v, int slot) { return (mono(__float_as_int(v)) & ~31) | slot; }
+__device__ __forceinline__ float key_value(int key) { return __int_as_float(mono(key & ~31)); }
 
 // Rare path: one accumulator value passed the register threshold.  Logs it and,
 // if it also beats the running k-th best, replaces that entry of the row's
 // UNSORTED top-k list in shared memory ([slot][row]: the 32 rows of a warp hit
-// 32 banks) and rescans the k slots for the new minimum — k independent loads
-// instead of an insertion sort's dependent chain.
-__device__ __noinline__ RowState filter_insert(RowState st, float v, int col, float* __restrict__ topv_row, int k,
+// 32 banks) and takes the minimum over the 32 slot keys — independent loads and a
+// min tree instead of an insertion sort's dependent chain.
+__device__ __noinline__ RowState filter_insert(RowState st, float v, int col, int* __restrict__ keys_row, int k,
                                                float* __restrict__ log_val, int* __restrict__ log_idx, int cap,
                                                float window_scaled) {
   if (st.cnt == cap) {
     // compact in place: entries below the current threshold can never be needed (tau only rises)
     int n = 0;
-    for (int e = 0; e < cap; ++e) {
-      float lv = log_val[e];
-      if (lv * kDotScale > st.tau_lo) {
-        int li = log_idx[e];
-        log_val[n] = lv;
-        log_idx[n] = li;
-        ++n;
+    for (int e0 = 0; e0 < cap; e0 += 8) {
+      float lv[8];
+      int li[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        lv[u] = log_val[e0 + u];
+        li[u] = log_idx[e0 + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (lv[u] * kDotScale > st.tau_lo) {
+          log_val[n] = lv[u];
+          log_idx[n] = li[u];
+          ++n;
+        }
       }
     }
     st.cnt = n;
@@ -226,19 +268,17 @@ __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, fl
     st.cnt = cap + 1;  // genuine overflow: more than `cap` candidates inside the window
   }
   if (v > st.kth) {
-    topv_row[st.kpos * BM] = v;
-    float mn = topv_row[0];
-    int mp = 0;
-    for (int j = 1; j < k; ++j) {
-      const float t = topv_row[j * BM];
-      if (t < mn) {
-        mn = t;
-        mp = j;
-      }
-    }
-    st.kth = mn;
-    st.kpos = mp;
-    st.tau_lo = mn - window_scaled;  // -inf until k values have been seen
+    keys_row[st.kpos * BM] = pack_key(v, st.kpos);
+    int key[kSlots];
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) key[j] = keys_row[j * BM];
+#pragma unroll
+    for (int w = kSlots / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int j = 0; j < w; ++j) key[j] = min(key[j], key[j + w]);
+    st.kth = key_value(key[0]);
+    st.kpos = key[0] & 31;
+    st.tau_lo = st.kth - window_scaled;  // stays ~-3e38 until k values have been seen
   }
   return st;
 }
@@ -251,7 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
                   int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
-                  float* __restrict__ seg_top, uint32_t idesc) {
+                  float* __restrict__ seg_top, uint32_t idesc, uint32_t spin_ns) {
   using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
@@ -310,7 +350,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int pt = t0; pt < t1; ++pt) {
           const int p_row = pt * BN + (int)cta_rank * L::B_ROWS;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(sbase + L::empty_bar + stage * 8, phase ^ 1);
+            mbar_wait_backoff(sbase + L::empty_bar + stage * 8, phase ^ 1, spin_ns);
             const uint32_t full_local = sbase + L::full_bar + stage * 8;
             uint32_t full = full_local;
             if constexpr (CTAS == 2) {
@@ -342,11 +382,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int pt = t0; pt < t1; ++pt, ++tile_n) {
           const uint32_t buf = tile_n & 1;
           const uint32_t buf_phase = (tile_n >> 1) & 1;
-          mbar_wait(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1);
+          mbar_wait_backoff(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1, spin_ns);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(sbase + L::full_bar + stage * 8, phase);
+            mbar_wait_backoff(sbase + L::full_bar + stage * 8, phase, spin_ns);
             tcgen05_fence_after();
             const uint32_t a_addr = sbase + L::ring + stage * L::STAGE_BYTES;
             const uint64_t da = make_smem_desc(a_addr);
@@ -370,7 +410,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ===================== epilogue: streaming candidate filter =====================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside this CTA's tile
-    float* topv_row = reinterpret_cast<float*>(smem + L::topv) + row_in_tile;
+    int* keys_row = reinterpret_cast<int*>(smem + L::topv) + row_in_tile;   // [kSlots][BM] packed keys
     const float window_scaled = 2.0f * kFilterEps * kDotScale;
     uint32_t tile_n = 0;
     for (int u = worker; u < n_units; u += n_workers) {
@@ -378,10 +418,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
       const int64_t row = (int64_t)(qt * CTAS + (int)cta_rank) * BM + row_in_tile;
       const bool row_ok = row < n_query;
-      for (int j = 0; j < k; ++j) topv_row[j * BM] = -INFINITY;
+      for (int j = 0; j < kSlots; ++j) keys_row[j * BM] = j < k ? pack_key(kEmpty, j) : INT_MAX;
       RowState st;
-      st.tau_lo = row_ok ? -INFINITY : INFINITY;
-      st.kth = -INFINITY;
+      st.tau_lo = row_ok ? kEmpty : INFINITY;
+      st.kth = kEmpty;
       st.kpos = 0;
       st.cnt = 0;
       const int64_t slot = row * n_seg + seg;
@@ -408,7 +448,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             for (int j = 0; j < 32; ++j) {
               const float v = __uint_as_float(r[j]);
               if (v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
-                st = filter_insert(st, v, cbase + j, topv_row, k, lv, li, cap, window_scaled);
+                st = filter_insert(st, v, cbase + j, keys_row, k, lv, li, cap, window_scaled);
             }
           }
         }
@@ -421,7 +461,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       if (row_ok) {
         log_cnt[slot] = st.cnt;
-        for (int j = 0; j < k; ++j) seg_top[slot * k + j] = topv_row[j * BM] * kDotUnscale;
+        for (int j = 0; j < k; ++j) seg_top[slot * k + j] = key_value(keys_row[j * BM]) * kDotUnscale;
       }
     }
   }
@@ -542,7 +582,7 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS>, map_q, map_p, n_query, n_pool, k_blocks, k, pl.n_qtiles,
-                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, idesc));
+                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, idesc, (uint32_t)opt_spin_ns()));
   return 0;
 }
 

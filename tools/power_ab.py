@@ -18,14 +18,18 @@ def clocks():
                          capture_output=True, text=True).stdout.strip()
     return out
 
+K = int(os.environ.get("K", 4))
 configs = [("cta1 fp16", 1, 0), ("cta2 fp16", 2, 0), ("cta1 bf16", 1, 1), ("cta2 bf16", 2, 1)]
+if os.environ.get("CONFIGS"):
+    configs = [c for c in configs if c[0] in os.environ["CONFIGS"].split(",")]
 reps = int(os.environ.get("REPS", 3))
 steps = int(os.environ.get("STEPS", 4))
 for rep in range(reps):
     for name, cg, bf in configs:
         lib.knnsvc_set_option(b"cta_group", cg); lib.knnsvc_set_option(b"bf16_operands", bf)
+        lib.knnsvc_set_option(b"spin_sleep_ns", int(os.environ.get("SPIN", 0)))
         qp, pp = ops.prepare_rows(q, check=False), ops.prepare_rows(p, check=False)
-        ops.knn_search(qp, pp, 4); torch.cuda.synchronize()
+        ops.knn_search(qp, pp, K); torch.cuda.synchronize()
         lib.knnsvc_filter_timing(1)
         samples = []
         stop = False
@@ -35,8 +39,9 @@ for rep in range(reps):
         th = threading.Thread(target=samp); th.start()
         t0 = time.time()
         for _ in range(steps):
-            d, i, st = ops.knn_search(qp, pp, 4, return_stats=True)
+            d, i, st = ops.knn_search(qp, pp, K, return_stats=True)
         torch.cuda.synchronize()
+        wall = (time.time() - t0) / steps * 1e3
         stop = True; th.join()
         buf = (ctypes.c_float * 256)()
         n = lib.knnsvc_filter_timing_collect(ctypes.cast(buf, ctypes.c_void_p), 256)
@@ -45,4 +50,4 @@ for rep in range(reps):
         mhz = [float(s.split(",")[0]) for s in samples if s]
         pw = [float(s.split(",")[1]) for s in samples if s]
         print(f"rep{rep} {name}: filter {ms:8.2f} ms  {2.0*T*NP*1024/ms/1e9:7.1f} TFLOP/s  clk med {statistics.median(mhz):.0f} MHz  pw med {statistics.median(pw):.0f} W"
-              f"  temp {samples[-1].split(',')[2] if samples else '?'}  flagged {int(st[0])} survivors {int(st[2])}", flush=True)
+              f"  temp {samples[-1].split(',')[2] if samples else '?'}  flagged {int(st[0])} logged {int(st[1])} survivors {int(st[2])} search wall {wall:.1f} ms", flush=True)
