@@ -29,7 +29,7 @@ int opt_cta_group() {
   return g_opt_cta_group;
 }
 int opt_bf16() { return g_opt_bf16; }
-static int g_opt_spin_ns = 0;
+static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
 int opt_spin_ns() { return g_opt_spin_ns; }
 
 static std::atomic<long long> g_launches{0};
@@ -52,6 +52,9 @@ struct KnnWorkspace {
   int* log_idx;
   int* log_cnt;
   float* seg_top;
+  float* seg_kth;
+  int* seg_flag;
+  size_t seg_flag_bytes;
   int64_t* flag_list;
   int* counters;  // [0] flag count, [1..8] stats
   void* exact_partial;
@@ -72,6 +75,9 @@ KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const Fil
   w.log_idx = reinterpret_cast<int*>(take(slots * pl.cap * sizeof(int)));
   w.log_cnt = reinterpret_cast<int*>(take(slots * sizeof(int)));
   w.seg_top = reinterpret_cast<float*>(take(slots * k * sizeof(float)));
+  w.seg_kth = reinterpret_cast<float*>(take(slots * sizeof(float)));
+  w.seg_flag_bytes = filter_flag_count(pl) * sizeof(int);
+  w.seg_flag = reinterpret_cast<int*>(take(w.seg_flag_bytes));
   w.flag_list = reinterpret_cast<int64_t*>(take((size_t)n_query * sizeof(int64_t)));
   w.counters = reinterpret_cast<int*>(take(16 * sizeof(int)));
   w.exact_partial = take(exact_partial_bytes(kFlagCap, n_pool, k));
@@ -134,10 +140,11 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
   KnnWorkspace w = carve(workspace, n_query, n_pool, k, pl);
   KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
   KNN_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), stream));
+  KNN_CUDA(cudaMemsetAsync(w.seg_flag, 0, w.seg_flag_bytes, stream));
   const bool timed = g_timing && g_ev_n < kTimingSlots;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                             stream);
+                             w.seg_kth, w.seg_flag, stream);
   if (rc) return rc;
   if (timed) {
     KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));

@@ -29,7 +29,8 @@ struct FilterPlan {
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
-                      cudaStream_t stream);
+                      float* seg_kth, int* seg_flag, cudaStream_t stream);
+size_t filter_flag_count(const FilterPlan& pl);
 
 // ---- knn_select.cu
 constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb

@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
                   int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
-                  float* __restrict__ seg_top, uint32_t idesc, uint32_t spin_ns) {
+                  float* __restrict__ seg_top, float* __restrict__ seg_kth, int* __restrict__ seg_flag,
+                  uint32_t idesc, uint32_t spin_ns) {
   using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
@@ -420,10 +421,26 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const bool row_ok = row < n_query;
       for (int j = 0; j < kSlots; ++j) keys_row[j * BM] = j < k ? pack_key(kEmpty, j) : INT_MAX;
       RowState st;
-      st.tau_lo = row_ok ? kEmpty : INFINITY;
       st.kth = kEmpty;
       st.kpos = 0;
       st.cnt = 0;
+      // Warm start: any finished segment's k-th best similarity is a lower bound of the row's
+      // global k-th best, so nothing more than 2*eps below it can be a true neighbour.  Units are
+      // ordered segment-major, so by the time segment s of a row tile starts, its earlier segments
+      // have usually been published (flag written after the values, both fenced).
+      float known = kEmpty;
+      const int flag_base = ((qt * CTAS + (int)cta_rank) * 4 + quad) * n_seg;
+      if (row_ok) {
+        for (int s2 = 0; s2 < n_seg; ++s2) {
+          if (s2 == seg) continue;
+          if (*reinterpret_cast<volatile int*>(seg_flag + flag_base + s2)) {
+            __threadfence();
+            known = fmaxf(known, __ldcg(seg_kth + row * n_seg + s2));
+          }
+        }
+      }
+      st.tau_lo = row_ok ? known * kDotScale - window_scaled : INFINITY;
+      const float warm_lo = st.tau_lo;
       const int64_t slot = row * n_seg + seg;
       float* lv = log_val + (row_ok ? slot * cap : 0);
       int* li = log_idx + (row_ok ? slot * cap : 0);
@@ -442,13 +459,25 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           float mx = __uint_as_float(r[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          if (mx > st.tau_lo) {
+          if (__any_sync(0xffffffffu, mx > st.tau_lo)) {
+            // Rare path, warp-cooperative: per-lane bitmask of passing columns, OR-reduced over the
+            // warp; each column in the union is re-read from TMEM (one value per lane, uniform
+            // column) so no register array has to be indexed dynamically.
             const int cbase = col0 + c * 32;
+            uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > st.tau_lo ? 1u : 0u) << j;
+            uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
+            while (umask) {
+              const int j = __ffs(umask) - 1;
+              umask &= umask - 1;
+              uint32_t one;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(one) : "r"(taddr + c * 32 + j) : "memory");
+              tmem_ld_wait();
+              const float v = __uint_as_float(one);
+              if (((mask >> j) & 1u) && v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
                 st = filter_insert(st, v, cbase + j, keys_row, k, lv, li, cap, window_scaled);
+              st.tau_lo = fmaxf(st.tau_lo, warm_lo);
             }
           }
         }
@@ -462,7 +491,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (row_ok) {
         log_cnt[slot] = st.cnt;
         for (int j = 0; j < k; ++j) seg_top[slot * k + j] = key_value(keys_row[j * BM]) * kDotUnscale;
+        seg_kth[slot] = st.kth * kDotUnscale;
       }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(seg_flag + flag_base + seg) = 1;
     }
   }
 
@@ -556,10 +589,12 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   return pl;
 }
 
+size_t filter_flag_count(const FilterPlan& pl) { return (size_t)pl.n_qtiles * pl.ctas * 4 * pl.n_seg; }
+
 template <int CTAS>
 static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
                           int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
-                          float* seg_top, cudaStream_t stream) {
+                          float* seg_top, float* seg_kth, int* seg_flag, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -582,13 +617,14 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS>, map_q, map_p, n_query, n_pool, k_blocks, k, pl.n_qtiles,
-                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, idesc, (uint32_t)opt_spin_ns()));
+                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth, seg_flag, idesc,
+                              (uint32_t)opt_spin_ns()));
   return 0;
 }
 
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
-                      cudaStream_t stream) {
+                      float* seg_kth, int* seg_flag, cudaStream_t stream) {
   KNN_CHECK_ARG(dim_pad % BK == 0 && dim_pad > 0, -3, "dim_pad %d must be a positive multiple of %d", dim_pad, BK);
   KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -3, "k=%d outside [1,%d]", k, kMaxK);
   KNN_CHECK_ARG(n_pool < (int64_t)1 << 31, -3, "pool shard of %lld rows exceeds int32 column indices", (long long)n_pool);
@@ -599,9 +635,9 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   if (rc) return rc;
   if (pl.ctas == 2)
     return launch_variant<2>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
-                             stream);
+                             seg_kth, seg_flag, stream);
   return launch_variant<1>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
-                           stream);
+                           seg_kth, seg_flag, stream);
 }
 
 }  // namespace knnsvc
