@@ -82,7 +82,9 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
 long long knnsvc_launch_count(void);
 /* tuning / experiment switches: "cta_group" = 1|2 (CTAs per tcgen05.mma),
  * "bf16_operands" = 0|1 (bf16 instead of fp16 tensor-core operands; measurement only,
- * the error window is sized for fp16). */
+ * the error window is sized for fp16), "concat_staged" = 1|0 (shared-memory staged K5
+ * kernel where the row shape allows it, or the general kernel only),
+ * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes). */
 int knnsvc_set_option(const char* name, int value);
 int knnsvc_filter_timing(int enable);
 int knnsvc_filter_timing_collect(float* ms_host, int max_n);

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 LIB = PKG / "libknnsvc_b200.so"
-SOURCES = ["capi.cu", "rows.cu", "knn_filter_sm100.cu", "knn_select.cu", "post.cu", "weight_fit.cu", "harmonic.cu"]
+SOURCES = ["capi.cu", "rows.cu", "knn_filter_sm100.cu", "knn_select.cu", "post.cu", "concat_cost_sm100.cu", "weight_fit.cu", "harmonic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -39,11 +39,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "knnsvc_b200.h"]
     nvcc = _nvcc()
+    extra = os.environ.get("KNNSVC_NVCC_EXTRA", "").split()     # e.g. -DKNNSVC_K5_PROFILE (debugging aids)
 
     def compile_one(src: str):
         s, o = CSRC / src, OBJ / (src + ".o")
         if force or _stale(o, [s] + headers):
-            r = subprocess.run([nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)], capture_output=True, text=True)
+            r = subprocess.run([nvcc, *NVCC_FLAGS, *extra, "-c", str(s), "-o", str(o)], capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
             (OBJ / (src + ".ptxas.txt")).write_text(r.stderr)

@@ -32,6 +32,9 @@ int opt_bf16() { return g_opt_bf16; }
 static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
 int opt_spin_ns() { return g_opt_spin_ns; }
 
+static int g_opt_concat_staged = 1;
+int opt_concat_staged() { return g_opt_concat_staged; }
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -176,6 +179,10 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "spin_sleep_ns") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 100000, -1, "set_option: spin_sleep_ns out of range");
     g_opt_spin_ns = value;
+    return 0;
+  }
+  if (strcmp(name, "concat_staged") == 0) {
+    g_opt_concat_staged = value != 0;
     return 0;
   }
   if (strcmp(name, "bf16_operands") == 0) {

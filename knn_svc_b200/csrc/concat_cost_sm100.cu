@@ -1,0 +1,433 @@
+// K5, staged variant: greedy concatenation-cost re-selection with every row the
+// recurrence touches resident in shared memory BEFORE the step that needs it.
+// knn_with_concat_cost — lib_ongaku_test.py:270-369, K = 4.
+//
+// The recurrence is serial in the frame index, so one CTA walks one utterance and the
+// cost of a step is a latency chain.  The general kernel in post.cu pays an L2 round
+// trip inside that chain (the rows "previous selection + 1" are only known after the
+// previous step).  Here the chain never leaves the SM:
+//
+//   * The candidates of step s are idx[s] (known up front) and sel[s-1] + 1, and sel[s-1]
+//     is a subset of the 8 candidates of step s-1.  So the 8 rows cand[s-1] + 1 are a
+//     superset of what step s can need, and they are known one whole step early (as soon
+//     as sel[s-2] is).  A producer warp fetches them speculatively with TMA bulk copies
+//     (cp.async.bulk, one 4 KB row per instruction, completion on an mbarrier), together
+//     with the idx[s] rows, the query row s and the log2-f0 of all twelve rows.
+//   * Three generations of 13 rows live in shared memory: step s reads generation s
+//     (its candidates) and generation s-1 (the four previously selected rows, which were
+//     candidates there), while generation s+1 is in flight.  13 x 4 KB x 3 = 156 KB.
+//   * Eight compute warps split the feature dimension: a thread keeps all 8 candidates x
+//     {c.c, src.c, prev_j.c} = 48 partial dot products for its 4 columns, so each staged
+//     row is read from shared memory once per step (52 KB) instead of once per candidate.
+//     Products are fp32 (packed FFMA2); the 48 sums are reduced as a TREE — in-thread,
+//     then a halving exchange over the warp (48 values -> 3 per lane in 45 shuffles), fp32,
+//     depth 7, worst-case relative error < 1e-6 — and across warps in fp64.
+//   * Warp 0 finishes the step: cosine distances 1 - x.c/(|x||c|) from the dot products and
+//     carried reciprocal norms (one rsqrt per candidate; no sqrt/divide chain), the
+//     reference's threshold edits, lower median and rank; it publishes the selection and
+//     the producer picks it up and issues generation s+2.
+//   The general kernel keeps the reference's direct-form distances in fp64; the
+//   two agree to ~1e-6 in every cost, far inside the 1e-5 tie criterion.
+//
+// Traffic per frame: 13 rows = 53 KB against 9 rows = 36.9 KB algorithmic (the price of
+// speculation); arithmetic per frame: 8 x 5 x 1024 fused difference-squares.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knnsvc {
+
+namespace {
+
+constexpr int CS_K = 4;
+constexpr int CS_C = 2 * CS_K;             // candidates per step
+constexpr int CS_ACC = 6;                  // |c|^2, d2(src,c), d2(prev_j,c) j = 0..3
+constexpr int CS_V = CS_C * CS_ACC;        // 48 partial sums per thread
+constexpr int CS_WARPS = 8;                // compute warps
+constexpr int CS_CT = CS_WARPS * 32;       // compute threads
+constexpr int CS_THREADS = CS_CT + 32;     // + producer warp
+constexpr int CS_ROWS = 13;                // rows per generation: 4 idx rows, 8 speculative rows, query row
+constexpr int CS_GENS = 3;
+constexpr int CS_MAX_DIM = 1024;
+
+struct CsMeta {
+  int64_t idx_g[CS_K];      // pool rows of idx[s]
+  int64_t spec_g[CS_C];     // pool rows cand[s-1] + 1 (clamped)
+  double lf0_idx[CS_K];     // log2(f0 + 1e-5) of those rows
+  double lf0_spec[CS_C];
+  double base, inv_src, lsrc; // 2*dist(src[s-1], src[s]), 1/|src[s]|, log2(src_f0[s] + 1e-5)
+};
+
+struct CsShared {
+  CsMeta meta[CS_GENS];
+  float part[CS_WARPS][CS_V];
+  double prev_n2[CS_K];
+  double prev_inv[CS_K];   // 1/|row| of the previous selections, carried from the step that scored them
+  unsigned long long full_bar[CS_GENS];
+  int sp[2][CS_K];          // candidate slot (0..7) of each selection, by step parity
+  int prow[CS_K];           // row (0..11) of the previous generation holding each selected row
+  volatile int sel_count;   // selections published so far
+};
+
+__device__ __forceinline__ uint32_t cs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cs_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// one row, global -> shared, completion credited to `bar`
+__device__ __forceinline__ void cs_bulk_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cs_compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CS_CT) : "memory"); }
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// one halving step of the warp reduction: lanes with `upper` keep v[H..2H), the others v[0..H)
+template <int H>
+__device__ __forceinline__ void cs_halve(float (&v)[CS_V], bool upper, int xor_mask) {
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    const float keep = upper ? v[k + H] : v[k];
+    const float send = upper ? v[k] : v[k + H];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, xor_mask);
+  }
+}
+
+#ifdef KNNSVC_K5_PROFILE
+__device__ long long g_k5_prof[8];
+#define K5_T(i) do { const long long _t = clock64(); prof[i] += _t - t_last; t_last = _t; } while (0)
+#else
+#define K5_T(i) do { } while (0)
+#endif
+
+}  // namespace
+
+__global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
+    const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
+    int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
+    const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
+    int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(128) unsigned char cs_raw[];
+  float* rows = reinterpret_cast<float*>(cs_raw);                                   // [gen][row][dim]
+  CsShared& sh = *reinterpret_cast<CsShared*>(cs_raw + (size_t)CS_GENS * CS_ROWS * dim * sizeof(float));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
+  const int64_t n = f_end - f_begin;
+  if (n <= 0) return;
+  const bool use_f0 = src_f0 != nullptr;
+  const uint32_t row_bytes = (uint32_t)dim * 4u;
+  auto row_ptr = [&](int gen, int r) { return rows + ((size_t)gen * CS_ROWS + r) * dim; };
+
+  if (tid == 0) {
+    for (int g = 0; g < CS_GENS; ++g) cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), 1);
+    for (int j = 0; j < CS_K; ++j) {
+      sh.sp[0][j] = j;      // "selection 0" = idx[0] itself, sitting in slots 0..3 of generation 0
+      sh.sp[1][j] = j;
+      sh.prow[j] = j;
+    }
+    sh.sel_count = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == CS_WARPS) {
+    // ============================ producer warp ============================
+    // generation 0: the four rows of idx[0] (the initial "previous selection")
+    if (lane < CS_K) {
+      const int64_t id = idx[f_begin * CS_K + lane];
+      sh.meta[0].idx_g[lane] = id;
+      cs_bulk_row(cs_smem_u32(row_ptr(0, lane)), pool + id * dim, row_bytes, cs_smem_u32(&sh.full_bar[0]));
+    }
+    __syncwarp();
+    if (lane == 0) cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[0]), CS_K * row_bytes);
+    // Everything addressed by the frame number alone is fetched one generation ahead into
+    // registers, so the only latency between a published selection and the generation it
+    // unlocks is the TMA copy itself (plus pool_f0 of the speculative rows).
+    int64_t next_idx = 0;                       // lanes 8..11: idx[s]
+    double next_base = 0.0, next_n2 = 1.0;      // lane 12: per-frame scalars of the query row
+    float next_f0 = 0.f;
+    if (n > 1) {
+      if (lane >= CS_C && lane < CS_C + CS_K) next_idx = idx[(f_begin + 1) * CS_K + (lane - CS_C)];
+      if (lane == CS_C + CS_K) {
+        next_base = base_all[f_begin + 1];
+        next_n2 = src_n2[f_begin + 1];
+        if (use_f0) next_f0 = __ldg(src_f0 + f_begin + 1);
+      }
+    }
+    for (int64_t s = 1; s < n; ++s) {
+      const int g = (int)(s % CS_GENS), gp = (int)((s - 1) % CS_GENS);
+      if (s >= 2) {  // cand[s-1] needs selection s-2
+        if (lane == 0)
+          while (sh.sel_count < (int)(s - 2)) {
+          }
+        __syncwarp();
+        __threadfence_block();
+      }
+      const uint32_t bar = cs_smem_u32(&sh.full_bar[g]);
+      int64_t id = -1;
+      if (lane < CS_C) {                       // speculative rows: cand[s-1][lane] + 1
+        int64_t c;
+        if (s == 1) c = sh.meta[0].idx_g[lane & 3];
+        else if (lane < CS_K) c = sh.meta[gp].idx_g[lane];
+        else c = sh.meta[gp].spec_g[sh.sp[(s - 2) & 1][lane - CS_K]];
+        id = c + 1 >= n_pool ? n_pool - 1 : c + 1;   // lib_ongaku_test.py:294-295
+        sh.meta[g].spec_g[lane] = id;
+        cs_bulk_row(cs_smem_u32(row_ptr(g, CS_K + lane)), pool + id * dim, row_bytes, bar);
+      } else if (lane < CS_C + CS_K) {         // rows of idx[s]
+        id = next_idx;
+        sh.meta[g].idx_g[lane - CS_C] = id;
+        cs_bulk_row(cs_smem_u32(row_ptr(g, lane - CS_C)), pool + id * dim, row_bytes, bar);
+        if (s + 1 < n) next_idx = idx[(f_begin + s + 1) * CS_K + (lane - CS_C)];
+      } else if (lane == CS_C + CS_K) {        // query row s and its per-frame scalars
+        cs_bulk_row(cs_smem_u32(row_ptr(g, CS_ROWS - 1)), src + (f_begin + s) * dim, row_bytes, bar);
+        sh.meta[g].base = next_base;
+        sh.meta[g].inv_src = rsqrt(next_n2);
+        sh.meta[g].lsrc = use_f0 ? log2((double)next_f0 + 1e-5) : 0.0;
+        if (s + 1 < n) {
+          next_base = base_all[f_begin + s + 1];
+          next_n2 = src_n2[f_begin + s + 1];
+          if (use_f0) next_f0 = __ldg(src_f0 + f_begin + s + 1);
+        }
+      }
+      if (use_f0 && lane < CS_C + CS_K) {
+        const double lf = log2((double)__ldg(pool_f0 + id) + 1e-5);
+        if (lane < CS_C) sh.meta[g].lf0_spec[lane] = lf;
+        else sh.meta[g].lf0_idx[lane - CS_C] = lf;
+      }
+      __syncwarp();
+      if (lane == 0) cs_mbar_expect_tx(bar, CS_ROWS * row_bytes);   // release: publishes meta[g] too
+    }
+    return;
+  }
+
+  // ============================ compute warps ============================
+  const int n4 = dim / 4;
+  cs_mbar_wait(cs_smem_u32(&sh.full_bar[0]), 0);
+  if (warp < CS_K) {  // |row|^2 of the four initial selections, one warp each
+    const float4* r4 = reinterpret_cast<const float4*>(row_ptr(0, warp));
+    double acc = 0.0;
+    for (int c = lane; c < n4; c += 32) {
+      const float4 v = r4[c];
+      float t = v.x * v.x;
+      t = fmaf(v.y, v.y, t);
+      t = fmaf(v.z, v.z, t);
+      t = fmaf(v.w, v.w, t);
+      acc += (double)t;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sh.prev_n2[warp] = acc;
+      sh.prev_inv[warp] = rsqrt(acc);
+    }
+    if (tid < CS_K) out_idx[f_begin * CS_K + tid] = sh.meta[0].idx_g[tid];
+  }
+  cs_compute_sync();
+
+  double w_sticky = (double)concat_weight;   // meaningful in warp 0
+#ifdef KNNSVC_K5_PROFILE
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+  long long t_last = clock64();
+#endif
+  for (int64_t s = 1; s < n; ++s) {
+    const int g = (int)(s % CS_GENS), gp = (int)((s - 1) % CS_GENS);
+    cs_mbar_wait(cs_smem_u32(&sh.full_bar[g]), (uint32_t)((s / CS_GENS) & 1));
+    K5_T(0);
+    const int* spv = sh.sp[(s - 1) & 1];
+    const float4* cand4[CS_C];
+#pragma unroll
+    for (int m = 0; m < CS_C; ++m)
+      cand4[m] = reinterpret_cast<const float4*>(row_ptr(g, m < CS_K ? m : CS_K + spv[m - CS_K]));
+    const float4* src4 = reinterpret_cast<const float4*>(row_ptr(g, CS_ROWS - 1));
+    const float4* prev4[CS_K];
+#pragma unroll
+    for (int j = 0; j < CS_K; ++j) prev4[j] = reinterpret_cast<const float4*>(row_ptr(gp, sh.prow[j]));
+
+    // per-thread partial dot products over this thread's columns: acc[a][m], a = 0: c.c, 1: src.c, 2+j: prev_j.c
+    float2 acc[CS_ACC][CS_C];
+#pragma unroll
+    for (int a = 0; a < CS_ACC; ++a)
+#pragma unroll
+      for (int m = 0; m < CS_C; ++m) acc[a][m] = make_float2(0.f, 0.f);
+    for (int c = tid; c < n4; c += CS_CT) {
+      float4 o[1 + CS_K];
+      o[0] = src4[c];
+#pragma unroll
+      for (int j = 0; j < CS_K; ++j) o[1 + j] = prev4[j][c];
+#pragma unroll
+      for (int m = 0; m < CS_C; ++m) {
+        const float4 cv = cand4[m][c];
+        const float2 cl = lo2(cv), chh = hi2(cv);
+        acc[0][m] = __ffma2_rn(cl, cl, acc[0][m]);
+        acc[0][m] = __ffma2_rn(chh, chh, acc[0][m]);
+#pragma unroll
+        for (int a = 0; a < 1 + CS_K; ++a) {
+          acc[1 + a][m] = __ffma2_rn(lo2(o[a]), cl, acc[1 + a][m]);
+          acc[1 + a][m] = __ffma2_rn(hi2(o[a]), chh, acc[1 + a][m]);
+        }
+      }
+    }
+    K5_T(1);
+    // warp tree reduction in fp32 (depth 2 + 5: worst-case relative error ~1e-6 / sqrt-ish typical 1e-7),
+    // halving exchange: 48 -> 24 -> 12 -> 6 -> 3 values per lane, then one butterfly step
+    float v[CS_V];
+#pragma unroll
+    for (int a = 0; a < CS_ACC; ++a)
+#pragma unroll
+      for (int m = 0; m < CS_C; ++m) v[a * CS_C + m] = acc[a][m].x + acc[a][m].y;
+    cs_halve<24>(v, lane & 16, 16);
+    cs_halve<12>(v, lane & 8, 8);
+    cs_halve<6>(v, lane & 4, 4);
+    cs_halve<3>(v, lane & 2, 2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
+    if (!(lane & 1)) {
+      const int off = ((lane & 16) ? 24 : 0) + ((lane & 8) ? 12 : 0) + ((lane & 4) ? 6 : 0) + ((lane & 2) ? 3 : 0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sh.part[warp][off + k] = v[k];
+    }
+    K5_T(2);
+    cs_compute_sync();
+    K5_T(3);
+
+    if (warp == 0) {
+      const CsMeta& mt = sh.meta[g];
+      const double base = mt.base;
+      if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
+      // cross-warp sums in fp64: lane l owns flat entries l and l + 32 (flat = a * 8 + candidate)
+      double p0[CS_WARPS], p1[CS_WARPS];
+#pragma unroll
+      for (int w = 0; w < CS_WARPS; ++w) {
+        p0[w] = (double)sh.part[w][lane];
+        p1[w] = lane < CS_V - 32 ? (double)sh.part[w][lane + 32] : 0.0;
+      }
+#pragma unroll
+      for (int st = CS_WARPS / 2; st > 0; st >>= 1)
+#pragma unroll
+        for (int w = 0; w < st; ++w) {
+          p0[w] += p0[w + st];
+          p1[w] += p1[w + st];
+        }
+      const double t0 = p0[0], t1 = p1[0];
+      double q[CS_ACC];   // lane m < 8: the six sums of candidate m
+#pragma unroll
+      for (int a = 0; a < 4; ++a) q[a] = __shfl_sync(0xffffffffu, t0, a * CS_C + (lane & 7));
+#pragma unroll
+      for (int a = 4; a < CS_ACC; ++a) q[a] = __shfl_sync(0xffffffffu, t1, (a - 4) * CS_C + (lane & 7));
+      double total = INFINITY, my_n2 = 0.0, my_inv = 0.0;
+      int64_t my_id = 0;
+      int my_row = 0;
+      if (lane < CS_C) {
+        const int slot = lane < CS_K ? 0 : spv[lane - CS_K];
+        my_id = lane < CS_K ? mt.idx_g[lane] : mt.spec_g[slot];
+        my_row = lane < CS_K ? lane : CS_K + slot;
+        const double lcand = lane < CS_K ? mt.lf0_idx[lane] : mt.lf0_spec[slot];
+        my_n2 = q[0];
+        my_inv = rsqrt(my_n2);
+        // cosine distance 1 - x.c/(|x||c|) (lib_ongaku_test.py:162-165) with carried reciprocal norms
+        const double match = 1.0 - q[1] * (mt.inv_src * my_inv);
+        double cc[CS_K];
+#pragma unroll
+        for (int j = 0; j < CS_K; ++j) cc[j] = 1.0 - q[2 + j] * (sh.prev_inv[j] * my_inv);
+        if (use_f0) {
+          if (base < 0.08) {
+#pragma unroll
+            for (int j = 0; j < CS_K; ++j)
+              if (cc[j] < 5.0 * base) cc[j] = 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CS_K; ++j)
+            if (cc[j] > base) cc[j] = 1.5 * cc[j] - base;
+        }
+        // lower median of 4 = second smallest (torch.median, lib_ongaku_test.py:337,342)
+        const double lo01 = fmin(cc[0], cc[1]), hi01 = fmax(cc[0], cc[1]);
+        const double lo23 = fmin(cc[2], cc[3]), hi23 = fmax(cc[2], cc[3]);
+        const double med = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+        total = w_sticky * med + match;
+        if (use_f0) total += fabs(lcand - mt.lsrc);
+      }
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < CS_C; ++j) {
+        const double tj = __shfl_sync(0xffffffffu, total, j);
+        rank += (tj < total) || (tj == total && j < lane);
+      }
+      __syncwarp();  // every lane has read prev_inv before it is overwritten
+      if (lane < CS_C && rank < CS_K) {
+        out_idx[(f_begin + s) * CS_K + rank] = my_id;
+        sh.sp[s & 1][rank] = lane;
+        sh.prow[rank] = my_row;
+        sh.prev_n2[rank] = my_n2;
+        sh.prev_inv[rank] = my_inv;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        sh.sel_count = (int)s;   // the producer may now form cand[s] and issue generation s+1
+      }
+    }
+    K5_T(4);
+    cs_compute_sync();
+    K5_T(5);
+  }
+#ifdef KNNSVC_K5_PROFILE
+  if (tid == 0 && blockIdx.x == 0)
+    for (int i = 0; i < 6; ++i) g_k5_prof[i] = prof[i];
+#endif
+}
+
+size_t concat_staged_smem_bytes(int dim) {
+  return (size_t)CS_GENS * CS_ROWS * dim * sizeof(float) + sizeof(CsShared);
+}
+
+bool concat_staged_eligible(const float* src, const float* pool, int dim) {
+  return dim >= 4 && dim % 4 == 0 && dim <= CS_MAX_DIM && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(pool) & 15) == 0;
+}
+
+int launch_concat_cost_staged(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+                              const float* src_f0, const float* pool_f0, float concat_weight,
+                              const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
+                              int64_t* out_idx, cudaStream_t stream) {
+  const size_t smem = concat_staged_smem_bytes(dim);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    KNN_CUDA(cudaFuncSetAttribute(concat_cost_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  concat_cost_staged_kernel<<<n_utt, CS_THREADS, smem, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0,
+                                                                 concat_weight, utt_offsets_dev, base, n2, out_idx);
+  KNN_LAUNCH_CHECK();
+#ifdef KNNSVC_K5_PROFILE
+  {  // debugging aid: cycles of block 0 / thread 0 per phase, accumulated over the launch
+    long long h[8] = {0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_k5_prof, sizeof(h));
+    fprintf(stderr, "[k5 prof] wait %lld math %lld reduce %lld sync1 %lld final %lld sync2 %lld\n", h[0], h[1], h[2], h[3],
+            h[4], h[5]);
+    long long z[8] = {0};
+    cudaMemcpyToSymbol(g_k5_prof, z, sizeof(z));
+  }
+#endif
+  return 0;
+}
+
+}  // namespace knnsvc

@@ -8,6 +8,7 @@ namespace knnsvc {
 // ---- tuning options (capi.cu): diagnostic switches, see knnsvc_set_option
 int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
+int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
 
 // ---- rows.cu
@@ -50,6 +51,13 @@ int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
 int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
                        int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream);
+
+// ---- concat_cost_sm100.cu
+bool concat_staged_eligible(const float* src, const float* pool, int dim);
+int launch_concat_cost_staged(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+                              const float* src_f0, const float* pool_f0, float concat_weight,
+                              const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
+                              int64_t* out_idx, cudaStream_t stream);
 
 // ---- weight_fit.cu
 size_t weight_fit_workspace_bytes(int64_t n_query, int k);

@@ -105,7 +105,9 @@ int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
 }
 
 // ------------------------------------------------------------------ K5 greedy re-selection
-// knn_with_concat_cost (lib_ongaku_test.py:270-369), K = 4.  The recurrence is
+// knn_with_concat_cost (lib_ongaku_test.py:270-369), K = 4.  This is the GENERAL kernel (any
+// feature dimension / alignment, rows read through L2 every step); feature rows of up to
+// 1024 aligned floats take the shared-memory staged kernel in concat_cost_sm100.cu.  The recurrence is
 // serial in the frame index (frame i's candidates include "previous selection + 1"),
 // so one CTA walks one utterance; parallelism is inside a step — 8 warps, one
 // candidate row each, 5 direct-form cosine distances per candidate — and across
@@ -362,6 +364,9 @@ int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, 
   if (grid > 148 * 16) grid = 148 * 16;
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
+  if (opt_concat_staged() && concat_staged_eligible(src, pool, dim))   // shared-memory staged recurrence (concat_cost_sm100.cu)
+    return launch_concat_cost_staged(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
+                                     base, n2, out_idx, stream);
   concat_cost_kernel<<<n_utt, CC_WARPS * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
                                                       utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();

@@ -258,6 +258,66 @@ def test_concat_cost_batched_utterances(ops):
     assert np.array_equal(whole, np.concatenate([a, b]))
 
 
+def _set_opt(name, value):
+    from knn_svc_b200 import _lib
+    assert _lib.load().knnsvc_set_option(name.encode(), int(value)) == 0
+
+
+@pytest.mark.parametrize("staged", [0, 1])
+def test_concat_cost_both_kernels_match_reference(ops, golden, staged):
+    """the shared-memory staged kernel (concat_cost_sm100.cu) and the general kernel (post.cu)
+    must each reproduce the reference's selections"""
+    _set_opt("concat_staged", staged)
+    try:
+        test_concat_cost_matches_reference(ops, golden)
+        test_concat_cost_batched_utterances(ops)
+    finally:
+        _set_opt("concat_staged", 1)
+
+
+@pytest.mark.parametrize("use_f0", [False, True])
+def test_concat_cost_staged_long_and_ragged(ops, use_f0):
+    """cfg 1/2 length (3001 frames, the speculative pipeline wraps its three generations 1000
+    times), ragged utterance batches, candidates at the end of the pool (the +1 clamp,
+    lib_ongaku_test.py:294-295) and a narrow feature dimension: staged == general everywhere,
+    and == the oracle on a prefix."""
+    T, Np = 3001, 3001
+    q = synth.ar1_frames(T, seed=71, reset_every=200)
+    p = synth.ar1_frames(Np, seed=72)
+    rs = np.random.RandomState(7)
+    idx = rs.randint(0, Np, size=(T, 4)).astype(np.int64)
+    idx[5] = Np - 1                                   # every candidate + 1 clamps
+    idx[100:120, 0] = Np - 2
+    f0q = synth.f0_track(T, seed=73) if use_f0 else None
+    f0p = synth.f0_track(Np, seed=74) if use_f0 else None
+    args = (dev(idx), dev(q), dev(p)) + ((dev(f0q), dev(f0p)) if use_f0 else (None, None))
+    offsets_sets = [None, [0, 1, 2, 5, 700, 701, 3001], [0, 3001]]
+    for offs in offsets_sets:
+        outs = []
+        for staged in (0, 1):
+            _set_opt("concat_staged", staged)
+            try:
+                outs.append(ops.concat_cost_reselect(*args, concat_weight=0.2, utt_offsets=offs).cpu().numpy())
+            finally:
+                _set_opt("concat_staged", 1)
+        assert np.array_equal(outs[0], outs[1]), f"staged and general kernels disagree (offsets {offs})"
+    n_chk = 300
+    want = orc.knn_with_concat_cost(idx[:n_chk], q[:n_chk], p, None if f0q is None else f0q[:n_chk], f0p, 0.2)
+    assert np.array_equal(outs[1][:n_chk], want)
+    # narrow rows (dim 64) through both kernels
+    q2, p2 = synth.ar1_frames(200, d=64, seed=75), synth.ar1_frames(500, d=64, seed=76)
+    idx2 = rs.randint(0, 500, size=(200, 4)).astype(np.int64)
+    outs = []
+    for staged in (0, 1):
+        _set_opt("concat_staged", staged)
+        try:
+            outs.append(ops.concat_cost_reselect(dev(idx2), dev(q2), dev(p2), concat_weight=0.2).cpu().numpy())
+        finally:
+            _set_opt("concat_staged", 1)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[1], orc.knn_with_concat_cost(idx2, q2, p2, concat_weight=0.2))
+
+
 # ----------------------------------------------------------------------------- K6
 @pytest.mark.parametrize("name,scale", [("wavlm", 0.1), ("ext", 1000.0)])
 def test_weight_fit_matches_reference(ops, golden, name, scale):
