@@ -135,6 +135,15 @@ int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
                       float* out_weights, double* info,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched form (BASELINE cfg 5: many utterances against one pool): utterance u owns frames
+ * [utt_offsets_host[u], utt_offsets_host[u+1]) of idx / out_weights; one CTA per utterance,
+ * every utterance with its own stop rule.  info (optional): double[n_utt][4]. */
+size_t knnsvc_weight_fit_batched_workspace_bytes(int64_t n_frames, int k, int n_utt);
+int knnsvc_weight_fit_batched(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                              const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale,
+                              int max_iters, float* out_weights, double* info,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K7 / K7': additive harmonic bank -------------------------------------
  * get_bulk_dsp_choral — ddsp_prematch_dataset.py:165-208 (amp != NULL, H harmonics)
  * and the single sinusoid of hifigan/ddsp_models_f0.py:344-352 (amp == NULL).

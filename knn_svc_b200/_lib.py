@@ -35,6 +35,8 @@ SIGNATURES = {
     "knnsvc_concat_cost_reselect": (i32, [vp, vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, vp]),
     "knnsvc_weight_fit_workspace_bytes": (sz, [i64, i32]),
     "knnsvc_weight_fit": (i32, [vp, vp, i64, i32, i64, i32, f64, i32, vp, vp, vp, sz, vp]),
+    "knnsvc_weight_fit_batched_workspace_bytes": (sz, [i64, i32, i32]),
+    "knnsvc_weight_fit_batched": (i32, [vp, vp, i64, i32, vp, i32, i32, f64, i32, vp, vp, vp, sz, vp]),
     "knnsvc_harmonic_bank": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]),
 }
 

@@ -277,15 +277,33 @@ int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const floa
   return rc;
 }
 
-size_t knnsvc_weight_fit_workspace_bytes(int64_t n_query, int k) { return weight_fit_workspace_bytes(n_query, k); }
+size_t knnsvc_weight_fit_workspace_bytes(int64_t n_query, int k) { return weight_fit_workspace_bytes(n_query, k, 1); }
 
 int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
                       double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
                       size_t workspace_bytes, void* stream) {
-  KNN_CHECK_ARG(idx && synth && out_weights && workspace, -1, "weight_fit: null pointer");
-  KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(n_query, k), -2, "weight_fit: workspace too small");
-  return launch_weight_fit(idx, synth, n_pool, dim, n_query, k, loss_scale, max_iters, out_weights, info, workspace,
+  KNN_CHECK_ARG(idx && synth && out_weights && workspace && n_query >= 0, -1, "weight_fit: bad arguments");
+  KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(n_query, k, 1), -2, "weight_fit: workspace too small");
+  const int64_t offs[2] = {0, n_query};
+  return launch_weight_fit(idx, synth, n_pool, dim, offs, 1, k, loss_scale, max_iters, out_weights, info, workspace,
                            (cudaStream_t)stream);
+}
+
+size_t knnsvc_weight_fit_batched_workspace_bytes(int64_t n_frames, int k, int n_utt) {
+  return weight_fit_workspace_bytes(n_frames, k, n_utt);
+}
+
+int knnsvc_weight_fit_batched(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                              const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
+                              float* out_weights, double* info, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  KNN_CHECK_ARG(idx && synth && out_weights && workspace && utt_offsets_host && n_utt >= 0, -1,
+                "weight_fit_batched: bad arguments");
+  if (n_utt == 0) return 0;
+  KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(utt_offsets_host[n_utt], k, n_utt), -2,
+                "weight_fit_batched: workspace too small");
+  return launch_weight_fit(idx, synth, n_pool, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, out_weights,
+                           info, workspace, (cudaStream_t)stream);
 }
 
 int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,

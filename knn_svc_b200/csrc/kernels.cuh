@@ -60,10 +60,10 @@ int launch_concat_cost_staged(const int64_t* idx, const float* src, const float*
                               int64_t* out_idx, cudaStream_t stream);
 
 // ---- weight_fit.cu
-size_t weight_fit_workspace_bytes(int64_t n_query, int k);
-int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
-                      double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
-                      cudaStream_t stream);
+size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt);
+int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                      const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
+                      float* out_weights, double* info, void* workspace, cudaStream_t stream);
 
 // ---- harmonic.cu
 int launch_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,

@@ -81,6 +81,7 @@ struct WfState {
   float* v;
   float* vmax;
   float* best;
+  float* grad;   // dL/dw scratch
   float* wglob;  // [T,4] softmax weights when they do not fit in shared memory
 };
 
@@ -96,19 +97,41 @@ __device__ __forceinline__ void softmax4(const float* th, float* w) {
   for (int k = 0; k < 4; ++k) w[k] = e[k] / s;
 }
 
-__global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double* __restrict__ gram, int64_t n_query,
-                                                                   int dim, double loss_scale, int max_iters,
-                                                                   WfState st, int use_smem,
-                                                                   float* __restrict__ out_weights,
-                                                                   double* __restrict__ info) {
+__global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double* __restrict__ gram_all,
+                                                                   const int64_t* __restrict__ utt_offsets,
+                                                                   int64_t n_pairs_total, int dim, double loss_scale,
+                                                                   int max_iters, WfState st_all, int smem_frames,
+                                                                   float* __restrict__ out_weights_all,
+                                                                   double* __restrict__ info_all) {
+  // one CTA per utterance: frames [f_begin, f_end) of the concatenated batch; every array is
+  // indexed by the global frame number, so the CTA just offsets its bases
   extern __shared__ __align__(16) float s_w_dyn[];
   __shared__ double s_red[WF_THREADS / 32];
   __shared__ double s_loss;
   __shared__ int s_ctl;  // bit0: stop, bit1: snapshot
   __shared__ float s_step_size, s_bc2_sqrt;
-  volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
+  const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
+  const int64_t T = f_end - f_begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t T = n_query;
+  float* out_weights = out_weights_all + f_begin * 4;
+  double* info = info_all ? info_all + (int64_t)blockIdx.x * 4 : nullptr;
+  if (T <= 0) return;
+  if (T < 2) {  // nothing to smooth: the reference's loop never improves on theta = 0 -> softmax = 1/4
+    if (tid < 4) out_weights[tid] = 0.25f;
+    if (tid == 0 && info) info[0] = info[1] = info[2] = info[3] = 0.0;
+    return;
+  }
+  WfState st;
+  st.theta = st_all.theta + f_begin * 4;
+  st.m = st_all.m + f_begin * 4;
+  st.v = st_all.v + f_begin * 4;
+  st.vmax = st_all.vmax + f_begin * 4;
+  st.best = st_all.best + f_begin * 4;
+  st.grad = st_all.grad + f_begin * 4;
+  st.wglob = st_all.wglob + f_begin * 4;
+  const double* gram = gram_all + f_begin;   // entry e of pair (t, t+1): gram[e * n_pairs_total + t]
+  const int use_smem = T <= smem_frames;
+  volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
   const double norm = loss_scale / ((double)(T - 1) * (double)dim);
   const float lr = 0.1f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
 
@@ -137,7 +160,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
     }
     __syncthreads();
     // ---- loss and dL/dw from the Gram blocks
-    const int64_t NP = T - 1;
+    const int64_t NP = n_pairs_total;
     double part = 0.0;
     for (int64_t t = tid; t < T; t += WF_THREADS) {
       double wt[4];
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       }
       // gradient wrt w, cast to fp32 where the fp64 graph meets the fp32 softmax output
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st.best[T * 4 + t * 4 + k] = (float)(2.0 * norm * g[k]);  // scratch after best[T*4]
+      for (int k = 0; k < 4; ++k) st.grad[t * 4 + k] = (float)(2.0 * norm * g[k]);
     }
     part = warp_sum(part);
     if (lane == 0) s_red[warp] = part;
@@ -222,7 +245,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         w[k] = wbuf[t * 4 + k];
-        gw[k] = st.best[T * 4 + t * 4 + k];
+        gw[k] = st.grad[t * 4 + k];
         dotgw += gw[k] * w[k];
       }
 #pragma unroll
@@ -258,50 +281,63 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
   }
 }
 
-__global__ void uniform_weights_kernel(float* w, int64_t n, float v) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = v;
-}
-
-size_t weight_fit_workspace_bytes(int64_t n_query, int k) {
-  if (n_query < 2) return 256;
-  size_t gram = (size_t)(n_query - 1) * WF_E * sizeof(double);
+size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt) {
+  if (n_query < 1) return 256;
+  size_t gram = (size_t)n_query * WF_E * sizeof(double);
   size_t state = (size_t)n_query * k * sizeof(float) * 7;  // theta, m, v, vmax, best, grad scratch, wglob
-  return gram + state + 1024;
+  size_t offs = ((size_t)(n_utt + 1) * sizeof(int64_t) + 255) / 256 * 256;
+  return gram + state + offs + 1024;
 }
 
-int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim, int64_t n_query, int k,
-                      double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
-                      cudaStream_t stream) {
+// Batched launch: utterance u owns frames [utt_offsets_host[u], utt_offsets_host[u+1]) of the
+// concatenated idx / out_weights; one CTA runs one utterance's whole optimisation, so a batch of
+// utterances (BASELINE cfg 5) fills the SMs.  info: double[n_utt][4].
+int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                      const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
+                      float* out_weights, double* info, void* workspace, cudaStream_t stream) {
   KNN_CHECK_ARG(k == WF_K, -3, "weight_fit: k=%d, only k=%d is on the reference path", k, WF_K);
-  if (n_query == 0) return 0;
-  if (n_query < 2) {
-    uniform_weights_kernel<<<1, 32, 0, stream>>>(out_weights, n_query * k, 1.0f / k);
-    KNN_LAUNCH_CHECK();
-    return 0;
+  if (n_utt == 0) return 0;
+  const int64_t n_query = utt_offsets_host[n_utt];
+  KNN_CHECK_ARG(utt_offsets_host[0] == 0, -1, "weight_fit: utterance offsets must start at 0");
+  int64_t longest = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    const int64_t len = utt_offsets_host[u + 1] - utt_offsets_host[u];
+    KNN_CHECK_ARG(len >= 0, -1, "weight_fit: utterance offsets must be non-decreasing");
+    longest = len > longest ? len : longest;
   }
+  if (n_query == 0) return 0;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   double* gram = reinterpret_cast<double*>(ws);
-  float* f = reinterpret_cast<float*>(ws + (size_t)(n_query - 1) * WF_E * sizeof(double));
+  float* f = reinterpret_cast<float*>(ws + (size_t)n_query * WF_E * sizeof(double));
   WfState st;
   const size_t n4 = (size_t)n_query * 4;
   st.theta = f;
   st.m = f + n4;
   st.v = f + 2 * n4;
   st.vmax = f + 3 * n4;
-  st.best = f + 4 * n4;  // followed by the gradient scratch at best + n4
+  st.best = f + 4 * n4;
+  st.grad = f + 5 * n4;
   st.wglob = f + 6 * n4;
-  weight_gram_kernel<<<(unsigned)(n_query - 1), WF_V * 32, 0, stream>>>(idx, synth, n_pool, dim, n_query, gram);
-  KNN_LAUNCH_CHECK();
-  const int use_smem = n_query <= WF_SMEM_FRAMES;
-  const size_t smem = use_smem ? n4 * sizeof(float) : 16;
+  int64_t* d_off = reinterpret_cast<int64_t*>(f + 7 * n4);
+  d_off = reinterpret_cast<int64_t*>((reinterpret_cast<uintptr_t>(d_off) + 255) & ~(uintptr_t)255);
+  KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           stream));
+  const int64_t n_pairs_total = n_query - 1;
+  if (n_pairs_total > 0) {
+    // pairs that straddle two utterances are computed too (same pool, in-range rows) and never read
+    weight_gram_kernel<<<(unsigned)n_pairs_total, WF_V * 32, 0, stream>>>(idx, synth, n_pool, dim, n_query, gram);
+    KNN_LAUNCH_CHECK();
+  }
+  const int smem_frames = longest <= WF_SMEM_FRAMES ? (int)longest : 0;   // all utterances or none use smem weights
+  const size_t smem = smem_frames ? (size_t)smem_frames * 4 * sizeof(float) : 16;
   static bool attr_done = false;
   if (!attr_done) {
     KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
     attr_done = true;
   }
-  weight_fit_kernel<<<1, WF_THREADS, smem, stream>>>(gram, n_query, dim, loss_scale, max_iters, st, use_smem,
-                                                     out_weights, info);
+  weight_fit_kernel<<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1, dim,
+                                                         loss_scale, max_iters, st, smem_frames, out_weights, info);
   KNN_LAUNCH_CHECK();
   return 0;
 }

@@ -232,21 +232,33 @@ def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tenso
 
 
 def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_iters: int = 100000,
-               return_info: bool = False):
+               return_info: bool = False, utt_offsets=None):
+    """Adam(amsgrad) fit of the softmax mixing weights (K6).  With `utt_offsets` the rows of
+    `idx` are a concatenation of utterances, each fitted independently (one CTA each, one
+    launch); info is then [n_utt, 4]."""
     _dev(synth, "synth_set")
     dev = synth.device
     idx, synth = _i64c(idx.to(dev)), _f32c(synth)
     T, k = idx.shape
+    offs = [0, T] if utt_offsets is None else [int(v) for v in utt_offsets]
+    if offs[0] != 0 or offs[-1] != T:
+        raise ValueError("utt_offsets must run from 0 to the number of frames")
+    n_utt = len(offs) - 1
     out = torch.empty((T, k), dtype=torch.float32, device=dev)
-    info = torch.zeros((4,), dtype=torch.float64, device=dev)
+    info = torch.zeros((n_utt, 4), dtype=torch.float64, device=dev)
     lib = _lib.load()
     if T > 0:
+        import ctypes
+        arr = (ctypes.c_int64 * len(offs))(*offs)
         with torch.cuda.device(dev):
-            nbytes = lib.knnsvc_weight_fit_workspace_bytes(T, k)
+            nbytes = lib.knnsvc_weight_fit_batched_workspace_bytes(T, k, n_utt)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            _lib.check(lib.knnsvc_weight_fit(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1], T, k,
-                                             float(loss_scale), int(max_iters), out.data_ptr(), info.data_ptr(),
-                                             ws.data_ptr(), ws.numel(), _stream()), "weight_fit")
+            _lib.check(lib.knnsvc_weight_fit_batched(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1],
+                                                     ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
+                                                     int(max_iters), out.data_ptr(), info.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), _stream()), "weight_fit")
+    if utt_offsets is None:
+        info = info[0]
     if return_info:
         return out, info
     return out

@@ -337,6 +337,34 @@ def test_weight_fit_matches_reference(ops, golden, name, scale):
     assert np.abs(w - ref_w).max() < 5e-2
 
 
+def test_weight_fit_batched_equals_per_utterance(ops):
+    """one launch over a ragged batch of utterances (one CTA each, cfg 5) == separate launches,
+    bit for bit, including each utterance's own stop iteration; 1-frame utterances get 1/4"""
+    pool = synth.ar1_frames(700, seed=81)
+    rs = np.random.RandomState(8)
+    lens = [150, 1, 2, 333, 64, 0, 90]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    base = rs.randint(0, 700, size=(offs[-1], 1))
+    idx = np.clip(base + rs.randint(-3, 4, size=(offs[-1], 4)), 0, 699).astype(np.int64)
+    w_all, info_all = ops.weight_fit(dev(idx), dev(pool), 0.1, return_info=True, utt_offsets=offs.tolist())
+    w_all, info_all = w_all.cpu().numpy(), info_all.cpu().numpy()
+    assert info_all.shape == (len(lens), 4)
+    for u, n in enumerate(lens):
+        a, b = offs[u], offs[u + 1]
+        if n == 0:
+            continue
+        w, info = ops.weight_fit(dev(idx[a:b]), dev(pool), 0.1, return_info=True)
+        assert np.array_equal(w.cpu().numpy(), w_all[a:b]), f"utterance {u}"
+        assert np.array_equal(info.cpu().numpy(), info_all[u])
+        if n == 1:
+            assert np.all(w_all[a:b] == 0.25)
+        elif n >= 64:
+            rows = orc._neighbour_rows(idx[a:b], np.asarray(pool, np.float64))
+            got = orc.smoothness_loss(w_all[a:b].astype(np.float64), rows, 0.1)
+            assert abs(info_all[u, 1] - got) <= 1e-6 * abs(got) + 1e-9
+            assert got < orc.smoothness_loss(np.full((n, 4), 0.25), rows, 0.1)
+
+
 # ----------------------------------------------------------------------------- K7
 def test_harmonic_bank_matches_reference(ops, golden):
     from knn_svc_b200.ddsp_prematch_dataset import f0_sinusoid, get_bulk_dsp_choral
