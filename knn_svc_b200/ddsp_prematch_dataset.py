@@ -58,20 +58,22 @@ def sort_by_f0_compatibility(expected_f0, f0_list, target_feature_indices):
     return ops.f0_rerank(expected_f0, f0_list, target_feature_indices)
 
 
-def compute_wavlm_weight(target_feature_indices, synth_set, process_type="sum_to_1_geq"):
+def compute_wavlm_weight(target_feature_indices, synth_set, process_type="sum_to_1_geq", utt_offsets=None):
     """Per-frame mixing weights minimising the neighbour-frame smoothness loss —
-    reference :574-680 (Adam amsgrad on softmax logits, loss 0.1*MSE)."""
+    reference :574-680 (Adam amsgrad on softmax logits, loss 0.1*MSE).  `utt_offsets`
+    (extension) fits a concatenated batch of utterances independently in one launch."""
     if process_type != "sum_to_1_geq":
         raise NotImplementedError("only sum_to_1_geq is on the reference's live path")
-    return ops.weight_fit(target_feature_indices, synth_set, 0.1)
+    return ops.weight_fit(target_feature_indices, synth_set, 0.1, utt_offsets=utt_offsets)
 
 
-def compute_extended_weight(target_feature_indices, synth_set, process_type="sum_to_1_geq", factors=[1]):
+def compute_extended_weight(target_feature_indices, synth_set, process_type="sum_to_1_geq", factors=[1],
+                            utt_offsets=None):
     """Same fit on the harmonic amplitudes, loss 1000*MSE — reference :807-924.
     `factors` must be [1] (the only value the reference passes, :1440)."""
     if process_type != "sum_to_1_geq" or list(factors) != [1]:
         raise NotImplementedError("only sum_to_1_geq with factors=[1] is on the reference's live path")
-    return ops.weight_fit(target_feature_indices, synth_set, 1000.0)
+    return ops.weight_fit(target_feature_indices, synth_set, 1000.0, utt_offsets=utt_offsets)
 
 
 def get_bulk_dsp_choral(f0, amp, sample_rate=16000, hop_size=320):
@@ -92,6 +94,33 @@ def shift_query_f0(query_f0, matching_f0):
     shifted = copy.deepcopy(query_f0)
     shifted[query_f0 != 0] = torch.exp(torch.log(query_f0[query_f0 != 0]) + matching_f0_median - query_f0_median)
     return shifted
+
+
+def _lower_median_rows(x: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+    """torch.median (lower median) of the valid entries of each row of a padded [U, L] batch."""
+    big = torch.finfo(x.dtype).max
+    srt = torch.sort(torch.where(valid, x, torch.full_like(x, big)), dim=1).values
+    cnt = valid.sum(1)
+    pos = ((cnt - 1).clamp_min(0) // 2)[:, None]
+    return srt.gather(1, pos)[:, 0]
+
+
+def shift_query_f0_batched(f0_list, matching_f0_median: torch.Tensor):
+    """`shift_query_f0` (reference :1224-1233) for a batch of utterances with a handful of batched
+    torch ops instead of ~10 small ones per utterance.  Returns one concatenated [sum T] tensor on
+    the device of `matching_f0_median`."""
+    dev = matching_f0_median.device
+    lens = [int(len(f)) for f in f0_list]
+    U, L = len(lens), max(lens + [1])
+    pad = torch.zeros((U, L), dtype=f0_list[0].dtype if U else torch.float32, device=dev)
+    for u, f in enumerate(f0_list):
+        pad[u, :lens[u]] = f.to(dev)
+    voiced = pad != 0
+    logf = torch.log(torch.where(voiced, pad, torch.ones_like(pad)))
+    med = _lower_median_rows(logf, voiced)                      # NaN-free even for all-unvoiced rows
+    shifted = torch.where(voiced, torch.exp(logf + matching_f0_median.to(pad.dtype) - med[:, None]), pad)
+    keep = torch.arange(L, device=dev)[None, :] < torch.tensor(lens, device=dev)[:, None]
+    return shifted[keep]
 
 
 def parse_post_opt(post_opt: str) -> float:
@@ -115,43 +144,66 @@ class MatchingPool:
         self.synth = self.matching.rows if same else synth_list.to(self.device, torch.float32).contiguous()
         self.f0 = matching_f0.to(torch.float32)
         self.f0_dev = self.f0.to(self.device)
+        voiced = self.f0_dev[self.f0_dev != 0]
+        # lower median of the voiced log-f0 (reference :1227), computed once per pool
+        self.log_f0_median = torch.median(torch.log(voiced)) if len(voiced) else torch.zeros((), device=self.device)
         self.harmonics = None if harmonics_synth_list is None else \
             harmonics_synth_list.to(self.device, torch.float32).contiguous()
 
 
-def match_utterance(query_seq, query_f0, pool: MatchingPool, post_opt="no_post_opt", ckpt_type="mix",
-                    prioritize_f0=True):
-    """Tensor-level body of match_at_inference_time for one query utterance (reference :1180-1451)."""
+def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_post_opt", ckpt_type="mix",
+                     prioritize_f0=True):
+    """Tensor-level body of match_at_inference_time (reference :1180-1451) for a BATCH of query
+    utterances against one pool (BASELINE cfg 5): the utterances are concatenated and every stage
+    runs once over the batch — one fused kNN search, one greedy re-selection launch (one CTA per
+    utterance), one weight-fit launch (one CTA per utterance), one gather-mix.  Each utterance's
+    results do not depend on what else is in the batch.  Returns a list of result dicts (views
+    into the batch tensors)."""
     assert prioritize_f0                                                     # reference :1375
     dev = pool.device
-    query = ops.prepare_rows(query_seq.to(dev))
+    lens = [int(q.shape[0]) for q in query_seqs]
+    if not lens:
+        return []
+    offs = [0]
+    for n in lens:
+        offs.append(offs[-1] + n)
+    query = ops.prepare_rows(torch.concat([q.to(dev) for q in query_seqs], dim=0))
     _, nearest_nbrs = ops.knn_search(query, pool.matching, 32)               # :1196-1206
-    shifted_query_f0 = shift_query_f0(query_f0, pool.f0)                     # :1224-1233
+    shifted_f0 = shift_query_f0_batched(query_f0s, pool.log_f0_median)       # :1224-1233
     concat_weight = parse_post_opt(post_opt)
-    target_feature_indices = nearest_nbrs[:, :4].contiguous()                # :1246 (topk ignored, SURVEY D4)
+    fit = "no_post_opt" not in post_opt
+    idx_w = nearest_nbrs[:, :4].contiguous()                                 # :1246
     if concat_weight != -1:
-        target_feature_indices = knn_with_concat_cost(target_feature_indices, query.rows, pool.matching.rows,
-                                                      concat_weight=concat_weight)           # :1295
-    if "no_post_opt" not in post_opt:
-        w = compute_wavlm_weight(target_feature_indices, pool.synth, "sum_to_1_geq")         # :1357
-    else:
-        w = None                                                             # softmax(ones) = 1/4 each, :1361
-    out_feats_weighted = ops.gather_mix(pool.synth, target_feature_indices, w)               # :1358 / :1364
-    result = {"out_feats": out_feats_weighted, "shifted_f0": shifted_query_f0, "wavlm_indices": target_feature_indices,
-              "nearest_nbrs": nearest_nbrs}
-    nearest_nbrs_f0_priority = sort_by_f0_compatibility(shifted_query_f0, pool.f0_dev, nearest_nbrs)   # :1377
-    target_feature_indices = nearest_nbrs_f0_priority[:, :4].contiguous()    # :1398
+        idx_w = ops.concat_cost_reselect(idx_w, query.rows, pool.matching.rows, concat_weight=concat_weight,
+                                         utt_offsets=offs)                   # :1295
+    w = compute_wavlm_weight(idx_w, pool.synth, "sum_to_1_geq", utt_offsets=offs) if fit else None   # :1357 / :1361
+    out_feats = ops.gather_mix(pool.synth, idx_w, w)                         # :1358 / :1364
+    prio = sort_by_f0_compatibility(shifted_f0, pool.f0_dev, nearest_nbrs)   # :1377
+    idx_h = prio[:, :4].contiguous()                                         # :1398
     if concat_weight != -1:
-        target_feature_indices = knn_with_concat_cost(target_feature_indices, query.rows, pool.matching.rows,
-                                                      shifted_query_f0, pool.f0_dev, concat_weight=concat_weight)  # :1414
-    result["harm_indices"] = target_feature_indices
+        idx_h = ops.concat_cost_reselect(idx_h, query.rows, pool.matching.rows, shifted_f0, pool.f0_dev,
+                                         concat_weight=concat_weight, utt_offsets=offs)      # :1414
+    harm = None
     if "wavlm_only" not in ckpt_type and "no_harm_no_amp" not in ckpt_type:
-        if "no_post_opt" not in post_opt:
-            hw = compute_extended_weight(target_feature_indices, pool.harmonics, "sum_to_1_geq", [1])  # :1441
-        else:
-            hw = None                                                        # plain mean, :1446
-        result["harmonics"] = ops.gather_mix(pool.harmonics, target_feature_indices, hw)     # :1444 / :1446
-    return result
+        hw = compute_extended_weight(idx_h, pool.harmonics, "sum_to_1_geq", [1], utt_offsets=offs) if fit else None
+        harm = ops.gather_mix(pool.harmonics, idx_h, hw)                     # :1444 / :1446
+    results = []
+    for u in range(len(lens)):
+        a, b = offs[u], offs[u + 1]
+        r = {"out_feats": out_feats[a:b], "shifted_f0": shifted_f0[a:b].to(query_f0s[u].device),
+             "wavlm_indices": idx_w[a:b], "nearest_nbrs": nearest_nbrs[a:b], "harm_indices": idx_h[a:b]}
+        if harm is not None:
+            r["harmonics"] = harm[a:b]
+        results.append(r)
+    return results
+
+
+def match_utterance(query_seq, query_f0, pool: MatchingPool, post_opt="no_post_opt", ckpt_type="mix",
+                    prioritize_f0=True):
+    """Tensor-level body of match_at_inference_time for one query utterance (reference :1180-1451):
+    a batch of one."""
+    return match_utterances([query_seq], [query_f0], pool, post_opt=post_opt, ckpt_type=ckpt_type,
+                            prioritize_f0=prioritize_f0)[0]
 
 
 def match_at_inference_time(src_wav_file, ref_wav_file, wavlm, match_weights, synth_weights, topk: int = 4,
@@ -179,12 +231,13 @@ def match_at_inference_time(src_wav_file, ref_wav_file, wavlm, match_weights, sy
     harmonics_out_feats_weighted_collection = dict()
     audio_out_feats_weighted_collection = dict()
     shifted_query_f0_collection = dict()
-    for item in query_pool:
-        if required_subset is not None and \
-                os.path.basename(item).split(".")[0] + "/" + os.path.basename(ref_wav_file) not in required_subset:
-            continue
-        res = match_utterance(query_pool[item], query_f0_pool[item], pool, post_opt=post_opt, ckpt_type=ckpt_type,
-                              prioritize_f0=prioritize_f0)
+    items = [item for item in query_pool
+             if required_subset is None or
+             os.path.basename(item).split(".")[0] + "/" + os.path.basename(ref_wav_file) in required_subset]   # :1181
+    # all query utterances of this (source, target) pair go through the matcher as ONE batch
+    results = match_utterances([query_pool[i] for i in items], [query_f0_pool[i] for i in items], pool,
+                               post_opt=post_opt, ckpt_type=ckpt_type, prioritize_f0=prioritize_f0)
+    for item, res in zip(items, results):
         out_feats_weighted_collection[item] = res["out_feats"]
         audio_out_feats_weighted_collection[item] = None
         shifted_query_f0_collection[item] = res["shifted_f0"]

@@ -431,6 +431,24 @@ def test_pipeline_matches_reference(ops, golden, post_opt):
         assert rel < 5e-3 and relh < 5e-2            # passes through the Adam fit
 
 
+@pytest.mark.parametrize("post_opt", ["no_post_opt", "post_opt_0.2"])
+def test_batched_utterances_equal_single(ops, post_opt):
+    """cfg 5 batch axis: match_utterances over a ragged batch == match_utterance one by one (bit for bit)"""
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    pf = synth.ar1_frames(900, seed=91)
+    pool = pm.MatchingPool(torch.from_numpy(pf), torch.from_numpy(pf), torch.from_numpy(synth.f0_track(900, seed=92)),
+                           torch.from_numpy(synth.harmonics_pool(900, seed=93)), DEV)
+    lens = [80, 33, 150, 1, 64]
+    qs = [torch.from_numpy(synth.ar1_frames(n, seed=100 + i, reset_every=40)) for i, n in enumerate(lens)]
+    f0s = [torch.from_numpy(synth.f0_track(n, seed=200 + i)) for i, n in enumerate(lens)]
+    batch = pm.match_utterances(qs, f0s, pool, post_opt=post_opt, ckpt_type="mix", prioritize_f0=True)
+    assert len(batch) == len(lens)
+    for q, f0, got in zip(qs, f0s, batch):
+        one = pm.match_utterance(q, f0, pool, post_opt=post_opt, ckpt_type="mix", prioritize_f0=True)
+        for key in ("out_feats", "harmonics", "shifted_f0", "wavlm_indices", "harm_indices", "nearest_nbrs"):
+            assert torch.equal(one[key].cpu(), got[key].cpu()), key
+
+
 def test_matcher_match_api(ops):
     from knn_svc_b200.ddsp_matcher import KNeighborsVC
     m = KNeighborsVC(None, None, None, device=DEV)
