@@ -73,6 +73,18 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
                       float* out_dist, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, int* stats, void* stream);
 
+/* Same search with a per-row masked column range: for query row t the pool columns
+ * [mask_lo[t], mask_hi[t]) (shard-local, before index_offset) have their cosine distance
+ * DEFINED as 1, exactly what the offline prematch does to an utterance's own frames —
+ * `dists[:, start_index:end_index] = 1` before `.topk(k=32)`, ddsp_prematch_dataset.py:1608-1632
+ * (per_spk_extract).  mask_lo/mask_hi: device int64 [n_query]; both NULL = knnsvc_knn_search. */
+int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query,
+                             const float* p, const void* ph, const float* pn, int64_t n_pool,
+                             int dim, int dim_pad, int k, int64_t index_offset,
+                             const int64_t* mask_lo, const int64_t* mask_hi,
+                             float* out_dist, int64_t* out_idx,
+                             void* workspace, size_t workspace_bytes, int* stats, void* stream);
+
 /* Measurement hooks used by bench.py (no effect on results).
  *   knnsvc_launch_count            kernels this library has launched in this process
  *   knnsvc_filter_timing(1/0)      bracket the tcgen05 filter launch of every later
@@ -143,6 +155,15 @@ int knnsvc_weight_fit_batched(const int64_t* idx, const float* synth, int64_t n_
                               const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale,
                               int max_iters, float* out_weights, double* info,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Training-time variant (offline prematch): compute_weight_with_amp —
+ * ddsp_prematch_dataset.py:684-803, called at :1681 with loss 1000*MSE (phase_mae :449-457).
+ * Every candidate row is scaled by amp_ratio[t,k] (device fp32 [n_frames, k]) before mixing;
+ * amp_ratio == NULL is knnsvc_weight_fit_batched. */
+int knnsvc_weight_fit_amp(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                          const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale,
+                          int max_iters, const float* amp_ratio, float* out_weights, double* info,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K7 / K7': additive harmonic bank -------------------------------------
  * get_bulk_dsp_choral — ddsp_prematch_dataset.py:165-208 (amp != NULL, H harmonics)

@@ -23,6 +23,8 @@ SIGNATURES = {
     "knnsvc_cosine_dist": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "knnsvc_knn_workspace_bytes": (sz, [i64, i64, i32, i32]),
     "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, sz, vp, vp]),
+    "knnsvc_knn_search_masked": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz,
+                                       vp, vp]),
     "knnsvc_launch_count": (C.c_longlong, []),
     "knnsvc_set_option": (i32, [C.c_char_p, i32]),
     "knnsvc_filter_timing": (i32, [i32]),
@@ -37,6 +39,7 @@ SIGNATURES = {
     "knnsvc_weight_fit": (i32, [vp, vp, i64, i32, i64, i32, f64, i32, vp, vp, vp, sz, vp]),
     "knnsvc_weight_fit_batched_workspace_bytes": (sz, [i64, i32, i32]),
     "knnsvc_weight_fit_batched": (i32, [vp, vp, i64, i32, vp, i32, i32, f64, i32, vp, vp, vp, sz, vp]),
+    "knnsvc_weight_fit_amp": (i32, [vp, vp, i64, i32, vp, i32, i32, f64, i32, vp, vp, vp, vp, sz, vp]),
     "knnsvc_harmonic_bank": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]),
 }
 

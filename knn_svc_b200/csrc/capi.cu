@@ -133,7 +133,18 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
                       const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
                       int64_t index_offset, float* out_dist, int64_t* out_idx, void* workspace,
                       size_t workspace_bytes, int* stats, void* stream_) {
+  return knnsvc_knn_search_masked(q, qh, qn, n_query, p, ph, pn, n_pool, dim, dim_pad, k, index_offset, nullptr,
+                                  nullptr, out_dist, out_idx, workspace, workspace_bytes, stats, stream_);
+}
+
+int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
+                             const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+                             int64_t index_offset, const int64_t* mask_lo, const int64_t* mask_hi,
+                             float* out_dist, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                             int* stats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -1,
+                "knn_search: mask_lo and mask_hi must be given together");
   KNN_CHECK_ARG(n_query >= 0 && n_pool >= 1 && dim >= 1 && dim_pad >= dim, -1, "knn_search: bad shape");
   KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -1, "knn_search: k=%d outside [1,%d]", k, kMaxK);
   KNN_CHECK_ARG(k <= n_pool, -1, "knn_search: k=%d exceeds the pool size %lld", k, (long long)n_pool);
@@ -147,18 +158,19 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
   const bool timed = g_timing && g_ev_n < kTimingSlots;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                             w.seg_kth, w.seg_flag, stream);
+                             w.seg_kth, w.seg_flag, mask_lo, mask_hi, stream);
   if (rc) return rc;
   if (timed) {
     KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));
     ++g_ev_n;
   }
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                          index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, stream);
+                          index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, mask_lo, mask_hi,
+                          stream);
   if (rc) return rc;
   // rows the error window could not decide: exact brute force, count known only on the device
   rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, w.flag_list, w.counters, 0, 0, kFlagCap,
-                             index_offset, out_dist, out_idx, w.exact_partial, stream);
+                             index_offset, out_dist, out_idx, w.exact_partial, mask_lo, mask_hi, stream);
   if (rc) return rc;
   if (stats) {
     write_plan_stats<<<1, 1, 0, stream>>>(stats, w.counters, pl.n_seg, pl.n_units, pl.grid, pl.cap);
@@ -230,7 +242,8 @@ int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query, const flo
   for (int64_t base = 0; base < n_query; base += cap) {
     const int64_t n = (n_query - base) < cap ? (n_query - base) : cap;
     int rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, nullptr, nullptr, n, base, cap,
-                                   index_offset, out_dist, out_idx, workspace, (cudaStream_t)stream);
+                                   index_offset, out_dist, out_idx, workspace, nullptr, nullptr,
+                                   (cudaStream_t)stream);
     if (rc) return rc;
   }
   return 0;
@@ -285,8 +298,8 @@ int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   KNN_CHECK_ARG(idx && synth && out_weights && workspace && n_query >= 0, -1, "weight_fit: bad arguments");
   KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(n_query, k, 1), -2, "weight_fit: workspace too small");
   const int64_t offs[2] = {0, n_query};
-  return launch_weight_fit(idx, synth, n_pool, dim, offs, 1, k, loss_scale, max_iters, out_weights, info, workspace,
-                           (cudaStream_t)stream);
+  return launch_weight_fit(idx, synth, n_pool, dim, offs, 1, k, loss_scale, max_iters, nullptr, out_weights, info,
+                           workspace, (cudaStream_t)stream);
 }
 
 size_t knnsvc_weight_fit_batched_workspace_bytes(int64_t n_frames, int k, int n_utt) {
@@ -297,13 +310,21 @@ int knnsvc_weight_fit_batched(const int64_t* idx, const float* synth, int64_t n_
                               const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
                               float* out_weights, double* info, void* workspace, size_t workspace_bytes,
                               void* stream) {
+  return knnsvc_weight_fit_amp(idx, synth, n_pool, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, nullptr,
+                               out_weights, info, workspace, workspace_bytes, stream);
+}
+
+int knnsvc_weight_fit_amp(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+                          const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
+                          const float* amp_ratio, float* out_weights, double* info, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   KNN_CHECK_ARG(idx && synth && out_weights && workspace && utt_offsets_host && n_utt >= 0, -1,
-                "weight_fit_batched: bad arguments");
+                "weight_fit: bad arguments");
   if (n_utt == 0) return 0;
   KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(utt_offsets_host[n_utt], k, n_utt), -2,
-                "weight_fit_batched: workspace too small");
-  return launch_weight_fit(idx, synth, n_pool, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, out_weights,
-                           info, workspace, (cudaStream_t)stream);
+                "weight_fit: workspace too small");
+  return launch_weight_fit(idx, synth, n_pool, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, amp_ratio,
+                           out_weights, info, workspace, (cudaStream_t)stream);
 }
 
 int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,

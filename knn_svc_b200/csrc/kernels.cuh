@@ -21,7 +21,8 @@ size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k);
 int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
-                          float* out_dist, int64_t* out_idx, void* partial, cudaStream_t stream);
+                          float* out_dist, int64_t* out_idx, void* partial, const int64_t* mask_lo,
+                          const int64_t* mask_hi, cudaStream_t stream);
 
 // ---- knn_filter_sm100.cu
 struct FilterPlan {
@@ -30,7 +31,8 @@ struct FilterPlan {
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
-                      float* seg_kth, int* seg_flag, cudaStream_t stream);
+                      float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
+                      cudaStream_t stream);
 size_t filter_flag_count(const FilterPlan& pl);
 
 // ---- knn_select.cu
@@ -39,7 +41,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       cudaStream_t stream);
+                       const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream);
 int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
                       int64_t* out_idx, cudaStream_t stream);
 
@@ -63,7 +65,7 @@ int launch_concat_cost_staged(const int64_t* idx, const float* src, const float*
 size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt);
 int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
                       const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
-                      float* out_weights, double* info, void* workspace, cudaStream_t stream);
+                      const float* amp, float* out_weights, double* info, void* workspace, cudaStream_t stream);
 
 // ---- harmonic.cu
 int launch_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,

@@ -286,13 +286,18 @@ __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, in
 }  // namespace
 
 // ----------------------------------------------------------------------------- kernel
-template <int CTAS>
+// MASKED: every query row carries a column range [mask_lo[row], mask_hi[row]) whose cosine
+// distance is DEFINED to be 1 (similarity 0) — the offline prematch's self-utterance rule
+// `dists[:, start_index:end_index] = 1` (ddsp_prematch_dataset.py:1623-1624).  The accumulator
+// values of those columns are replaced by 0 before the filter sees them.
+template <int CTAS, bool MASKED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
                   int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
                   float* __restrict__ seg_top, float* __restrict__ seg_kth, int* __restrict__ seg_flag,
-                  uint32_t idesc, uint32_t spin_ns) {
+                  uint32_t idesc, uint32_t spin_ns, const int64_t* __restrict__ mask_lo,
+                  const int64_t* __restrict__ mask_hi) {
   using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
@@ -441,6 +446,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       st.tau_lo = row_ok ? known * kDotScale - window_scaled : INFINITY;
       const float warm_lo = st.tau_lo;
+      int m_lo = 0, m_hi = 0;   // masked column range of this row (empty unless MASKED)
+      if constexpr (MASKED) {
+        if (row_ok) {
+          m_lo = (int)mask_lo[row];
+          m_hi = (int)mask_hi[row];
+        }
+      }
       const int64_t slot = row * n_seg + seg;
       float* lv = log_val + (row_ok ? slot * cap : 0);
       int* li = log_idx + (row_ok ? slot * cap : 0);
@@ -456,6 +468,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if constexpr (MASKED) {
+            const int cb = col0 + c * 32;
+            if (cb < m_hi && cb + 32 > m_lo) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cb + j >= m_lo && cb + j < m_hi) r[j] = 0u;   // similarity 0 <=> distance 1
+            }
+          }
           float mx = __uint_as_float(r[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
@@ -474,7 +494,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               uint32_t one;
               asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(one) : "r"(taddr + c * 32 + j) : "memory");
               tmem_ld_wait();
-              const float v = __uint_as_float(one);
+              float v = __uint_as_float(one);
+              if constexpr (MASKED) {
+                if (cbase + j >= m_lo && cbase + j < m_hi) v = 0.f;
+              }
               if (((mask >> j) & 1u) && v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
                 st = filter_insert(st, v, cbase + j, keys_row, k, lv, li, cap, window_scaled);
               st.tau_lo = fmaxf(st.tau_lo, warm_lo);
@@ -591,13 +614,14 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
 
 size_t filter_flag_count(const FilterPlan& pl) { return (size_t)pl.n_qtiles * pl.ctas * 4 * pl.n_seg; }
 
-template <int CTAS>
+template <int CTAS, bool MASKED>
 static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
                           int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
-                          float* seg_top, float* seg_kth, int* seg_flag, cudaStream_t stream) {
+                          float* seg_top, float* seg_kth, int* seg_flag, const int64_t* mask_lo,
+                          const int64_t* mask_hi, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg<CTAS>::SMEM_BYTES));
     attr_done = true;
   }
@@ -616,15 +640,17 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   count_launch();
   // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
-  KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS>, map_q, map_p, n_query, n_pool, k_blocks, k, pl.n_qtiles,
-                              pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth, seg_flag, idesc,
-                              (uint32_t)opt_spin_ns()));
+  KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS, MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
+                              pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
+                              seg_flag, idesc, (uint32_t)opt_spin_ns(), mask_lo, mask_hi));
   return 0;
 }
 
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
-                      float* seg_kth, int* seg_flag, cudaStream_t stream) {
+                      float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
+                      cudaStream_t stream) {
+  KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -3, "mask_lo and mask_hi must be given together");
   KNN_CHECK_ARG(dim_pad % BK == 0 && dim_pad > 0, -3, "dim_pad %d must be a positive multiple of %d", dim_pad, BK);
   KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -3, "k=%d outside [1,%d]", k, kMaxK);
   KNN_CHECK_ARG(n_pool < (int64_t)1 << 31, -3, "pool shard of %lld rows exceeds int32 column indices", (long long)n_pool);
@@ -633,11 +659,16 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   if (rc) return rc;
   rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN / pl.ctas);
   if (rc) return rc;
-  if (pl.ctas == 2)
-    return launch_variant<2>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
-                             seg_kth, seg_flag, stream);
-  return launch_variant<1>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
-                           seg_kth, seg_flag, stream);
+#define KNN_FILTER_GO(C, M)                                                                                   \
+  return launch_variant<C, M>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top, \
+                              seg_kth, seg_flag, mask_lo, mask_hi, stream)
+  if (pl.ctas == 2) {
+    if (mask_lo) KNN_FILTER_GO(2, true);
+    KNN_FILTER_GO(2, false);
+  }
+  if (mask_lo) KNN_FILTER_GO(1, true);
+  KNN_FILTER_GO(1, false);
+#undef KNN_FILTER_GO
 }
 
 }  // namespace knnsvc

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ log_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
     const float* __restrict__ seg_top, int64_t index_offset, float* __restrict__ out_dist,
     int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list, int* __restrict__ flag_count,
-    int* __restrict__ stats) {
+    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
   extern __shared__ __align__(16) float s_q[];  // [dim]
   __shared__ float s_top[RS_MAXTOP];
   __shared__ double s_d[RS_WARPS][kMaxK];   // per-warp exact top-k, ascending by (dist, idx)
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     }
     const float thr = s_thr;
     const double qnorm = (double)qn[row];
+    // masked column range: distance defined as 1 (ddsp_prematch_dataset.py:1623-1624)
+    const int64_t m_lo = mask_lo ? mask_lo[row] : 0, m_hi = mask_lo ? mask_hi[row] : 0;
     int my_surv = 0;
     double kth_d = INFINITY;   // warp-uniform copy of this warp's current k-th best
     int kth_i = INT_MAX;
@@ -104,7 +106,9 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
           const int pr = __shfl_sync(0xffffffffu, cand, b);
           const float* prow = p + (int64_t)pr * dim;
           double acc = 0.0;
-          if ((dim & 3) == 0) {
+          const bool masked = pr >= m_lo && pr < m_hi;   // warp-uniform
+          if (masked) {
+          } else if ((dim & 3) == 0) {
             const float4* p4 = reinterpret_cast<const float4*>(prow);
             const float4* q4 = reinterpret_cast<const float4*>(s_q);
             for (int cc = lane; cc < dim / 4; cc += 32) {
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
             for (int cc = lane; cc < dim; cc += 32) acc += (double)__ldg(prow + cc) * (double)s_q[cc];
           }
           acc = warp_sum(acc);
-          const double d = 1.0 - acc / (qnorm * (double)pn[pr]);
+          const double d = masked ? 1.0 : 1.0 - acc / (qnorm * (double)pn[pr]);
           ++my_surv;
           if (rs_less(d, pr, kth_d, kth_i)) {
             if (lane == 0) {
@@ -165,7 +169,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       cudaStream_t stream) {
+                       const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream) {
   if (n_query == 0) return 0;
   KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
@@ -174,7 +178,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, log_val, log_idx, log_cnt, seg_top,
                                                                    index_offset, out_dist, out_idx, flag_list,
-                                                                   flag_count, stats);
+                                                                   flag_count, stats, mask_lo, mask_hi);
   KNN_LAUNCH_CHECK();
   return 0;
 }

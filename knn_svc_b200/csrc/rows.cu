@@ -182,13 +182,15 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
     const float* __restrict__ pn, int64_t n_pool, int dim, int k, const int64_t* __restrict__ row_list,
     const int* __restrict__ row_count_dev, int64_t row_count_host, int64_t slot_base, int64_t slot_cap,
     double* __restrict__ part_d, int64_t* __restrict__ part_i, int direct, int64_t index_offset,
-    float* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+    float* __restrict__ out_dist, int64_t* __restrict__ out_idx, const int64_t* __restrict__ mask_lo,
+    const int64_t* __restrict__ mask_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);                       // [EX_Q][dim]
   double* ld = reinterpret_cast<double*>(sq + (size_t)EX_Q * dim);      // [EX_WARPS][EX_Q][k]
   int64_t* li = reinterpret_cast<int64_t*>(ld + EX_WARPS * EX_Q * k);   // same shape
   __shared__ int64_t rows_s[EX_Q];
   __shared__ double qn_s[EX_Q];
+  __shared__ int64_t mlo_s[EX_Q], mhi_s[EX_Q];   // masked column range per query (distance := 1)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_chunks = gridDim.x;
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
       if (s < total) r = row_list ? row_list[s] : (slot_base + s);
       rows_s[threadIdx.x] = r;
       qn_s[threadIdx.x] = (r >= 0) ? (double)qn[r] : 1.0;
+      mlo_s[threadIdx.x] = (r >= 0 && mask_lo) ? mask_lo[r] : 0;
+      mhi_s[threadIdx.x] = (r >= 0 && mask_lo) ? mask_hi[r] : 0;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < EX_Q * dim; e += blockDim.x) {
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
         for (int qi = 0; qi < EX_Q; ++qi)
           if (qi == lane) dot = acc[qi];
         double d = 1.0 - dot / (qn_s[lane] * (double)pn[pr]);
+        if (pr >= mlo_s[lane] && pr < mhi_s[lane]) d = 1.0;
         double* ldq = ld + (warp * EX_Q + lane) * k;
         int64_t* liq = li + (warp * EX_Q + lane) * k;
         if (ex_less(d, pr, ldq[k - 1], liq[k - 1])) {
@@ -371,7 +376,8 @@ size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k) {
 int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
-                          float* out_dist, int64_t* out_idx, void* partial, cudaStream_t stream) {
+                          float* out_dist, int64_t* out_idx, void* partial, const int64_t* mask_lo,
+                          const int64_t* mask_hi, cudaStream_t stream) {
   const int n_chunks = exact_chunks(n_pool);
   double* part_d = reinterpret_cast<double*>(partial);
   int64_t* part_i = reinterpret_cast<int64_t*>(part_d + (size_t)slot_cap * n_chunks * k);
@@ -391,13 +397,13 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
   knn_exact_partial_kernel<<<grid, EX_WARPS * 32, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, row_list,
                                                                    row_count_dev, row_count_host, slot_base,
                                                                    slot_cap, part_d, part_i, 0, index_offset, out_dist,
-                                                                   out_idx);
+                                                                   out_idx, mask_lo, mask_hi);
   KNN_LAUNCH_CHECK();
   if (row_count_dev) {
     // many-rows regime (exits immediately unless the device-side count exceeds slot_cap)
     knn_exact_partial_kernel<<<dim3(1, 148 * 2), EX_WARPS * 32, smem, stream>>>(
         q, qn, n_query, p, pn, n_pool, dim, k, row_list, row_count_dev, row_count_host, slot_base, slot_cap, part_d,
-        part_i, 1, index_offset, out_dist, out_idx);
+        part_i, 1, index_offset, out_dist, out_idx, mask_lo, mask_hi);
     KNN_LAUNCH_CHECK();
   }
   int64_t mg = row_count_dev ? slot_cap : row_count_host;

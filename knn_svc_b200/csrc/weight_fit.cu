@@ -97,10 +97,15 @@ __device__ __forceinline__ void softmax4(const float* th, float* w) {
   for (int k = 0; k < 4; ++k) w[k] = e[k] / s;
 }
 
+// AMP: every candidate row is scaled by amp[t,k] before mixing (compute_weight_with_amp,
+// ddsp_prematch_dataset.py:684-803: `synth_set[...] * amp_ratio[:, :, None]` for all three
+// neighbour offsets), i.e. the loss is the same quadratic form in a (.) w instead of w.
+template <bool AMP>
 __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double* __restrict__ gram_all,
                                                                    const int64_t* __restrict__ utt_offsets,
                                                                    int64_t n_pairs_total, int dim, double loss_scale,
                                                                    int max_iters, WfState st_all, int smem_frames,
+                                                                   const float* __restrict__ amp_all,
                                                                    float* __restrict__ out_weights_all,
                                                                    double* __restrict__ info_all) {
   // one CTA per utterance: frames [f_begin, f_end) of the concatenated batch; every array is
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
   st.grad = st_all.grad + f_begin * 4;
   st.wglob = st_all.wglob + f_begin * 4;
   const double* gram = gram_all + f_begin;   // entry e of pair (t, t+1): gram[e * n_pairs_total + t]
+  const float* amp = AMP ? amp_all + f_begin * 4 : nullptr;
   const int use_smem = T <= smem_frames;
   volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
   const double norm = loss_scale / ((double)(T - 1) * (double)dim);
@@ -163,15 +169,18 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
     const int64_t NP = n_pairs_total;
     double part = 0.0;
     for (int64_t t = tid; t < T; t += WF_THREADS) {
-      double wt[4];
+      double wt[4], at[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) wt[k] = (double)wbuf[t * 4 + k];
+      for (int k = 0; k < 4; ++k) {
+        at[k] = AMP ? (double)amp[t * 4 + k] : 1.0;
+        wt[k] = (double)wbuf[t * 4 + k] * at[k];
+      }
       double g[4] = {0.0, 0.0, 0.0, 0.0};
       if (t >= 1) {  // pair t-1: this frame is the "t+1" member -> rows 0..3 of G u = A w[t] - B w[t-1]
         const double* G = gram + (t - 1);
         double wp[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wp[k] = (double)wbuf[(t - 1) * 4 + k];
+        for (int k = 0; k < 4; ++k) wp[k] = (double)wbuf[(t - 1) * 4 + k] * (AMP ? (double)amp[(t - 1) * 4 + k] : 1.0);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double y = 0.0;
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
         const double* G = gram + t;
         double wn[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wn[k] = (double)wbuf[(t + 1) * 4 + k];
+        for (int k = 0; k < 4; ++k) wn[k] = (double)wbuf[(t + 1) * 4 + k] * (AMP ? (double)amp[(t + 1) * 4 + k] : 1.0);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double y = 0.0;
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       }
       // gradient wrt w, cast to fp32 where the fp64 graph meets the fp32 softmax output
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st.grad[t * 4 + k] = (float)(2.0 * norm * g[k]);
+      for (int k = 0; k < 4; ++k) st.grad[t * 4 + k] = (float)(2.0 * norm * g[k] * at[k]);
     }
     part = warp_sum(part);
     if (lane == 0) s_red[warp] = part;
@@ -294,7 +303,7 @@ size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt) {
 // utterances (BASELINE cfg 5) fills the SMs.  info: double[n_utt][4].
 int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
                       const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
-                      float* out_weights, double* info, void* workspace, cudaStream_t stream) {
+                      const float* amp, float* out_weights, double* info, void* workspace, cudaStream_t stream) {
   KNN_CHECK_ARG(k == WF_K, -3, "weight_fit: k=%d, only k=%d is on the reference path", k, WF_K);
   if (n_utt == 0) return 0;
   const int64_t n_query = utt_offsets_host[n_utt];
@@ -332,12 +341,20 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   const size_t smem = smem_frames ? (size_t)smem_frames * 4 * sizeof(float) : 16;
   static bool attr_done = false;
   if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
     attr_done = true;
   }
-  weight_fit_kernel<<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1, dim,
-                                                         loss_scale, max_iters, st, smem_frames, out_weights, info);
+  if (amp)
+    weight_fit_kernel<true><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
+                                                                 dim, loss_scale, max_iters, st, smem_frames, amp,
+                                                                 out_weights, info);
+  else
+    weight_fit_kernel<false><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
+                                                                  dim, loss_scale, max_iters, st, smem_frames, nullptr,
+                                                                  out_weights, info);
   KNN_LAUNCH_CHECK();
   return 0;
 }

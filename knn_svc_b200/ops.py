@@ -113,10 +113,17 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 
 def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0,
-               return_stats: bool = False):
+               return_stats: bool = False, mask_lo: torch.Tensor | None = None,
+               mask_hi: torch.Tensor | None = None):
     """k smallest cosine distances per query row, ascending, with int64 pool
     indices — the fused replacement of fast_cosine_dist + topk
-    (ddsp_prematch_dataset.py:1196-1206, ddsp_matcher.py:550-554)."""
+    (ddsp_prematch_dataset.py:1196-1206, ddsp_matcher.py:550-554).
+
+    `mask_lo` / `mask_hi` ([T] int64, together): the pool columns [mask_lo[t], mask_hi[t]) of
+    query row t get distance exactly 1 — the offline prematch's self-utterance rule
+    `dists[:, start_index:end_index] = 1` (ddsp_prematch_dataset.py:1623-1624)."""
+    if (mask_lo is None) != (mask_hi is None):
+        raise ValueError("mask_lo and mask_hi must be given together")
     if not (1 <= k <= MAX_K):
         raise ValueError(f"k={k} outside [1,{MAX_K}]")
     if k > pool.n:
@@ -129,15 +136,20 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
     idx = torch.empty((T, k), dtype=torch.int64, device=dev)
     stats = torch.zeros((8,), dtype=torch.int32, device=dev)
     lib = _lib.load()
+    if mask_lo is not None:
+        mask_lo, mask_hi = _i64c(mask_lo.to(dev)), _i64c(mask_hi.to(dev))
+        if mask_lo.shape != (T,) or mask_hi.shape != (T,):
+            raise ValueError("mask_lo / mask_hi must have one entry per query row")
     if T > 0:
         with torch.cuda.device(dev):
             nbytes = lib.knnsvc_knn_workspace_bytes(T, pool.n, query.dim_pad, k)
             ws = _workspace(nbytes, dev)
-            _lib.check(lib.knnsvc_knn_search(query.rows.data_ptr(), query.half.data_ptr(), query.norms.data_ptr(), T,
-                                             pool.rows.data_ptr(), pool.half.data_ptr(), pool.norms.data_ptr(),
-                                             pool.n, query.dim, query.dim_pad, k, index_offset, dist.data_ptr(),
-                                             idx.data_ptr(), ws.data_ptr(), ws.numel(), stats.data_ptr(), _stream()),
-                       "knn_search")
+            _lib.check(lib.knnsvc_knn_search_masked(query.rows.data_ptr(), query.half.data_ptr(),
+                                                    query.norms.data_ptr(), T, pool.rows.data_ptr(),
+                                                    pool.half.data_ptr(), pool.norms.data_ptr(), pool.n, query.dim,
+                                                    query.dim_pad, k, index_offset, _ptr(mask_lo), _ptr(mask_hi),
+                                                    dist.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    stats.data_ptr(), _stream()), "knn_search")
     if return_stats:
         return dist, idx, stats
     return dist, idx
@@ -232,14 +244,20 @@ def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tenso
 
 
 def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_iters: int = 100000,
-               return_info: bool = False, utt_offsets=None):
+               return_info: bool = False, utt_offsets=None, amp_ratio: torch.Tensor | None = None):
     """Adam(amsgrad) fit of the softmax mixing weights (K6).  With `utt_offsets` the rows of
     `idx` are a concatenation of utterances, each fitted independently (one CTA each, one
-    launch); info is then [n_utt, 4]."""
+    launch); info is then [n_utt, 4].  `amp_ratio` [T,k] scales every candidate row before
+    mixing (compute_weight_with_amp, ddsp_prematch_dataset.py:684-803)."""
     _dev(synth, "synth_set")
     dev = synth.device
     idx, synth = _i64c(idx.to(dev)), _f32c(synth)
     T, k = idx.shape
+    amp = None
+    if amp_ratio is not None:
+        if tuple(amp_ratio.shape) != (T, k):
+            raise AssertionError("amp_ratio must have the shape of target_feature_indices")   # reference :687
+        amp = _f32c(amp_ratio.to(dev))
     offs = [0, T] if utt_offsets is None else [int(v) for v in utt_offsets]
     if offs[0] != 0 or offs[-1] != T:
         raise ValueError("utt_offsets must run from 0 to the number of frames")
@@ -253,10 +271,10 @@ def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_it
         with torch.cuda.device(dev):
             nbytes = lib.knnsvc_weight_fit_batched_workspace_bytes(T, k, n_utt)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            _lib.check(lib.knnsvc_weight_fit_batched(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1],
-                                                     ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
-                                                     int(max_iters), out.data_ptr(), info.data_ptr(), ws.data_ptr(),
-                                                     ws.numel(), _stream()), "weight_fit")
+            _lib.check(lib.knnsvc_weight_fit_amp(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1],
+                                                 ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
+                                                 int(max_iters), _ptr(amp), out.data_ptr(), info.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream()), "weight_fit")
     if utt_offsets is None:
         info = info[0]
     if return_info:

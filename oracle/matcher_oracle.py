@@ -69,11 +69,18 @@ def topk_smallest(dists: np.ndarray, k: int):
     return order.astype(np.int64), np.take_along_axis(dists, order, axis=-1)
 
 
-def knn(query: np.ndarray, pool: np.ndarray, k: int = 32):
-    """HOT LOOP A — ddsp_prematch_dataset.py:1196-1206: chunk-20 distance + top-32."""
+def knn(query: np.ndarray, pool: np.ndarray, k: int = 32, mask_lo=None, mask_hi=None):
+    """HOT LOOP A — ddsp_prematch_dataset.py:1196-1206: chunk-20 distance + top-32.
+    With mask_lo/mask_hi ([T] each) the columns [mask_lo[t], mask_hi[t]) of row t are set to
+    distance 1 before the top-k — the offline prematch's self-utterance rule,
+    `dists[:, start_index:end_index] = 1`, ddsp_prematch_dataset.py:1608-1632."""
     idx, val = [], []
     for a in range(0, len(query), 20):
-        i, v = topk_smallest(cosine_dist(query[a:a + 20], pool, direct=False if len(pool) > 25 else None), k)
+        d = cosine_dist(query[a:a + 20], pool, direct=False if len(pool) > 25 else None)
+        if mask_lo is not None:
+            for r in range(d.shape[0]):
+                d[r, int(mask_lo[a + r]):int(mask_hi[a + r])] = 1.0
+        i, v = topk_smallest(d, k)
         idx.append(i)
         val.append(v)
     return np.concatenate(idx, 0), np.concatenate(val, 0)
@@ -231,7 +238,8 @@ def smoothness_loss(weights: np.ndarray, rows, scale: float) -> float:
     return float(scale * (r1 ** 2).mean(-1).mean() + scale * (r2 ** 2).mean(-1).mean())
 
 
-def compute_weight(idx, synth, scale: float, max_iters: int = 100000, return_info: bool = False):
+def compute_weight(idx, synth, scale: float, max_iters: int = 100000, return_info: bool = False,
+                   amp_ratio=None):
     """Adam(amsgrad) fit of per-frame softmax mixing weights —
     compute_wavlm_weight ddsp_prematch_dataset.py:574-680 (scale 0.1) and
     compute_extended_weight :807-924 (scale 1000; its `scaling_factors`
@@ -245,12 +253,19 @@ def compute_weight(idx, synth, scale: float, max_iters: int = 100000, return_inf
     of `synth` promoted with fp32 weights (fp64 on the real path), and its
     gradient is cast to fp32 before the softmax backward — mirrored here.
     The AMSGrad update follows torch.optim.Adam's documented single-tensor form.
+
+    `amp_ratio` [T,K] (compute_weight_with_amp, :684-803): every gathered row is multiplied
+    by amp_ratio[t,k] for all three neighbour offsets (:713) before the same loop runs.
     """
     idx = np.asarray(idx, dtype=np.int64)
     synth = np.asarray(synth, dtype=np.float64)
     t_len, k = idx.shape
     d = synth.shape[-1]
     rows = _neighbour_rows(idx, synth)
+    if amp_ratio is not None:
+        amp = np.asarray(amp_ratio, dtype=np.float64)
+        assert amp.shape == idx.shape                                     # :687
+        rows = [r * amp[..., None] for r in rows]
     theta = np.zeros((t_len, k), dtype=np.float32)
     m = np.zeros_like(theta)
     v = np.zeros_like(theta)
@@ -313,6 +328,11 @@ def compute_wavlm_weight(idx, synth, **kw):
 
 def compute_extended_weight(idx, synth, **kw):
     return compute_weight(idx, synth, 1000.0, **kw)
+
+
+def compute_weight_with_amp(idx, synth, amp_ratio=None, **kw):
+    """ddsp_prematch_dataset.py:684-803 (phase_mae: 1000*MSE, :449-457)."""
+    return compute_weight(idx, synth, 1000.0, amp_ratio=amp_ratio, **kw)
 
 
 # --------------------------------------------------------------------------- K7
@@ -427,4 +447,107 @@ def match_utterance(query, query_f0, pool, pool_f0, harmonics, post_opt="no_post
             out["harmonics"] = gather_mix(harmonics, idx_h, wh)      # :1444
         else:
             out["harmonics"] = gather_mix(harmonics, idx_h, None)    # :1446
+    return out
+
+
+# --------------------------------------------------------------------------- §8f rank 3: pool-builder tensor ops
+
+
+def layer_mix(feats: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """`(feats * weights[:, None]).sum(dim=0)` — ddsp_prematch_dataset.py:349-350.
+    feats [L,T,D], weights [L,1] or [L] -> [T,D] (float64, as the reference's float64
+    weighting produces)."""
+    f = np.asarray(feats, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    return np.einsum("ltd,l->td", f, w)
+
+
+def stft_magnitude(x: np.ndarray, n_frames: int | None = None, n_fft: int = 400, hop: int = 320) -> np.ndarray:
+    """`torchaudio.transforms.Spectrogram(n_fft=400, hop_length=320, center=True, power=1)`
+    (periodic Hann window, reflect padding, one-sided) followed by `.T[:, :-1]` and the crop to
+    the WavLM frame count — ddsp_prematch_dataset.py:326, :361-363.  x [N] -> [frames, n_fft/2]."""
+    x = np.asarray(x, dtype=np.float64)
+    pad = n_fft // 2
+    xp = np.pad(x, (pad, pad), mode="reflect")
+    frames = 1 + len(x) // hop
+    win = 0.5 - 0.5 * np.cos(2.0 * math.pi * np.arange(n_fft) / n_fft)
+    seg = np.stack([xp[i * hop:i * hop + n_fft] for i in range(frames)]) * win[None, :]
+    mag = np.abs(np.fft.rfft(seg, axis=1))[:, :-1]
+    return mag if n_frames is None else mag[:n_frames]
+
+
+def interp_linear(spec: np.ndarray, factor: int = 8) -> np.ndarray:
+    """`F.interpolate(spec[None], scale_factor=8, mode='linear')` along the frequency axis
+    (align_corners=False) — ddsp_prematch_dataset.py:395.  [T,S] -> [T,S*factor]; torch
+    evaluates the source position and both weights in the tensor dtype (fp32)."""
+    spec = np.asarray(spec, dtype=np.float32)
+    s_in = spec.shape[1]
+    j = np.arange(s_in * factor, dtype=np.float32)
+    src = np.maximum(np.float32(1.0 / factor) * (j + np.float32(0.5)) - np.float32(0.5), np.float32(0)).astype(np.float32)
+    i0 = np.floor(src).astype(np.int64)
+    i1 = np.minimum(i0 + 1, s_in - 1)
+    lam1 = (src - i0.astype(np.float32)).astype(np.float32)
+    lam0 = (np.float32(1) - lam1).astype(np.float32)
+    # torch's CPU kernel evaluates lam0*x0 + lam1*x1 as fma(lam0, x0, round(lam1*x1)) (measured:
+    # bit-exact on the fixture); the device kernel uses the same contraction.
+    hi = (lam1[None, :] * spec[:, i1]).astype(np.float32).astype(np.float64)
+    return (lam0[None, :].astype(np.float64) * spec[:, i0].astype(np.float64) + hi).astype(np.float32)
+
+
+def harmonic_amplitudes(spec: np.ndarray, f0: np.ndarray, n_harm: int = 49, sr: int = 16000) -> np.ndarray:
+    """Amplitudes of the first 49 harmonics read off the x8-interpolated magnitude spectrum —
+    ddsp_prematch_dataset.py:391-404.  spec [T,S] (S=200), f0 [T] -> [T,49] fp32:
+    bin = round(clamp(f0*h*2*(8S)/sr, max=8S)) into the spectrum padded with one 0;
+    unvoiced frames (f0 == 0): harmonic 1 = max of the raw spectrum row, others 0; all x0.0108."""
+    spec = np.asarray(spec, dtype=np.float32)
+    f0 = np.asarray(f0, dtype=np.float32)
+    up = interp_linear(spec, 8)
+    n_up = up.shape[1]
+    h = np.arange(1, n_harm + 1, dtype=np.float32)
+    mh = (f0[:, None] * h[None, :]).astype(np.float32)                       # :391
+    pos = (((mh * np.float32(2)).astype(np.float32) * np.float32(n_up)).astype(np.float32) / np.float32(sr)).astype(np.float32)
+    bins = np.rint(np.minimum(pos, np.float32(n_up))).astype(np.int64)       # :397 (round half to even)
+    padded = np.concatenate([up, np.zeros((len(up), 1), np.float32)], axis=1)   # F.pad(.., (0, 1))
+    out = np.take_along_axis(padded, bins, axis=1)
+    unvoiced = f0 == 0
+    out[unvoiced, 1:] = 0                                                    # :401
+    out[unvoiced, 0] = spec.max(1)[unvoiced]                                 # :402
+    return (np.float32(0.0108) * out).astype(np.float32)                     # :404
+
+
+def amp_ratio(spec_query: np.ndarray, spec_pool: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """L1-norm ratio of the utterance's own spectrum rows to the gathered candidates' —
+    ddsp_prematch_dataset.py:1672-1675.  [T,S], [Np,S], [T,K] -> [T,K]."""
+    orig = np.abs(np.asarray(spec_query, dtype=np.float64)).sum(1)
+    knn_l1 = np.abs(np.asarray(spec_pool, dtype=np.float64)).sum(1)[idx]
+    return orig[:, None] / (knn_l1 + 1e-5)
+
+
+# --------------------------------------------------------------------------- §8f rank 1: offline prematch
+
+
+def half_round(x: np.ndarray) -> np.ndarray:
+    """`.half().float()` — ddsp_prematch_dataset.py:1510, :1567, :1613."""
+    return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float32)
+
+
+def prematch_utterance(start: int, end: int, matching_list: np.ndarray, f0_list: np.ndarray,
+                       spec_list: np.ndarray, harmonics_list: np.ndarray, fit: bool = True, nbrs=None):
+    """Body of per_spk_extract for ONE utterance occupying pool rows [start, end) —
+    ddsp_prematch_dataset.py:1608-1769: masked top-32 against the speaker's own pool, f0
+    re-rank, amp_ratio, compute_weight_with_amp.  `matching_list` is the `.half().float()`
+    rounded pool (:1567); the query rows are the same rows (:1613)."""
+    t_len = end - start
+    q = matching_list[start:end]
+    lo = np.full(t_len, start, np.int64)
+    hi = np.full(t_len, end, np.int64)
+    if nbrs is None:   # (tests pass the reference's own top-32 to compare the later stages past tied slots)
+        nbrs, _ = knn(q, matching_list, 32, lo, hi)                          # :1608-1632
+    prio = sort_by_f0_compatibility(f0_list[start:end], f0_list, nbrs)       # :1646
+    idx = prio[:, :4].copy()                                                 # :1655
+    ratio = amp_ratio(spec_list[start:end], spec_list, idx)                  # :1672-1675
+    out = {"slice": (start, end), "nearest_nbrs": nbrs, "nearest_nbrs_f0_priority": prio,
+           "amp_ratio": ratio.astype(np.float32)}
+    if fit:
+        out["harmonics_best_weight_para"] = compute_weight_with_amp(idx, harmonics_list, amp_ratio=ratio)   # :1681
     return out

@@ -20,6 +20,12 @@ def golden():
     return dict(np.load(ROOT / "tests" / "golden" / "reference_outputs.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_pm():
+    """Reference outputs for the SURVEY §8(f) rows (tests/golden/make_golden_prematch.py)."""
+    return dict(np.load(ROOT / "tests" / "golden" / "prematch_outputs.npz"))
+
+
 def has_gpu():
     try:
         import torch

@@ -27,3 +27,23 @@ def check_knn_against_oracle(idx, dist, o_idx, o_val, k, min_cover=0.3):
     rows = set_rows(o_val, k)
     assert np.array_equal(np.sort(idx[rows], 1), np.sort(o_idx[rows, :k], 1)), "top-k set mismatch"
     return m.mean(), rows.mean()
+
+
+def prematch_inputs(golden_pm):
+    """Seeded synthetic speaker (3 utterances) of tests/golden/make_golden_prematch.py;
+    the f0 track is real data and comes from the fixture."""
+    from knn_svc_b200 import synth
+    lens = [60, 90, 50]
+    feats = synth.ar1_frames(sum(lens), seed=61, reset_every=70)
+    spec = np.abs(synth.randn_frames(sum(lens), 200, seed=62)).astype(np.float32) + 0.05
+    harm = synth.harmonics_pool(sum(lens), seed=63)
+    return lens, feats, spec, harm, golden_pm["pm_f0"]
+
+
+def pool_builder_inputs(golden_pm):
+    """audio crop (float32 in [-1,1)), layer features [25,T,64], f0 of the pool-builder fixture"""
+    from knn_svc_b200 import synth
+    x = golden_pm["pb_pcm"].astype(np.float32) / 32768.0
+    T = golden_pm["pb_spec"].shape[0]
+    layer_feats = synth.randn_frames(25 * T, 64, seed=71).reshape(25, T, 64)
+    return x, layer_feats, golden_pm["pb_f0"][:T]
