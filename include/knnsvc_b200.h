@@ -174,6 +174,32 @@ int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t f
                          int n_harm, int sample_rate, int hop, float* out,
                          double* phase_ws, void* stream);
 
+/* ==== SURVEY §8(f): the tensor ops either side of the matcher ==============
+ * Pool builder (get_complete_spk_pool, ddsp_prematch_dataset.py:301-423) after WavLM: */
+
+/* (feats*weights[:, None]).sum(dim=0) — :349-350.  feats [n_layers, frames, dim] fp32;
+ * weights_*_host: HOST double[n_layers] (the reference's weighting is float64);
+ * both mixes (matching + synthesis weights) in one pass; weights_b_host/out_b may be NULL. */
+int knnsvc_layer_mix(const float* feats, int n_layers, int64_t frames, int dim,
+                     const double* weights_a_host, const double* weights_b_host,
+                     float* out_a, float* out_b, void* stream);
+
+/* torchaudio Spectrogram(n_fft=400, hop_length=320, center=True, power=1)(x).T[:, :-1][:frames]
+ * — :326, :361-363.  audio [n_samples] fp32 -> out [frames, n_fft/2] fp32 magnitudes. */
+int knnsvc_stft_magnitude(const float* audio, int64_t n_samples, int64_t frames, int n_fft, int hop,
+                          float* out, void* stream);
+
+/* Harmonic amplitudes read off the x8-interpolated spectrum — :391-404.
+ * spec [frames, n_bins] (n_bins = 200), f0 [frames] -> out [frames, n_harm] (n_harm = 49). */
+int knnsvc_harmonic_amplitudes(const float* spec, const float* f0, int64_t frames, int n_bins,
+                               int n_harm, int sample_rate, float* out, void* stream);
+
+/* Offline prematch (per_spk_extract :1672-1675): amp_ratio[t,k] =
+ * |spec_utt[t]|_1 / (|spec_pool[idx[t,k]]|_1 + 1e-5).  knnsvc_row_l1: out[r] = sum |x[r,:]|. */
+int knnsvc_row_l1(const float* x, int64_t rows, int dim, float* out, void* stream);
+int knnsvc_amp_ratio(const float* l1_query, const float* l1_pool, const int64_t* idx,
+                     int64_t n_query, int k, int64_t n_pool, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

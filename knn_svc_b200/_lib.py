@@ -41,6 +41,11 @@ SIGNATURES = {
     "knnsvc_weight_fit_batched": (i32, [vp, vp, i64, i32, vp, i32, i32, f64, i32, vp, vp, vp, sz, vp]),
     "knnsvc_weight_fit_amp": (i32, [vp, vp, i64, i32, vp, i32, i32, f64, i32, vp, vp, vp, vp, sz, vp]),
     "knnsvc_harmonic_bank": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]),
+    "knnsvc_layer_mix": (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp]),
+    "knnsvc_stft_magnitude": (i32, [vp, i64, i64, i32, i32, vp, vp]),
+    "knnsvc_harmonic_amplitudes": (i32, [vp, vp, i64, i32, i32, i32, vp, vp]),
+    "knnsvc_row_l1": (i32, [vp, i64, i32, vp, vp]),
+    "knnsvc_amp_ratio": (i32, [vp, vp, vp, i64, i32, i64, vp, vp]),
 }
 
 

@@ -16,7 +16,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 LIB = PKG / "libknnsvc_b200.so"
-SOURCES = ["capi.cu", "rows.cu", "knn_filter_sm100.cu", "knn_select.cu", "post.cu", "concat_cost_sm100.cu", "weight_fit.cu", "harmonic.cu"]
+SOURCES = ["capi.cu", "rows.cu", "knn_filter_sm100.cu", "knn_select.cu", "post.cu", "concat_cost_sm100.cu", "weight_fit.cu", "harmonic.cu",
+           "pool_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

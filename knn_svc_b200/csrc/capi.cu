@@ -333,4 +333,37 @@ int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t f
   return launch_harmonic_bank(f0, amp, batch, frames, n_harm, sample_rate, hop, out, phase_ws, (cudaStream_t)stream);
 }
 
+int knnsvc_layer_mix(const float* feats, int n_layers, int64_t frames, int dim, const double* weights_a_host,
+                     const double* weights_b_host, float* out_a, float* out_b, void* stream) {
+  KNN_CHECK_ARG(feats && weights_a_host && out_a && frames >= 0 && dim >= 1, -1, "layer_mix: bad arguments");
+  KNN_CHECK_ARG((weights_b_host == nullptr) == (out_b == nullptr), -1,
+                "layer_mix: weights_b_host and out_b must be given together");
+  return launch_layer_mix(feats, n_layers, frames, dim, weights_a_host, weights_b_host, out_a, out_b,
+                          (cudaStream_t)stream);
+}
+
+int knnsvc_stft_magnitude(const float* audio, int64_t n_samples, int64_t frames, int n_fft, int hop, float* out,
+                          void* stream) {
+  KNN_CHECK_ARG(audio && out && n_samples >= 1 && frames >= 0, -1, "stft_magnitude: bad arguments");
+  return launch_stft_magnitude(audio, n_samples, frames, n_fft, hop, out, (cudaStream_t)stream);
+}
+
+int knnsvc_harmonic_amplitudes(const float* spec, const float* f0, int64_t frames, int n_bins, int n_harm,
+                               int sample_rate, float* out, void* stream) {
+  KNN_CHECK_ARG(spec && f0 && out && frames >= 0 && sample_rate > 0, -1, "harmonic_amplitudes: bad arguments");
+  return launch_harmonic_amplitudes(spec, f0, frames, n_bins, n_harm, sample_rate, out, (cudaStream_t)stream);
+}
+
+int knnsvc_row_l1(const float* x, int64_t rows, int dim, float* out, void* stream) {
+  KNN_CHECK_ARG(x && out && rows >= 0 && dim >= 1, -1, "row_l1: bad arguments");
+  return launch_row_l1(x, rows, dim, out, (cudaStream_t)stream);
+}
+
+int knnsvc_amp_ratio(const float* l1_query, const float* l1_pool, const int64_t* idx, int64_t n_query, int k,
+                     int64_t n_pool, float* out, void* stream) {
+  KNN_CHECK_ARG(l1_query && l1_pool && idx && out && n_query >= 0 && k >= 1 && n_pool >= 1, -1,
+                "amp_ratio: bad arguments");
+  return launch_amp_ratio(l1_query, l1_pool, idx, n_query, k, n_pool, out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -71,4 +71,16 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
 int launch_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,
                          int hop, float* out, double* phase_ws, cudaStream_t stream);
 
+// ---- pool_ops.cu
+constexpr int kMaxLayers = 32;   // WavLM-Large exposes 25 layer outputs
+int launch_layer_mix(const float* feats, int n_layers, int64_t frames, int dim, const double* w_a_host,
+                     const double* w_b_host, float* out_a, float* out_b, cudaStream_t stream);
+int launch_stft_magnitude(const float* audio, int64_t n_samples, int64_t frames, int n_fft, int hop, float* out,
+                          cudaStream_t stream);
+int launch_harmonic_amplitudes(const float* spec, const float* f0, int64_t frames, int n_bins, int n_harm,
+                               int sample_rate, float* out, cudaStream_t stream);
+int launch_row_l1(const float* x, int64_t rows, int dim, float* out, cudaStream_t stream);
+int launch_amp_ratio(const float* l1_query, const float* l1_pool, const int64_t* idx, int64_t n_query, int k,
+                     int64_t n_pool, float* out, cudaStream_t stream);
+
 }  // namespace knnsvc

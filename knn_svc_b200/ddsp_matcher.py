@@ -179,13 +179,17 @@ class KNeighborsVC(nn.Module):
 
     def bulk_match(self, src_dataset_path, tgt_dataset_path, converted_audio_dir, topk: int = 4, device=None,
                    prioritize_f0=True, ckpt_type="mix", tgt_loudness_db=-16, required_subset_file=None,
-                   post_opt="no_post_opt", duration_limit=None):
+                   post_opt="no_post_opt", duration_limit=None, cache_pools: bool = True):
         """Dataset -> dataset conversion over (source speaker, target speaker) folder pairs
         (reference :1027-1150).  The split file lists `<utt>/<tgt_spk>` pairs in column 2 of
-        rows labelled "0"."""
+        rows labelled "0".  `cache_pools` keeps every speaker's pool (WavLM features, and for
+        targets the HBM-resident prepared pool) across the pair loop instead of rebuilding both
+        for each pair as the reference does (:1073-1112); results are identical."""
         import csv
         import torchaudio
+        from .ddsp_prematch_dataset import PoolCache
         device = torch.device(device) if device is not None else self.device
+        cache = PoolCache() if cache_pools else None
         required = None
         if required_subset_file is not None:
             with open(required_subset_file) as fh:
@@ -198,7 +202,7 @@ class KNeighborsVC(nn.Module):
                     continue
                 res = self._convert(s_dir, t_dir, topk, device, prioritize_f0, ckpt_type, post_opt,
                                     src_dataset_path=src_dataset_path, tgt_dataset_path=tgt_dataset_path,
-                                    required_subset=required, duration_limit=duration_limit)
+                                    required_subset=required, duration_limit=duration_limit, pool_cache=cache)
                 feats, f0 = res[0], res[-1]
                 harm = res[1] if len(res) == 4 else None
                 for item in feats:

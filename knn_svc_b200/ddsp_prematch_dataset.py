@@ -76,6 +76,17 @@ def compute_extended_weight(target_feature_indices, synth_set, process_type="sum
     return ops.weight_fit(target_feature_indices, synth_set, 1000.0, utt_offsets=utt_offsets)
 
 
+def compute_weight_with_amp(target_feature_indices, synth_set, process_type="sum_to_1_geq", amp_ratio=None,
+                            utt_offsets=None):
+    """Training-time variant of the fit (offline prematch): every candidate row is scaled by
+    amp_ratio[t,k] before mixing, loss 1000*MSE — reference :684-803, called at :1681."""
+    if process_type != "sum_to_1_geq":
+        raise NotImplementedError("only sum_to_1_geq is on the reference's live path")
+    if amp_ratio is not None:
+        assert amp_ratio.shape == target_feature_indices.shape                      # :687
+    return ops.weight_fit(target_feature_indices, synth_set, 1000.0, utt_offsets=utt_offsets, amp_ratio=amp_ratio)
+
+
 def get_bulk_dsp_choral(f0, amp, sample_rate=16000, hop_size=320):
     """Additive harmonic bank — reference :165-208.  f0 [B,T,1], amp [B,T,H] -> [B,T*hop,1]."""
     assert f0.device == amp.device, [f0.device, amp.device]
@@ -206,27 +217,66 @@ def match_utterance(query_seq, query_f0, pool: MatchingPool, post_opt="no_post_o
                             prioritize_f0=prioritize_f0)[0]
 
 
+class PoolCache:
+    """In-process cache of speaker pools for dataset -> dataset conversion.
+    The reference rebuilds both pools — WavLM over every file of both speakers — for every
+    (source speaker, target speaker) pair and force-disables its pickle cache
+    (ddsp_prematch_dataset.py:1086-1087, ddsp_matcher.py:1073-1112).  Here the query-side
+    feature dicts and the target side's HBM-resident `MatchingPool` (fp32 rows, fp16 operand,
+    norms, f0 median) are kept per (path, duration_limit), least recently used evicted first."""
+
+    def __init__(self, max_entries: int = 16):
+        from collections import OrderedDict
+        self.max_entries = max_entries
+        self._d = OrderedDict()
+        self.hits = 0
+        self.misses = 0
+
+    def get(self, key, build):
+        if key in self._d:
+            self._d.move_to_end(key)
+            self.hits += 1
+            return self._d[key]
+        self.misses += 1
+        val = build()
+        self._d[key] = val
+        while len(self._d) > self.max_entries:
+            self._d.popitem(last=False)
+        return val
+
+
 def match_at_inference_time(src_wav_file, ref_wav_file, wavlm, match_weights, synth_weights, topk: int = 4,
                             device="cuda", prioritize_f0=False, ckpt_type="wavlm_only", src_dataset_path=None,
                             tgt_dataset_path=None, cache_dir=None, required_subset=None, post_opt="no_post_opt",
-                            duration_limit=None):
+                            duration_limit=None, pool_cache: "PoolCache | None" = None):
     """Same call, same returns as the reference (ddsp_prematch_dataset.py:1074-1459):
     dicts keyed by query file of matched features [T,D] fp32, (mix only) mixed
-    harmonics [T,49], a dict of None, and the shifted f0 [T]."""
+    harmonics [T,49], a dict of None, and the shifted f0 [T].  `pool_cache` (extension,
+    default off = the reference's behaviour) reuses pools across calls, see PoolCache."""
     if src_dataset_path is None:
         assert os.path.isfile(src_wav_file)
-    query_pool, _, _, query_spec_pool, query_f0_pool, _ = get_complete_spk_pool(
-        src_wav_file, wavlm, match_weights, synth_weights, device=device)
+
+    def build_query():
+        return get_complete_spk_pool(src_wav_file, wavlm, match_weights, synth_weights, device=device)
+
+    def build_target():
+        matching_pool, synth_pool, audio_synth_pool, spec_synth_pool, f0_pool, harmonics_synth_pool = \
+            get_complete_spk_pool(ref_wav_file, wavlm, match_weights, synth_weights, device=device,
+                                  duration_limit=duration_limit)
+        keys = list(matching_pool)
+        return MatchingPool(torch.concat([matching_pool[k] for k in keys], dim=0),
+                            torch.concat([synth_pool[k] for k in keys], dim=0),
+                            torch.concat([f0_pool[k] for k in keys], dim=0),
+                            torch.concat([harmonics_synth_pool[k] for k in keys], dim=0), device)
+
     if tgt_dataset_path is None:
         assert os.path.isfile(ref_wav_file)
-    matching_pool, synth_pool, audio_synth_pool, spec_synth_pool, f0_pool, harmonics_synth_pool = \
-        get_complete_spk_pool(ref_wav_file, wavlm, match_weights, synth_weights, device=device,
-                              duration_limit=duration_limit)
-    keys = list(matching_pool)
-    pool = MatchingPool(torch.concat([matching_pool[k] for k in keys], dim=0),
-                        torch.concat([synth_pool[k] for k in keys], dim=0),
-                        torch.concat([f0_pool[k] for k in keys], dim=0),
-                        torch.concat([harmonics_synth_pool[k] for k in keys], dim=0), device)
+    if pool_cache is None:
+        query_side, pool = build_query(), build_target()
+    else:
+        query_side = pool_cache.get(("query", str(src_wav_file), str(device)), build_query)
+        pool = pool_cache.get(("target", str(ref_wav_file), duration_limit, str(device)), build_target)
+    query_pool, _, _, query_spec_pool, query_f0_pool, _ = query_side
     out_feats_weighted_collection = dict()
     harmonics_out_feats_weighted_collection = dict()
     audio_out_feats_weighted_collection = dict()
@@ -249,3 +299,141 @@ def match_at_inference_time(src_wav_file, ref_wav_file, wavlm, match_weights, sy
         return (out_feats_weighted_collection, harmonics_out_feats_weighted_collection,
                 audio_out_feats_weighted_collection, shifted_query_f0_collection)
     raise NotImplementedError
+
+
+# ----------------------------------------------------------------------------- SURVEY §8(f)
+# rank 3: the tensor arithmetic of the pool builder after WavLM; rank 1: the offline prematch.
+
+
+def spk_pool_from_features(feats, x, f0, match_weights, synth_weights, device="cuda"):
+    """Tensor part of get_complete_spk_pool for ONE utterance (reference :347-404): given the
+    WavLM layer stack `feats` [L,T,D], the mono 16 kHz waveform `x` [N] and the f0 track
+    [T or T+1], returns (matching [T,D], synth [T,D], audio frames [T,320], spec [T,200],
+    f0 [T], harmonic amplitudes [T,49]) — all on `device`, fp32.  WavLM, file IO and pyworld
+    (the producers of feats / x / f0) stay with the caller."""
+    dev = torch.device(device)
+    feats = feats.to(dev)
+    mw = match_weights.detach().cpu().double().reshape(-1).numpy()
+    sw = synth_weights.detach().cpu().double().reshape(-1).numpy()
+    matching, synth = ops.layer_mix(feats, mw, sw)                                   # :349-350
+    T = matching.shape[0]
+    x = x.to(dev).reshape(-1).float()
+    assert len(x) >= DOWNSAMPLE_FACTOR * T                                           # :354
+    audio = x[:DOWNSAMPLE_FACTOR * T].reshape(T, DOWNSAMPLE_FACTOR)                  # :355
+    spec = ops.stft_magnitude(x, T, 400, DOWNSAMPLE_FACTOR)                          # :326, :361-363
+    assert abs(len(f0) - T) <= 1 and len(f0) >= T                                    # :385
+    f0 = f0[:T].to(dev).float()
+    harmonics = ops.harmonic_amplitudes(spec, f0, 49, 16000)                         # :391-404
+    return matching, synth, audio, spec, f0, harmonics
+
+
+def prematch_speaker(matching_list, f0_list, spec_list, harmonics_list, utterance_start_indices, fit=True):
+    """Tensor-level body of per_spk_extract for ONE speaker (reference :1560-1769), all
+    utterances at once: the speaker's `.half().float()` pool is matched against itself with
+    every utterance's own frames masked to distance 1 (:1623-1624) in ONE fused search, then
+    one f0 re-rank, one amp_ratio gather and one batched compute_weight_with_amp launch
+    (one CTA per utterance).  Returns per-utterance dicts in the on-disk layout (:1750-1769)."""
+    dev = matching_list.device
+    offs = [int(v) for v in utterance_start_indices]
+    n = offs[-1]
+    assert n == len(matching_list)                                                   # :1514
+    pool = ops.prepare_rows(matching_list)
+    lens = torch.tensor([offs[u + 1] - offs[u] for u in range(len(offs) - 1)], device=dev)
+    starts = torch.tensor(offs[:-1], device=dev, dtype=torch.int64)
+    mask_lo = torch.repeat_interleave(starts, lens)
+    mask_hi = torch.repeat_interleave(starts + lens, lens)
+    _, nearest_nbrs = ops.knn_search(pool, pool, 32, mask_lo=mask_lo, mask_hi=mask_hi)          # :1608-1632
+    f0_dev = f0_list.to(dev).float()
+    prio = sort_by_f0_compatibility(f0_dev, f0_dev, nearest_nbrs)                    # :1646
+    idx = prio[:, :4].contiguous()                                                   # :1655
+    l1 = ops.row_l1(spec_list.to(dev))                                               # :1672-1673
+    ratio = ops.amp_ratio(l1, l1, idx)                                               # :1674
+    weights = compute_weight_with_amp(idx, harmonics_list.to(dev), "sum_to_1_geq", amp_ratio=ratio,
+                                      utt_offsets=offs) if fit else None             # :1681
+    out = []
+    for u in range(len(offs) - 1):
+        a, b = offs[u], offs[u + 1]
+        d = {"slice": (a, b), "nearest_nbrs": nearest_nbrs[a:b], "nearest_nbrs_f0_priority": prio[a:b],
+             "amp_ratio": ratio[a:b]}
+        if weights is not None:
+            d["harmonics_best_weight_para"] = weights[a:b]
+        out.append(d)
+    return out
+
+
+def per_spk_extract(wavlm, device, ls_path, out_path, synth_weights, match_weights, save_pool_only=False):
+    """Offline prematch, speaker by speaker — same call and same files as the reference
+    (:1464-1770): `<out>/<spk>/pool.npy`, `pool_harmonics.npy` (and `pool_f0.npy`,
+    `pool_spec.npy` with save_pool_only) plus one pickle per utterance
+    {slice, nearest_nbrs [T,32], nearest_nbrs_f0_priority [T,32], harmonics_best_weight_para
+    [T,4], amp_ratio [T,4]} that hifigan/ddsp_meldataset.py:473-486 and
+    hifigan/knn_data_cnpop.py:200-207 read.  The feature producer `get_complete_spk_pool` is the
+    module attribute (the reference's, unless the caller assigns another)."""
+    import pickle
+    from pathlib import Path
+
+    import numpy as np
+    ls_path, out_path = Path(ls_path), Path(out_path)
+    audio_files = list(ls_path.glob("**/*.wav")) + list(ls_path.glob("**/*.flac"))
+    spk_folders = list(set(f.parent for f in audio_files))                           # :1473
+    dev = torch.device(device)
+    for i, folder in enumerate(spk_folders):
+        matching_pool, synth_pool, audio_synth_pool, spec_synth_pool, f0_pool, harmonics_synth_pool = \
+            get_complete_spk_pool(folder, wavlm, match_weights, synth_weights, device=device)
+        items = list(matching_pool)
+        offs = [0]
+        for item in items:
+            offs.append(offs[-1] + len(matching_pool[item]))
+        synth_list = torch.concat([synth_pool[k] for k in items], dim=0).half().float()          # :1510
+        spec_list = torch.concat([spec_synth_pool[k] for k in items], dim=0)
+        f0_list = torch.concat([f0_pool[k] for k in items], dim=0)
+        harmonics_list = torch.concat([harmonics_synth_pool[k] for k in items], dim=0)
+        assert offs[-1] == len(synth_list)                                           # :1514
+        spk_cache_folder = out_path / folder.relative_to(ls_path)
+        os.makedirs(spk_cache_folder, exist_ok=True)
+        np.save(str(spk_cache_folder / "pool.npy"), synth_list.cpu().numpy())        # :1534
+        np.save(str(spk_cache_folder / "pool_harmonics.npy"), harmonics_list.cpu().numpy())      # :1536
+        results = None
+        if save_pool_only:
+            np.save(str(spk_cache_folder / "pool_f0.npy"), f0_list.cpu().numpy())    # :1595-1597
+            np.save(str(spk_cache_folder / "pool_spec.npy"), spec_list.cpu().numpy())
+        else:
+            matching_list = torch.concat([matching_pool[k] for k in items], dim=0).to(dev).half().float()   # :1567
+            results = prematch_speaker(matching_list, f0_list, spec_list, harmonics_list, offs)
+        for k, item in enumerate(items):
+            target = out_path / Path(item).relative_to(ls_path).with_suffix(".pt")
+            os.makedirs(target.parent, exist_ok=True)
+            existing = {"slice": (offs[k], offs[k + 1])}
+            if os.path.isfile(target):
+                with open(target, "rb") as handle:
+                    existing = pickle.load(handle)
+                assert existing["slice"] == (offs[k], offs[k + 1])                   # :1587
+            if results is not None:
+                r = results[k]
+                existing["nearest_nbrs"] = r["nearest_nbrs"].cpu().numpy()           # :1754
+                existing["nearest_nbrs_f0_priority"] = r["nearest_nbrs_f0_priority"].cpu().numpy()
+                existing["harmonics_best_weight_para"] = r["harmonics_best_weight_para"].cpu().numpy()
+                existing.pop("best_weights", None)                                   # :1761-1762
+                existing["amp_ratio"] = r["amp_ratio"].cpu().numpy()
+            with open(target, "wb") as handle:
+                pickle.dump(existing, handle, protocol=pickle.HIGHEST_PROTOCOL)
+        print(i, "/", len(spk_folders), "/".join(str(folder).split("/")[-3:]), flush=True)
+
+
+def read_prematched(feat_path, device="cuda"):
+    """What the training datasets read back (hifigan/ddsp_meldataset.py:473-486,
+    hifigan/knn_data_cnpop.py:200-207): `pool.npy[nearest_nbrs[:, :4]].mean(1)` and the gathered
+    harmonic candidates with their amp_ratio.  Returns (mel [T,D], harmonics [T,4,H], amp_ratio [T,4])."""
+    import pickle
+    from pathlib import Path
+
+    import numpy as np
+    feat_path = Path(feat_path)
+    with open(feat_path, "rb") as handle:
+        feat_dict = pickle.load(handle)
+    dev = torch.device(device)
+    pool = torch.from_numpy(np.load(str(feat_path.parent / "pool.npy"))).to(dev)
+    mel = ops.gather_mix(pool, torch.from_numpy(feat_dict["nearest_nbrs"][:, :4].copy()).to(dev), None)
+    harm_pool = torch.from_numpy(np.load(str(feat_path.parent / "pool_harmonics.npy"))).to(dev)
+    hidx = torch.from_numpy(feat_dict["nearest_nbrs_f0_priority"][:, :4].copy()).to(dev)
+    return mel, harm_pool[hidx], torch.from_numpy(feat_dict["amp_ratio"]).to(dev)

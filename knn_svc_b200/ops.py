@@ -300,3 +300,95 @@ def harmonic_bank(f0: torch.Tensor, amp: torch.Tensor | None, sample_rate: int =
         _lib.check(lib.knnsvc_harmonic_bank(f0.data_ptr(), _ptr(amp), B, T, H, int(sample_rate), int(hop),
                                             out.data_ptr(), ws.data_ptr(), _stream()), "harmonic_bank")
     return out
+
+
+# ----------------------------------------------------------------------------- SURVEY §8(f) ops
+
+
+def layer_mix(feats: torch.Tensor, weights_a, weights_b=None):
+    """`(feats*weights[:, None]).sum(dim=0)` for one or two weight vectors in one pass over the
+    [L, T, D] layer stack (ddsp_prematch_dataset.py:349-350).  Weights are host float64."""
+    _dev(feats, "feats")
+    feats = _f32c(feats)
+    L, T, D = feats.shape
+    import ctypes
+    import numpy as np
+    wa = np.ascontiguousarray(np.asarray(weights_a, dtype=np.float64).reshape(-1))
+    if wa.shape[0] != L:
+        raise ValueError("one weight per layer expected")
+    wb = None
+    out_a = torch.empty((T, D), dtype=torch.float32, device=feats.device)
+    out_b = None
+    if weights_b is not None:
+        wb = np.ascontiguousarray(np.asarray(weights_b, dtype=np.float64).reshape(-1))
+        if wb.shape[0] != L:
+            raise ValueError("one weight per layer expected")
+        out_b = torch.empty_like(out_a)
+    lib = _lib.load()
+    with torch.cuda.device(feats.device):
+        _lib.check(lib.knnsvc_layer_mix(feats.data_ptr(), L, T, D, wa.ctypes.data_as(ctypes.c_void_p),
+                                        None if wb is None else wb.ctypes.data_as(ctypes.c_void_p),
+                                        out_a.data_ptr(), _ptr(out_b), _stream()), "layer_mix")
+    return out_a if weights_b is None else (out_a, out_b)
+
+
+def stft_magnitude(audio: torch.Tensor, frames: int | None = None, n_fft: int = 400, hop: int = 320) -> torch.Tensor:
+    """Spectrogram(n_fft, hop, center=True, power=1)(x).T[:, :-1][:frames] — reference :326, :361-363."""
+    _dev(audio, "audio")
+    x = _f32c(audio.reshape(-1))
+    n = x.shape[0]
+    total = 1 + n // hop
+    frames = total if frames is None else int(frames)
+    if frames > total:
+        raise AssertionError("spectrogram shorter than the feature sequence")       # reference :362
+    out = torch.empty((frames, n_fft // 2), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.knnsvc_stft_magnitude(x.data_ptr(), n, frames, n_fft, hop, out.data_ptr(), _stream()),
+                   "stft_magnitude")
+    return out
+
+
+def harmonic_amplitudes(spec: torch.Tensor, f0: torch.Tensor, n_harm: int = 49, sample_rate: int = 16000) -> torch.Tensor:
+    """0.0108 * spectrum magnitude at the first `n_harm` harmonics of f0 — reference :391-404."""
+    _dev(spec, "spec")
+    spec = _f32c(spec)
+    f0 = _f32c(f0.to(spec.device))
+    T, S = spec.shape
+    if f0.shape != (T,):
+        raise ValueError("one f0 value per spectrum row expected")
+    if sample_rate / (2 * S) != 40:
+        raise AssertionError([sample_rate / (2 * S)])                                # reference :392
+    out = torch.empty((T, n_harm), dtype=torch.float32, device=spec.device)
+    lib = _lib.load()
+    with torch.cuda.device(spec.device):
+        _lib.check(lib.knnsvc_harmonic_amplitudes(spec.data_ptr(), f0.data_ptr(), T, S, n_harm, int(sample_rate),
+                                                  out.data_ptr(), _stream()), "harmonic_amplitudes")
+    return out
+
+
+def row_l1(x: torch.Tensor) -> torch.Tensor:
+    """`x.norm(dim=1, p=1)` (reference :1672)."""
+    _dev(x, "rows")
+    x = _f32c(x)
+    out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.knnsvc_row_l1(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "row_l1")
+    return out
+
+
+def amp_ratio(l1_query: torch.Tensor, l1_pool: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """amp_ratio[t,k] = l1_query[t] / (l1_pool[idx[t,k]] + 1e-5) — reference :1672-1675."""
+    _dev(l1_pool, "l1_pool")
+    dev = l1_pool.device
+    q, p, idx = _f32c(l1_query.to(dev)), _f32c(l1_pool), _i64c(idx.to(dev))
+    T, k = idx.shape
+    if q.shape != (T,):
+        raise ValueError("one query norm per index row expected")
+    out = torch.empty((T, k), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.knnsvc_amp_ratio(q.data_ptr(), p.data_ptr(), idx.data_ptr(), T, k, p.shape[0], out.data_ptr(),
+                                        _stream()), "amp_ratio")
+    return out
