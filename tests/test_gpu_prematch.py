@@ -78,18 +78,19 @@ def test_masked_search_distance_one_semantics(ops):
 def test_masked_search_through_exact_fallback(ops):
     """hundreds of duplicated pool rows overflow the candidate log -> the exact brute-force
     kernel decides, and it must honour the mask too"""
-    p = synth.ar1_frames(900, seed=94)
-    p[100:700] = p[50]                                        # 600 exact duplicates of row 50
+    base = synth.ar1_frames(3000, seed=94)
+    p = np.concatenate([base, base, base])                    # 9000 rows -> pool segments of 2-3 tiles
+    p[100:6100] = p[5]                                        # 6000 exact duplicates of row 5
     rs = np.random.RandomState(2)
-    q = (p[50][None, :] + 0.05 * rs.standard_normal((24, 1024))).astype(np.float32)
-    lo = np.full(24, 90, np.int64); hi = np.full(24, 400, np.int64)   # 300 duplicates stay unmasked (> log cap 256)
+    q = (p[5][None, :] + 0.05 * rs.standard_normal((24, 1024))).astype(np.float32)
+    lo = np.full(24, 90, np.int64); hi = np.full(24, 3000, np.int64)   # 3100 duplicates stay unmasked (log cap 256)
     d, i, st = ops.knn_search(ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p)), 4, mask_lo=dev(lo),
                               mask_hi=dev(hi), return_stats=True)
     o_idx, o_val = orc.knn(q, p, 5, lo, hi)
     assert int(st[0]) == 24, st.tolist()                      # every row went down the exact path
     d, i = d.cpu().numpy(), i.cpu().numpy()
     assert np.abs(d - o_val[:, :4]).max() < 2e-6
-    assert np.array_equal(i, np.tile(np.array([50, 400, 401, 402]), (24, 1)))   # (dist, index) order, mask honoured
+    assert np.array_equal(i, np.tile(np.array([5, 3000, 3001, 3002]), (24, 1)))   # (dist, index) order, mask honoured
     assert np.array_equal(i, o_idx[:, :4])
 
 
