@@ -41,10 +41,14 @@ int knnsvc_version(void);
  *   norms    [rows] fp32 = |x|
  *   bad_rows int counter, incremented per zero-norm / non-finite row (the
  *            reference NaNs and exits there, lib_ongaku_test.py:166-169)
+ *   max_err  optional float, ZEROED BY THE CALLER: receives max over rows of
+ *            |operand/2^10 - x/|x||_2, the measured rounding error the search's
+ *            rigorous error window is built from (NULL: not measured; the search
+ *            then assumes the fp16 worst case)
  */
 int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld,
                         void* half_out, int dim_pad, float* norms,
-                        int* bad_rows, void* stream);
+                        int* bad_rows, float* max_err, void* stream);
 
 /* ---- K1 full matrix (API parity only; never on the fused path) -----------
  * fast_cosine_dist(source_feats, matching_pool) — lib_ongaku_test.py:148-175,
@@ -62,6 +66,8 @@ int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t 
  * The [n_query, n_pool] matrix is never written.
  *   q/p       fp32 rows [n, dim] (ld = dim); qh/ph/qn/pn from knnsvc_prepare_rows
  *   index_offset  added to every returned index (pool shard offset, C1)
+ *   q_err/p_err   the max_err scalars knnsvc_prepare_rows produced for the two row
+ *             sets (device pointers; NULL = fp16 worst case, a wider window, same results)
  *   out_dist  [n_query, k] fp32 ascending;  out_idx [n_query, k] int64
  *   stats     optional int[8]: {flagged rows, logged candidates (sat.), survivors,
  *             segments, units, grid, log cap, reserved}
@@ -70,6 +76,7 @@ size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, 
 int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query,
                       const float* p, const void* ph, const float* pn, int64_t n_pool,
                       int dim, int dim_pad, int k, int64_t index_offset,
+                      const float* q_err, const float* p_err,
                       float* out_dist, int64_t* out_idx,
                       void* workspace, size_t workspace_bytes, int* stats, void* stream);
 
@@ -81,6 +88,7 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
 int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query,
                              const float* p, const void* ph, const float* pn, int64_t n_pool,
                              int dim, int dim_pad, int k, int64_t index_offset,
+                             const float* q_err, const float* p_err,
                              const int64_t* mask_lo, const int64_t* mask_hi,
                              float* out_dist, int64_t* out_idx,
                              void* workspace, size_t workspace_bytes, int* stats, void* stream);

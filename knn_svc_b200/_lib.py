@@ -19,12 +19,13 @@ i64, i32, f32, f64, vp, sz = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_void
 SIGNATURES = {
     "knnsvc_last_error": (C.c_char_p, []),
     "knnsvc_version": (i32, []),
-    "knnsvc_prepare_rows": (i32, [vp, i64, i32, i64, vp, i32, vp, vp, vp]),
+    "knnsvc_prepare_rows": (i32, [vp, i64, i32, i64, vp, i32, vp, vp, vp, vp]),
     "knnsvc_cosine_dist": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "knnsvc_knn_workspace_bytes": (sz, [i64, i64, i32, i32]),
-    "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, sz, vp, vp]),
-    "knnsvc_knn_search_masked": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz,
-                                       vp, vp]),
+    "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp,
+                                vp]),
+    "knnsvc_knn_search_masked": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp,
+                                       vp, sz, vp, vp]),
     "knnsvc_launch_count": (C.c_longlong, []),
     "knnsvc_set_option": (i32, [C.c_char_p, i32]),
     "knnsvc_filter_timing": (i32, [i32]),

@@ -110,10 +110,10 @@ const char* knnsvc_last_error(void) { return g_err; }
 int knnsvc_version(void) { return 100; }
 
 int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad, float* norms,
-                        int* bad_rows, void* stream) {
+                        int* bad_rows, float* max_err, void* stream) {
   KNN_CHECK_ARG(rows >= 0 && dim >= 1 && ld >= dim && dim_pad >= dim, -1, "prepare_rows: bad shape");
   KNN_CHECK_ARG(x && half_out && norms && bad_rows, -1, "prepare_rows: null pointer");
-  return launch_prepare_rows(x, rows, dim, ld, half_out, dim_pad, norms, bad_rows, (cudaStream_t)stream);
+  return launch_prepare_rows(x, rows, dim, ld, half_out, dim_pad, norms, bad_rows, max_err, (cudaStream_t)stream);
 }
 
 int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t n_pool, int dim, float* out,
@@ -131,17 +131,17 @@ size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, 
 
 int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
                       const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
-                      int64_t index_offset, float* out_dist, int64_t* out_idx, void* workspace,
-                      size_t workspace_bytes, int* stats, void* stream_) {
-  return knnsvc_knn_search_masked(q, qh, qn, n_query, p, ph, pn, n_pool, dim, dim_pad, k, index_offset, nullptr,
-                                  nullptr, out_dist, out_idx, workspace, workspace_bytes, stats, stream_);
+                      int64_t index_offset, const float* q_err, const float* p_err, float* out_dist,
+                      int64_t* out_idx, void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
+  return knnsvc_knn_search_masked(q, qh, qn, n_query, p, ph, pn, n_pool, dim, dim_pad, k, index_offset, q_err, p_err,
+                                  nullptr, nullptr, out_dist, out_idx, workspace, workspace_bytes, stats, stream_);
 }
 
 int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
                              const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
-                             int64_t index_offset, const int64_t* mask_lo, const int64_t* mask_hi,
-                             float* out_dist, int64_t* out_idx, void* workspace, size_t workspace_bytes,
-                             int* stats, void* stream_) {
+                             int64_t index_offset, const float* q_err, const float* p_err,
+                             const int64_t* mask_lo, const int64_t* mask_hi, float* out_dist, int64_t* out_idx,
+                             void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -1,
                 "knn_search: mask_lo and mask_hi must be given together");
@@ -158,7 +158,7 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   const bool timed = g_timing && g_ev_n < kTimingSlots;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                             w.seg_kth, w.seg_flag, mask_lo, mask_hi, stream);
+                             w.seg_kth, w.seg_flag, mask_lo, mask_hi, q_err, p_err, stream);
   if (rc) return rc;
   if (timed) {
     KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));
@@ -166,7 +166,7 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   }
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
                           index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, mask_lo, mask_hi,
-                          stream);
+                          q_err, p_err, stream);
   if (rc) return rc;
   // rows the error window could not decide: exact brute force, count known only on the device
   rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, w.flag_list, w.counters, 0, 0, kFlagCap,

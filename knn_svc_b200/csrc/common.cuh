@@ -42,11 +42,25 @@ constexpr float kHalfScale = 1024.0f;
 constexpr float kDotScale = 1048576.0f;        // 2^20
 constexpr float kDotUnscale = 1.0f / 1048576.0f;
 
-// Rigorous half-width of the filter's error window in cosine units:
-// |s_fp16gemm - s_exact| <= kFilterEps.  Two fp16 roundings of unit vectors
-// contribute <= 2*2^-11 + 2^-22 (Cauchy-Schwarz), the fp32 normalisation and
-// <=1024-term fp32 accumulation in the tensor core <= 1.3e-4; see DESIGN.md.
-constexpr float kFilterEps = 1.2e-3f;
+// Rigorous half-width eps of the filter's error window in cosine units:
+// |s_fp16gemm - s_exact| <= eps = rho_q + rho_p + rho_q*rho_p + kAccEps, where
+// rho = |u - x/|x||_2 is the distance between a row's fp16 operand u (unscaled) and its exact
+// unit vector (Cauchy-Schwarz on  u.v - q.p = (u-q).v + q.(v-p)), and kAccEps bounds the
+// <= 1088 fp32 additions of the tensor-core accumulation (|sum| <= ~1, truncation allowed).
+// prepare_rows MEASURES rho per row and publishes the maximum over the row set, so eps is as
+// tight as the data allows (~7e-4 on Gaussian-like rows); without a measured value the worst
+// case of an fp16 rounding, 2^-11 (+ fp32 normalisation), is assumed: 2*5.3e-4 + 1.4e-4 = 1.2e-3.
+constexpr float kAccEps = 1.4e-4f;
+constexpr float kWorstRowEps = 5.3e-4f;
+__host__ __device__ inline float filter_eps_from(float rho_q, float rho_p) {
+  return rho_q + rho_p + rho_q * rho_p + kAccEps;
+}
+// rho as published by prepare_rows (device scalars; nullptr = worst case)
+__device__ __forceinline__ float filter_eps(const float* __restrict__ q_err, const float* __restrict__ p_err) {
+  const float rq = q_err ? __ldg(q_err) : kWorstRowEps;
+  const float rp = p_err ? __ldg(p_err) : kWorstRowEps;
+  return filter_eps_from(rq, rp);
+}
 
 constexpr int kMaxK = 32;
 

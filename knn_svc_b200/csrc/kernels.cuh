@@ -13,7 +13,7 @@ int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA 
 
 // ---- rows.cu
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
-                        float* norms, int* bad_rows, cudaStream_t stream);
+                        float* norms, int* bad_rows, float* max_err, cudaStream_t stream);
 int launch_cosine_dist(const float* q, int64_t nq, const float* p, int64_t np_, int dim, float* out,
                        cudaStream_t stream);
 int exact_chunks(int64_t n_pool);
@@ -32,7 +32,7 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
                       float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
-                      cudaStream_t stream);
+                      const float* q_err, const float* p_err, cudaStream_t stream);
 size_t filter_flag_count(const FilterPlan& pl);
 
 // ---- knn_select.cu
@@ -41,7 +41,8 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream);
+                       const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err, const float* p_err,
+                       cudaStream_t stream);
 int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
                       int64_t* out_idx, cudaStream_t stream);
 

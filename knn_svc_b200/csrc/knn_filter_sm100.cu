@@ -22,7 +22,7 @@
 //
 // Filter rule (rigorous, DESIGN.md "exact top-k from an fp16 GEMM"): operands are
 // unit-normalised rows cast to fp16, so the accumulator is the cosine similarity
-// s~ with |s~ - s| <= eps.  The thread tracks tau_k = k-th largest s~ seen so far
+// s~ with |s~ - s| <= eps (eps from the rows' MEASURED rounding errors, common.cuh).  The thread tracks tau_k = k-th largest s~ seen so far
 // and LOGS every column with s~ > tau_k - 2*eps.  Every true top-k member is in
 // the log; knn_rescore re-scores the log exactly from the fp32 rows.
 #include <cuda.h>
@@ -297,7 +297,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                   int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
                   float* __restrict__ seg_top, float* __restrict__ seg_kth, int* __restrict__ seg_flag,
                   uint32_t idesc, uint32_t spin_ns, const int64_t* __restrict__ mask_lo,
-                  const int64_t* __restrict__ mask_hi) {
+                  const int64_t* __restrict__ mask_hi, const float* __restrict__ q_err,
+                  const float* __restrict__ p_err) {
   using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
@@ -417,7 +418,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside this CTA's tile
     int* keys_row = reinterpret_cast<int*>(smem + L::topv) + row_in_tile;   // [kSlots][BM] packed keys
-    const float window_scaled = 2.0f * kFilterEps * kDotScale;
+    const float window_scaled = 2.0f * filter_eps(q_err, p_err) * kDotScale;
     uint32_t tile_n = 0;
     for (int u = worker; u < n_units; u += n_workers) {
       const int seg = u / n_qtiles, qt = u % n_qtiles;
@@ -618,7 +619,7 @@ template <int CTAS, bool MASKED>
 static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
                           int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
                           float* seg_top, float* seg_kth, int* seg_flag, const int64_t* mask_lo,
-                          const int64_t* mask_hi, cudaStream_t stream) {
+                          const int64_t* mask_hi, const float* q_err, const float* p_err, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -642,14 +643,14 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS, MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
                               pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
-                              seg_flag, idesc, (uint32_t)opt_spin_ns(), mask_lo, mask_hi));
+                              seg_flag, idesc, (uint32_t)opt_spin_ns(), mask_lo, mask_hi, q_err, p_err));
   return 0;
 }
 
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
                       float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
-                      cudaStream_t stream) {
+                      const float* q_err, const float* p_err, cudaStream_t stream) {
   KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -3, "mask_lo and mask_hi must be given together");
   KNN_CHECK_ARG(dim_pad % BK == 0 && dim_pad > 0, -3, "dim_pad %d must be a positive multiple of %d", dim_pad, BK);
   KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -3, "k=%d outside [1,%d]", k, kMaxK);
@@ -661,7 +662,7 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   if (rc) return rc;
 #define KNN_FILTER_GO(C, M)                                                                                   \
   return launch_variant<C, M>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top, \
-                              seg_kth, seg_flag, mask_lo, mask_hi, stream)
+                              seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, stream)
   if (pl.ctas == 2) {
     if (mask_lo) KNN_FILTER_GO(2, true);
     KNN_FILTER_GO(2, false);

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ log_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
     const float* __restrict__ seg_top, int64_t index_offset, float* __restrict__ out_dist,
     int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list, int* __restrict__ flag_count,
-    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
+    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi,
+    const float* __restrict__ q_err, const float* __restrict__ p_err) {
   extern __shared__ __align__(16) float s_q[];  // [dim]
   __shared__ float s_top[RS_MAXTOP];
   __shared__ double s_d[RS_WARPS][kMaxK];   // per-warp exact top-k, ascending by (dist, idx)
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
         const float o = s_top[j];
         rank += (o > v) || (o == v && j < e);
       }
-      if (rank == k - 1) s_thr = v - 2.0f * kFilterEps;
+      if (rank == k - 1) s_thr = v - 2.0f * filter_eps(q_err, p_err);
     }
     for (int s = tid; s < n_seg; s += RS_THREADS) {
       const int c = log_cnt[row * n_seg + s];
@@ -169,7 +170,8 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream) {
+                       const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err, const float* p_err,
+                       cudaStream_t stream) {
   if (n_query == 0) return 0;
   KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
@@ -178,7 +180,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, log_val, log_idx, log_cnt, seg_top,
                                                                    index_offset, out_dist, out_idx, flag_list,
-                                                                   flag_count, stats, mask_lo, mask_hi);
+                                                                   flag_count, stats, mask_lo, mask_hi, q_err, p_err);
   KNN_LAUNCH_CHECK();
   return 0;
 }

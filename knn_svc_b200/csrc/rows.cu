@@ -19,7 +19,8 @@ namespace knnsvc {
 // One warp per row; HBM-bound: reads dim*4 B, writes dim_pad*2 + 4 B per row.
 __global__ void __launch_bounds__(256) prepare_rows_kernel(
     const float* __restrict__ x, int64_t rows, int dim, int64_t ld,
-    __half* __restrict__ hout, int dim_pad, float* __restrict__ norms, int* __restrict__ bad_rows, int bf16) {
+    __half* __restrict__ hout, int dim_pad, float* __restrict__ norms, int* __restrict__ bad_rows, int bf16,
+    float* __restrict__ max_err) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -48,6 +49,11 @@ __global__ void __launch_bounds__(256) prepare_rows_kernel(
       if (bad) atomicAdd(bad_rows, 1);
     }
     const float sc = bad ? 0.0f : (float)((double)kHalfScale / nrm);
+    // rho^2 = sum (u_i - x_i/|x|)^2 with u_i = operand_i / 2^10: the row's actual rounding error
+    // (fp32 evaluation; the subtraction of nearly equal numbers is exact and the product's
+    // rounding is 2^-24 relative, both far below the 1e-3 relative margin applied at the end)
+    const float inv_nrm = bad ? 0.0f : (float)(1.0 / nrm);
+    float err2 = 0.f;
     __half* hr = hout + r * (int64_t)dim_pad;
     if (vec) {
       const float4* x4 = reinterpret_cast<const float4*>(xr);
@@ -55,36 +61,60 @@ __global__ void __launch_bounds__(256) prepare_rows_kernel(
       for (int c = lane; c < dim_pad / 4; c += 32) {
         float4 v = (c < dim / 4) ? __ldg(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint2 o;
+        float2 ua, ub;
         if (bf16) {
           __nv_bfloat162 a = __floats2bfloat162_rn(v.x * sc, v.y * sc);
           __nv_bfloat162 b = __floats2bfloat162_rn(v.z * sc, v.w * sc);
           o.x = *reinterpret_cast<uint32_t*>(&a);
           o.y = *reinterpret_cast<uint32_t*>(&b);
+          ua = __bfloat1622float2(a);
+          ub = __bfloat1622float2(b);
         } else {
           __half2 a = __floats2half2_rn(v.x * sc, v.y * sc);
           __half2 b = __floats2half2_rn(v.z * sc, v.w * sc);
           o.x = *reinterpret_cast<uint32_t*>(&a);
           o.y = *reinterpret_cast<uint32_t*>(&b);
+          ua = __half22float2(a);
+          ub = __half22float2(b);
         }
         h4[c] = o;
+        const float e0 = fmaf(ua.x, 1.0f / kHalfScale, -v.x * inv_nrm), e1 = fmaf(ua.y, 1.0f / kHalfScale, -v.y * inv_nrm);
+        const float e2 = fmaf(ub.x, 1.0f / kHalfScale, -v.z * inv_nrm), e3 = fmaf(ub.y, 1.0f / kHalfScale, -v.w * inv_nrm);
+        err2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
       }
     } else {
       for (int c = lane; c < dim_pad; c += 32) {
-        float v = (c < dim) ? __ldg(xr + c) * sc : 0.0f;
-        if (bf16) reinterpret_cast<__nv_bfloat16*>(hr)[c] = __float2bfloat16_rn(v);
-        else hr[c] = __float2half_rn(v);
+        const float x0 = (c < dim) ? __ldg(xr + c) : 0.0f;
+        const float v = x0 * sc;
+        float u;
+        if (bf16) {
+          const __nv_bfloat16 b = __float2bfloat16_rn(v);
+          reinterpret_cast<__nv_bfloat16*>(hr)[c] = b;
+          u = __bfloat162float(b);
+        } else {
+          const __half h = __float2half_rn(v);
+          hr[c] = h;
+          u = __half2float(h);
+        }
+        const float e = fmaf(u, 1.0f / kHalfScale, -x0 * inv_nrm);
+        err2 += e * e;
       }
+    }
+    if (max_err) {
+      err2 = warp_sum(err2);
+      // positive floats order like their bit patterns; 1e-3 relative + 1e-6 absolute cover the fp32 evaluation
+      if (lane == 0 && !bad) atomicMax(reinterpret_cast<int*>(max_err), __float_as_int(sqrtf(err2) * 1.001f + 1e-6f));
     }
   }
 }
 
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
-                        float* norms, int* bad_rows, cudaStream_t stream) {
+                        float* norms, int* bad_rows, float* max_err, cudaStream_t stream) {
   if (rows == 0) return 0;
   int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   prepare_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, dim, ld, (__half*)half_out, dim_pad,
-                                                            norms, bad_rows, opt_bf16());
+                                                            norms, bad_rows, opt_bf16(), max_err);
   KNN_LAUNCH_CHECK();
   return 0;
 }

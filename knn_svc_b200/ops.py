@@ -48,6 +48,7 @@ class PreparedRows:
     rows: torch.Tensor      # [n, dim] fp32
     half: torch.Tensor      # [n, dim_pad] fp16 = fp16(rows * 1024/|row|)
     norms: torch.Tensor     # [n] fp32
+    err: torch.Tensor = None  # [1] fp32: max over rows of |half/1024 - row/|row||_2 (measured rounding error)
 
     @property
     def n(self) -> int:
@@ -74,15 +75,16 @@ def prepare_rows(x: torch.Tensor, check: bool = True) -> PreparedRows:
     dim_pad = (dim + _HALF_ALIGN - 1) // _HALF_ALIGN * _HALF_ALIGN
     half = torch.empty((n, dim_pad), dtype=torch.float16, device=x.device)
     norms = torch.empty((n,), dtype=torch.float32, device=x.device)
-    bad = torch.zeros((1,), dtype=torch.int32, device=x.device)
+    scal = torch.zeros((2,), dtype=torch.int32, device=x.device)     # [0] bad-row counter, [1] max error (float bits)
+    bad, err = scal[0:1], scal[1:2].view(torch.float32)
     lib = _lib.load()
     with torch.cuda.device(x.device):
         _lib.check(lib.knnsvc_prepare_rows(x.data_ptr(), n, dim, dim, half.data_ptr(), dim_pad, norms.data_ptr(),
-                                           bad.data_ptr(), _stream()), "prepare_rows")
+                                           bad.data_ptr(), err.data_ptr(), _stream()), "prepare_rows")
     if check and n > 0 and int(bad.item()) != 0:
         raise ValueError(f"{int(bad.item())} zero-norm or non-finite feature rows: cosine distance undefined "
                          "(the reference exits with 'containing nan')")
-    return PreparedRows(x, half, norms)
+    return PreparedRows(x, half, norms, err)
 
 
 def cosine_dist(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
@@ -147,7 +149,8 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
             _lib.check(lib.knnsvc_knn_search_masked(query.rows.data_ptr(), query.half.data_ptr(),
                                                     query.norms.data_ptr(), T, pool.rows.data_ptr(),
                                                     pool.half.data_ptr(), pool.norms.data_ptr(), pool.n, query.dim,
-                                                    query.dim_pad, k, index_offset, _ptr(mask_lo), _ptr(mask_hi),
+                                                    query.dim_pad, k, index_offset, _ptr(query.err), _ptr(pool.err),
+                                                    _ptr(mask_lo), _ptr(mask_hi),
                                                     dist.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
                                                     stats.data_ptr(), _stream()), "knn_search")
     if return_stats:

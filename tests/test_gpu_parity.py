@@ -39,6 +39,29 @@ def test_prepare_rows(ops):
         ops.prepare_rows(dev(bad))
 
 
+@pytest.mark.parametrize("kind", ["ar1", "randn", "odd_dim"])
+def test_prepare_rows_measures_its_rounding_error(ops, kind):
+    """the published max |operand/1024 - x/|x||_2 is what the search's rigorous error window is
+    built from: it must be an UPPER bound of the true value (fp64 here), and a tight one"""
+    x = {"ar1": lambda: synth.ar1_frames(500, seed=7), "randn": lambda: synth.randn_frames(500, seed=8),
+         "odd_dim": lambda: synth.randn_frames(77, d=49, seed=9)}[kind]()
+    pr = ops.prepare_rows(dev(x))
+    u = pr.half.float().cpu().numpy().astype(np.float64)[:, :x.shape[1]] / 1024.0
+    unit = x.astype(np.float64) / orc.row_norms(x)[:, None]
+    rho = np.sqrt(((u - unit) ** 2).sum(1)).max()
+    got = float(pr.err.item())
+    assert rho <= got <= rho * 1.01 + 2e-6, (rho, got)
+    assert got < 5.3e-4                      # below the fp16 worst case the library falls back to
+    # the filter's error window really covers the tensor-core similarities of these rows
+    y = synth.ar1_frames(300, seed=10) if x.shape[1] == 1024 else synth.randn_frames(300, d=49, seed=10)
+    pq = ops.prepare_rows(dev(y))
+    approx = (pq.half.float() @ pr.half.float().T).double().cpu().numpy() / 2.0 ** 20     # what the GEMM sees (fp32 acc)
+    exact = 1.0 - orc.cosine_dist(y, x)
+    eps = float(pq.err.item()) + got + float(pq.err.item()) * got + 1.4e-4
+    assert np.abs(approx - exact).max() <= eps, (np.abs(approx - exact).max(), eps)
+    print(f"{kind}: measured eps {eps:.2e} (worst-case 1.2e-3), actual max |s~ - s| {np.abs(approx - exact).max():.2e}")
+
+
 def test_prepare_rows_pads_odd_dim(ops):
     x = synth.randn_frames(37, d=49, seed=6)
     pr = ops.prepare_rows(dev(x))

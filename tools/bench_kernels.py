@@ -97,3 +97,33 @@ for B in (1, 64):
            {"Gsamples_per_s": round(samples / (ms * 1e-3) / 1e9, 3), "sinf_per_s": round(samples * 49 / (ms * 1e-3) / 1e12, 3)})
     ms = timed(lambda: ops.harmonic_bank(f0, None))
     report(f"f0_sinusoid B={B}", ms, B * 3001 * (4 + 320 * 4), B * 3001)
+
+# ---- pool-builder ops (a 10-minute recording: 30k frames) and the offline prematch
+Tl, L = 30_000, 25
+layers = torch.randn((L, Tl, D), device=dev, generator=g)
+wa = np.random.RandomState(0).rand(L); wb = np.zeros(L); wb[6] = 1.0
+ms = timed(lambda: ops.layer_mix(layers, wa, wb), reps=5)
+report("layer_mix L=25 (two mixes, one pass)", ms, Tl * (L * D * 4 + 2 * D * 4), Tl)
+del layers
+audio = torch.randn(320 * Tl + 80, device=dev, generator=g) * 0.1
+ms = timed(lambda: ops.stft_magnitude(audio, Tl))
+report("stft_magnitude n_fft=400 hop=320", ms, Tl * (320 * 4 + 200 * 4), Tl, {"GFMA_per_s": round(Tl * 400 * 200 * 2 / (ms * 1e-3) / 1e9, 1)})
+spec = ops.stft_magnitude(audio, Tl)
+f0u = torch.from_numpy(synth.f0_track(Tl, seed=7)).to(dev)
+ms = timed(lambda: ops.harmonic_amplitudes(spec, f0u))
+report("harmonic_amplitudes H=49", ms, Tl * (200 * 4 + 4 + 49 * 4), Tl)
+spec_pool = torch.rand((2_000_000, 200), device=dev, generator=g)
+ms = timed(lambda: ops.row_l1(spec_pool))
+report("row_l1 S=200", ms, 2_000_000 * (200 * 4 + 4), 2_000_000)
+del spec_pool
+# masked self-search: one speaker's pool (256k frames = 85 min) against itself, k=32, utterances of 512 frames
+ns = 262_144
+xs = ops.prepare_rows(torch.randn((ns, D), device=dev, generator=g), check=False)
+starts = torch.arange(ns // 512, device=dev) * 512
+lens = torch.full((ns // 512,), 512, device=dev)
+mlo, mhi = torch.repeat_interleave(starts, lens), torch.repeat_interleave(starts + 512, lens)
+ms_m = timed(lambda: ops.knn_search(xs, xs, 32, mask_lo=mlo, mask_hi=mhi), reps=3, warm=1, flush_l2=False)
+ms_u = timed(lambda: ops.knn_search(xs, xs, 32), reps=3, warm=1, flush_l2=False)
+print(json.dumps({"kernel": "prematch self-search 262144^2 k=32 (filter+rescore)", "ms_masked": round(ms_m, 2), "ms_unmasked": round(ms_u, 2),
+                  "frames_per_s_masked": round(ns / (ms_m * 1e-3)), "TFLOPs_masked": round(2.0 * ns * ns * D / (ms_m * 1e-3) / 1e12, 1),
+                  "TFLOPs_unmasked": round(2.0 * ns * ns * D / (ms_u * 1e-3) / 1e12, 1)}), flush=True)

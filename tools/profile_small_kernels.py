@@ -29,3 +29,23 @@ amp = torch.from_numpy(synth.harmonics_pool(3001, seed=6)).to(dev)[None].repeat(
 for _ in range(2):
     ops.harmonic_bank(f0, amp)
 torch.cuda.synchronize()
+# ---- SURVEY §8(f) kernels: pool-builder ops, amp_ratio, masked self-search (offline prematch shape)
+L, Tl = 25, 3001
+layers = torch.randn((L, Tl, D), device=dev, generator=g)
+wa = np.random.RandomState(0).rand(L); wb = np.zeros(L); wb[6] = 1.0
+audio = torch.randn(320 * Tl + 80, device=dev, generator=g) * 0.1
+f0u = torch.from_numpy(synth.f0_track(Tl, seed=7)).to(dev)
+spec_pool = torch.rand((n // 4, 200), device=dev, generator=g)
+idx4 = torch.randint(0, n // 4, (T, 4), device=dev, generator=g)
+for _ in range(2):
+    ops.layer_mix(layers, wa, wb)
+    spec = ops.stft_magnitude(audio, Tl)
+    ops.harmonic_amplitudes(spec, f0u)
+    l1 = ops.row_l1(spec_pool)
+    ops.amp_ratio(l1[:T], l1, idx4)
+lens = torch.full((64,), 512, device=dev)
+starts = torch.arange(64, device=dev) * 512
+pself = ops.prepare_rows(x[:32768])
+for _ in range(2):
+    ops.knn_search(pself, pself, 32, mask_lo=torch.repeat_interleave(starts, lens), mask_hi=torch.repeat_interleave(starts + 512, lens))
+torch.cuda.synchronize()
