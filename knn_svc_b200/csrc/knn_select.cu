@@ -9,8 +9,8 @@
 //      dist = 1 - q.p/(|q||p|)   (lib_ongaku_test.py:162-165).
 //   4. survivors are ranked by (dist, index) and the first k written, ascending —
 //      the order dists.topk(k, largest=False) returns (ddsp_prematch_dataset.py:1203).
-// Survivors are streamed (no cap): each warp re-scores its share and keeps a
-// sorted exact top-k; the warps' lists are merged at the end.  Rows whose log
+// Survivors are compacted into a shared-memory list (any number: the list is reduced to its
+// best k whenever it fills), scored two per warp pass, and ranked by counting.  Rows whose log
 // overflowed in some segment (more than `cap` candidates inside the window:
 // massive ties) are appended to the flag list for the exact brute-force kernel.
 #include <limits.h>
@@ -23,9 +23,55 @@ namespace knnsvc {
 constexpr int RS_THREADS = 128;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAXTOP = 16 * kMaxK;  // n_seg <= 16
+constexpr int RS_LIST = 1024;          // survivors held in shared memory between two reductions to the best k
 
 __device__ __forceinline__ bool rs_less(double da, int ia, double db, int ib) {
   return da < db || (da == db && ia < ib);
+}
+
+// dot products of ONE or TWO pool rows with the query row held in shared memory as fp64
+// (products of two fp32 values are exact in fp64; the accumulation order is fixed, so every
+// kernel that scores a pair gets the same bits).  Two rows per pass share the query loads and
+// give the scheduler two independent DFMA chains.
+template <bool VEC>
+__device__ __forceinline__ void rs_dot2(const float* __restrict__ pa, const float* __restrict__ pb,
+                                        const double* __restrict__ s_q, int dim, int lane, double& ra, double& rb) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  if (VEC) {
+    const float4* a4 = reinterpret_cast<const float4*>(pa);
+    const float4* b4 = reinterpret_cast<const float4*>(pb);
+    // VEC layout of the query: element pairs (4c, 4c+1) in the first half, (4c+2, 4c+3) in the
+    // second, so consecutive lanes read consecutive 16-byte words (no bank conflicts)
+    const double2* q2 = reinterpret_cast<const double2*>(s_q);
+    const int nv = dim / 4;
+#pragma unroll 4
+    for (int c = lane; c < nv; c += 32) {
+      const float4 va = __ldg(a4 + c);
+      const float4 vb = __ldg(b4 + c);
+      const double2 qa = q2[c], qb = q2[nv + c];
+      a0 = fma((double)va.x, qa.x, a0);
+      a1 = fma((double)va.y, qa.y, a1);
+      a0 = fma((double)va.z, qb.x, a0);
+      a1 = fma((double)va.w, qb.y, a1);
+      b0 = fma((double)vb.x, qa.x, b0);
+      b1 = fma((double)vb.y, qa.y, b1);
+      b0 = fma((double)vb.z, qb.x, b0);
+      b1 = fma((double)vb.w, qb.y, b1);
+    }
+  } else {
+    for (int c = lane; c < dim; c += 32) {
+      const double qv = s_q[c];
+      a0 = fma((double)__ldg(pa + c), qv, a0);
+      b0 = fma((double)__ldg(pb + c), qv, b0);
+    }
+  }
+  ra = a0 + a1;
+  rb = b0 + b1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ra += __shfl_xor_sync(0xffffffffu, ra, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+  }
 }
 
 __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
@@ -36,29 +82,36 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list, int* __restrict__ flag_count,
     int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi,
     const float* __restrict__ q_err, const float* __restrict__ p_err) {
-  extern __shared__ __align__(16) float s_q[];  // [dim]
+  extern __shared__ __align__(16) double s_q[];  // [dim] the query row, converted once
   __shared__ float s_top[RS_MAXTOP];
-  __shared__ double s_d[RS_WARPS][kMaxK];   // per-warp exact top-k, ascending by (dist, idx)
-  __shared__ int s_i[RS_WARPS][kMaxK];
-  __shared__ int s_nsurv[RS_WARPS];
-  __shared__ int s_overflow, s_logged;
+  __shared__ double s_dist[RS_LIST];             // exact distances of the survivors in s_cand
+  __shared__ int s_cand[RS_LIST];
+  __shared__ double s_best_d[kMaxK];             // scratch for the reduction to the best k
+  __shared__ int s_best_i[kMaxK];
+  __shared__ int s_n, s_overflow, s_logged, s_nsurv;
   __shared__ float s_thr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 
   for (int64_t row = blockIdx.x; row < n_query; row += gridDim.x) {
     __syncthreads();
     if (tid == 0) {
       s_overflow = 0;
       s_logged = 0;
+      s_nsurv = 0;
+      s_n = 0;
       s_thr = -INFINITY;
     }
-    if (tid < RS_WARPS) s_nsurv[tid] = 0;
     const int n_top = n_seg * k;
     for (int e = tid; e < n_top; e += RS_THREADS) s_top[e] = seg_top[row * n_top + e];
-    for (int c = tid; c < dim; c += RS_THREADS) s_q[c] = __ldg(q + row * dim + c);
-    for (int e = tid; e < RS_WARPS * kMaxK; e += RS_THREADS) {
-      s_d[e / kMaxK][e % kMaxK] = INFINITY;
-      s_i[e / kMaxK][e % kMaxK] = INT_MAX;
+    if (vec) {
+      const int nv = dim / 4;
+      for (int c = tid; c < dim; c += RS_THREADS) {
+        const int g4 = c >> 2, r = c & 3;
+        s_q[(r < 2 ? 0 : 2 * nv) + 2 * g4 + (r & 1)] = (double)__ldg(q + row * dim + c);
+      }
+    } else {
+      for (int c = tid; c < dim; c += RS_THREADS) s_q[c] = (double)__ldg(q + row * dim + c);
     }
     __syncthreads();
     // k-th largest of the union of the segment lists (rank counting, ties by position)
@@ -90,78 +143,80 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const double qnorm = (double)qn[row];
     // masked column range: distance defined as 1 (ddsp_prematch_dataset.py:1623-1624)
     const int64_t m_lo = mask_lo ? mask_lo[row] : 0, m_hi = mask_lo ? mask_hi[row] : 0;
-    int my_surv = 0;
-    double kth_d = INFINITY;   // warp-uniform copy of this warp's current k-th best
-    int kth_i = INT_MAX;
-    for (int s = 0; s < n_seg; ++s) {
-      const int64_t slot = row * n_seg + s;
-      const int c = log_cnt[slot];
-      for (int base = warp * 32; base < c; base += RS_THREADS) {
-        const int e = base + lane;
-        int cand = -1;
-        if (e < c && log_val[slot * cap + e] >= thr) cand = log_idx[slot * cap + e];
-        unsigned mask = __ballot_sync(0xffffffffu, cand >= 0);
-        while (mask) {
-          const int b = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int pr = __shfl_sync(0xffffffffu, cand, b);
-          const float* prow = p + (int64_t)pr * dim;
-          double acc = 0.0;
-          const bool masked = pr >= m_lo && pr < m_hi;   // warp-uniform
-          if (masked) {
-          } else if ((dim & 3) == 0) {
-            const float4* p4 = reinterpret_cast<const float4*>(prow);
-            const float4* q4 = reinterpret_cast<const float4*>(s_q);
-            for (int cc = lane; cc < dim / 4; cc += 32) {
-              const float4 a = __ldg(p4 + cc);
-              const float4 bq = q4[cc];
-              acc += (double)a.x * bq.x + (double)a.y * bq.y + (double)a.z * bq.z + (double)a.w * bq.w;
-            }
+    int n_scored = 0;   // entries [0, n_scored) of the list already carry their exact distance
+
+    // score list entries [n_scored, s_n): a warp takes two survivors per pass
+    auto score = [&]() {
+      const int n = s_n;
+      for (int e = n_scored + 2 * warp; e < n; e += 2 * RS_WARPS) {
+        const int ia = s_cand[e];
+        const bool has_b = e + 1 < n;
+        const int ib = has_b ? s_cand[e + 1] : ia;
+        double da, db;
+        if (vec) rs_dot2<true>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, s_q, dim, lane, da, db);
+        else rs_dot2<false>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, s_q, dim, lane, da, db);
+        if (lane == 0) {
+          s_dist[e] = (ia >= m_lo && ia < m_hi) ? 1.0 : 1.0 - da / (qnorm * (double)pn[ia]);
+          if (has_b) s_dist[e + 1] = (ib >= m_lo && ib < m_hi) ? 1.0 : 1.0 - db / (qnorm * (double)pn[ib]);
+        }
+      }
+      n_scored = n;
+    };
+    // keep the best k of the scored list (rank by (dist, index)); final: write them out in order
+    auto reduce_to_best = [&](bool final) {
+      const int n = s_n;
+      for (int e = tid; e < n; e += RS_THREADS) {
+        const double d = s_dist[e];
+        const int i = s_cand[e];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += rs_less(s_dist[j], s_cand[j], d, i);
+        if (rank < k) {
+          if (final) {
+            out_dist[row * k + rank] = (float)d;
+            out_idx[row * k + rank] = (int64_t)i + index_offset;
           } else {
-            for (int cc = lane; cc < dim; cc += 32) acc += (double)__ldg(prow + cc) * (double)s_q[cc];
-          }
-          acc = warp_sum(acc);
-          const double d = masked ? 1.0 : 1.0 - acc / (qnorm * (double)pn[pr]);
-          ++my_surv;
-          if (rs_less(d, pr, kth_d, kth_i)) {
-            if (lane == 0) {
-              int j = k - 1;
-              while (j > 0 && rs_less(d, pr, s_d[warp][j - 1], s_i[warp][j - 1])) {
-                s_d[warp][j] = s_d[warp][j - 1];
-                s_i[warp][j] = s_i[warp][j - 1];
-                --j;
-              }
-              s_d[warp][j] = d;
-              s_i[warp][j] = pr;
-            }
-            __syncwarp();
-            kth_d = s_d[warp][k - 1];
-            kth_i = s_i[warp][k - 1];
+            s_best_d[rank] = d;
+            s_best_i[rank] = i;
           }
         }
       }
-    }
-    if (lane == 0) s_nsurv[warp] = my_surv;
-    __syncthreads();
-    // merge the RS_WARPS sorted lists: rank of each entry among all RS_WARPS*k by (dist, idx)
-    for (int e = tid; e < RS_WARPS * k; e += RS_THREADS) {
-      const int w = e / k, j = e % k;
-      const double d = s_d[w][j];
-      const int i = s_i[w][j];
-      if (i == INT_MAX) continue;
-      int rank = 0;
-      for (int w2 = 0; w2 < RS_WARPS; ++w2)
-        for (int j2 = 0; j2 < k; ++j2) rank += rs_less(s_d[w2][j2], s_i[w2][j2], d, i);
-      if (rank < k) {
-        out_dist[row * k + rank] = (float)d;
-        out_idx[row * k + rank] = (int64_t)i + index_offset;
+      if (!final) {
+        __syncthreads();
+        const int keep = n < k ? n : k;
+        if (tid < keep) {
+          s_dist[tid] = s_best_d[tid];
+          s_cand[tid] = s_best_i[tid];
+        }
+        if (tid == 0) s_n = keep;
+        n_scored = keep;
+        __syncthreads();
+      }
+    };
+
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t slot = row * n_seg + s;
+      const int c = log_cnt[slot];
+      for (int base = 0; base < c; base += RS_THREADS) {
+        if (s_n + RS_THREADS > RS_LIST) {   // block-uniform (s_n is read after a barrier)
+          score();
+          __syncthreads();
+          reduce_to_best(false);
+        }
+        const int e = base + tid;
+        if (e < c && log_val[slot * cap + e] >= thr) {
+          const int pos = atomicAdd(&s_n, 1);
+          s_cand[pos] = log_idx[slot * cap + e];
+          atomicAdd(&s_nsurv, 1);
+        }
+        __syncthreads();
       }
     }
+    score();
+    __syncthreads();
+    reduce_to_best(true);
     if (tid == 0 && stats) {
-      int ns = 0;
-      for (int w = 0; w < RS_WARPS; ++w) ns += s_nsurv[w];
       atomicAdd(stats + 1, s_logged);
-      atomicAdd(stats + 2, ns);
+      atomicAdd(stats + 2, s_nsurv);
     }
   }
 }
@@ -175,7 +230,7 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
   if (n_query == 0) return 0;
   KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
-  size_t smem = (size_t)dim * sizeof(float);
+  size_t smem = (size_t)dim * sizeof(double);
   KNN_CHECK_ARG(smem <= 32 * 1024, -3, "dim %d too large for the rescoring kernel", dim);
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, log_val, log_idx, log_cnt, seg_top,
