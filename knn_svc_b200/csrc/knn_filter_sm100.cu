@@ -230,6 +230,20 @@ __device__ __forceinline__ int mono(int b) { return b ^ ((b >> 31) & 0x7fffffff)
 __device__ __forceinline__ int pack_key(float v, int slot) { return (mono(__float_as_int(v)) & ~31) | slot; }
 __device__ __forceinline__ float key_value(int key) { return __int_as_float(mono(key & ~31)); }
 
+// r[j] for a runtime j without local memory: a 5-level select tree (31 SELs).
+__device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+
 // Rare path: one accumulator value passed the register threshold.  Logs it and,
 // if it also beats the running k-th best, replaces that entry of the row's
 // UNSORTED top-k list in shared memory ([slot][row]: the 32 rows of a warp hit
@@ -481,28 +495,24 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
           if (__any_sync(0xffffffffu, mx > st.tau_lo)) {
-            // Rare path, warp-cooperative: per-lane bitmask of passing columns, OR-reduced over the
-            // warp; each column in the union is re-read from TMEM (one value per lane, uniform
-            // column) so no register array has to be indexed dynamically.
+            // Rare path, lane-parallel: every lane walks ITS OWN passing columns (a divergent loop:
+            // the trip count is the largest per-lane count, not the size of the warp's union), picking
+            // the value out of its registers with a select tree so the array is never indexed
+            // dynamically.  The threshold only rises, so later columns of the chunk are re-checked.
             const int cbase = col0 + c * 32;
             uint32_t mask = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > st.tau_lo ? 1u : 0u) << j;
-            uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
-            while (umask) {
-              const int j = __ffs(umask) - 1;
-              umask &= umask - 1;
-              uint32_t one;
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(one) : "r"(taddr + c * 32 + j) : "memory");
-              tmem_ld_wait();
-              float v = __uint_as_float(one);
-              if constexpr (MASKED) {
-                if (cbase + j >= m_lo && cbase + j < m_hi) v = 0.f;
-              }
-              if (((mask >> j) & 1u) && v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap)
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float v = __uint_as_float(select32(r, j));
+              if (v > st.tau_lo && (int64_t)(cbase + j) < n_pool && st.cnt <= cap) {
                 st = filter_insert(st, v, cbase + j, keys_row, k, lv, li, cap, window_scaled);
-              st.tau_lo = fmaxf(st.tau_lo, warm_lo);
+                st.tau_lo = fmaxf(st.tau_lo, warm_lo);
+              }
             }
+            __syncwarp();
           }
         }
         tcgen05_fence_before();
