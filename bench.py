@@ -35,6 +35,19 @@ METRIC = "query_frames_per_s_vs_10M_frame_pool_topk4"
 UNIT = "query frames/s"
 
 
+def _filter_traffic(T, n_shard):
+    """DRAM bytes of ONE filter launch from the committed ncu capture of this workload
+    (profiles/filter_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum); None when the
+    capture is for another shape."""
+    f = ROOT / "profiles" / "filter_traffic.json"
+    if not f.exists():
+        return None
+    d = json.loads(f.read_text())
+    if d.get("query_frames") == T and d.get("pool_frames_per_gpu") == n_shard:
+        return d.get("dram_bytes_per_launch")
+    return None
+
+
 def _peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -218,12 +231,24 @@ def main():
     # ---- end-to-end leg: pinned host query batch in, matched features + indices out, pool resident
     pool_prepared = ops.prepare_rows(pool, check=False)
 
+    # At N > 1 the host batch crosses PCIe ONCE in total: rank r uploads rows [r*chunk, (r+1)*chunk) and the
+    # ranks replicate the batch over NVLink (one all-gather); each rank downloads its own slice of the results.
+    chunk = (T + world - 1) // world
+    q_lo, q_hi = min(T, rank * chunk), min(T, (rank + 1) * chunk)
+    q_all = torch.zeros((world * chunk, DIM), device=dev) if world > 1 else None
+
     def e2e_step():
-        q_dev = query_host.to(dev, non_blocking=True)
+        if world > 1:
+            part = q_all[rank * chunk:(rank + 1) * chunk]
+            part[:q_hi - q_lo].copy_(query_host[q_lo:q_hi], non_blocking=True)
+            dist.all_gather_into_tensor(q_all, part.clone())
+            q_dev = q_all[:T]
+        else:
+            q_dev = query_host.to(dev, non_blocking=True)
         d, i, f = match_step(q_dev, pool_prepared)
-        feats_host.copy_(f, non_blocking=True)
-        idx_host.copy_(i, non_blocking=True)
-        dist_host.copy_(d, non_blocking=True)
+        feats_host[q_lo:q_hi].copy_(f[q_lo:q_hi], non_blocking=True)
+        idx_host[q_lo:q_hi].copy_(i[q_lo:q_hi], non_blocking=True)
+        dist_host[q_lo:q_hi].copy_(d[q_lo:q_hi], non_blocking=True)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -248,9 +273,11 @@ def main():
                     "peak_source": f"{peak_src} sustained cuBLAS bf16 (kernel timed inside a long step)",
                     "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                     "kernel_ms": filter_ms, "kernel_share_of_step": filter_ms / ms_step,
-                    "algorithmic_flops_per_launch": flops, "traffic": None}
+                    "algorithmic_flops_per_launch": flops, "traffic": _filter_traffic(T, n_shard),
+                    "traffic_note": "DRAM bytes per launch from the committed ncu capture profiles/filter_traffic.json "
+                                    "(not measured in this run); the kernel is tensor-bound, operands stream from L2"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
             from oracle import cpu_baseline              # checker/baseline only, never the measured path
             sec, threads = cpu_baseline.time_sample(args.cpu_queries, args.cpu_pool, DIM, steps=1, warmup=0)
             v = args.cpu_queries / (sec * (NP / args.cpu_pool))
@@ -268,8 +295,9 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": T * DIM * 4, "d2h_bytes_per_step": T * DIM * 4 + T * TOPK * 12,
-                        "note": "pinned host query batch in, features+indices+distances out; pool resident in HBM "
-                                "(built once, as get_matching_set does)"},
+                        "note": "pinned host query batch in, features+indices+distances out (bytes are totals over "
+                                "ranks: at N>1 each rank moves its 1/N slice over PCIe and the batch is replicated "
+                                "over NVLink); pool resident in HBM (built once, as get_matching_set does)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:

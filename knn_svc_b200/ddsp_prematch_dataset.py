@@ -142,6 +142,16 @@ def parse_post_opt(post_opt: str) -> float:
         return 0.3 if post_opt.split("_")[-1] == "extra" else -1
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]
+
+
 class MatchingPool:
     """Target-speaker pool resident in HBM: fp32 rows, fp16 tensor-core operand,
     norms, f0 and harmonic amplitudes (reference :1163-1168 builds the same
@@ -183,21 +193,32 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
     shifted_f0 = shift_query_f0_batched(query_f0s, pool.log_f0_median)       # :1224-1233
     concat_weight = parse_post_opt(post_opt)
     fit = "no_post_opt" not in post_opt
+    # Two independent chains follow the search — features (plain top-4 -> K5 -> K6 -> mix) and
+    # harmonics (f0 re-rank -> K5 with f0 -> K6 -> mix).  For a single utterance each stage is one
+    # CTA walking a serial recurrence, so the chains run on two streams and overlap.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if (concat_weight != -1 or fit) else main     # nothing long to overlap without post_opt
+    side.wait_stream(main)
+    harm = None
+    with torch.cuda.stream(side):
+        prio = sort_by_f0_compatibility(shifted_f0, pool.f0_dev, nearest_nbrs)   # :1377
+        idx_h = prio[:, :4].contiguous()                                         # :1398
+        if concat_weight != -1:
+            idx_h = ops.concat_cost_reselect(idx_h, query.rows, pool.matching.rows, shifted_f0, pool.f0_dev,
+                                             concat_weight=concat_weight, utt_offsets=offs)      # :1414
+        if "wavlm_only" not in ckpt_type and "no_harm_no_amp" not in ckpt_type:
+            hw = compute_extended_weight(idx_h, pool.harmonics, "sum_to_1_geq", [1], utt_offsets=offs) if fit else None
+            harm = ops.gather_mix(pool.harmonics, idx_h, hw)                     # :1444 / :1446
     idx_w = nearest_nbrs[:, :4].contiguous()                                 # :1246
     if concat_weight != -1:
         idx_w = ops.concat_cost_reselect(idx_w, query.rows, pool.matching.rows, concat_weight=concat_weight,
                                          utt_offsets=offs)                   # :1295
     w = compute_wavlm_weight(idx_w, pool.synth, "sum_to_1_geq", utt_offsets=offs) if fit else None   # :1357 / :1361
     out_feats = ops.gather_mix(pool.synth, idx_w, w)                         # :1358 / :1364
-    prio = sort_by_f0_compatibility(shifted_f0, pool.f0_dev, nearest_nbrs)   # :1377
-    idx_h = prio[:, :4].contiguous()                                         # :1398
-    if concat_weight != -1:
-        idx_h = ops.concat_cost_reselect(idx_h, query.rows, pool.matching.rows, shifted_f0, pool.f0_dev,
-                                         concat_weight=concat_weight, utt_offsets=offs)      # :1414
-    harm = None
-    if "wavlm_only" not in ckpt_type and "no_harm_no_amp" not in ckpt_type:
-        hw = compute_extended_weight(idx_h, pool.harmonics, "sum_to_1_geq", [1], utt_offsets=offs) if fit else None
-        harm = ops.gather_mix(pool.harmonics, idx_h, hw)                     # :1444 / :1446
+    main.wait_stream(side)
+    for t in (prio, idx_h, harm):
+        if t is not None:
+            t.record_stream(main)
     results = []
     for u in range(len(lens)):
         a, b = offs[u], offs[u + 1]
