@@ -109,6 +109,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        del os.environ["OMP_NUM_THREADS"]               # torchrun's default; the CPU arm may use every host core
     import torch
     from oracle import cpu_baseline                     # the one place bench.py executes oracle/
     nq, npool = args.cpu_queries, args.cpu_pool

@@ -34,8 +34,22 @@ def match_sample(query: torch.Tensor, pool: torch.Tensor, k_search: int = 32, k_
     return nbrs, out
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use every host core it may."""
+    import os
+    if torch.get_num_threads() > 1:
+        return torch.get_num_threads()          # torch's own default (affinity / cgroup aware) stands
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, min(n, 32)))   # capped: 20-row GEMM chunks do not scale past a few dozen threads
+    return torch.get_num_threads()
+
+
 def time_sample(n_query: int, n_pool: int, dim: int, steps: int = 1, warmup: int = 0, seed: int = 0):
     """Returns (seconds per pass, threads used)."""
+    use_all_host_threads()
     g = torch.Generator().manual_seed(seed)
     q = torch.randn((n_query, dim), generator=g)
     p = torch.randn((n_pool, dim), generator=g)
