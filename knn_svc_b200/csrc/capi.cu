@@ -31,6 +31,8 @@ int opt_cta_group() {
 int opt_bf16() { return g_opt_bf16; }
 static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
 int opt_spin_ns() { return g_opt_spin_ns; }
+static int g_opt_epi_sleep_ns = 0;
+int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns; }
 
 static int g_opt_concat_staged = 1;
 int opt_concat_staged() { return g_opt_concat_staged; }
@@ -189,8 +191,13 @@ int knnsvc_set_option(const char* name, int value) {
     return 0;
   }
   if (strcmp(name, "spin_sleep_ns") == 0) {
-    KNN_CHECK_ARG(value >= 0 && value <= 100000, -1, "set_option: spin_sleep_ns out of range");
+    KNN_CHECK_ARG(value >= 0 && value <= 60000, -1, "set_option: spin_sleep_ns out of range");
     g_opt_spin_ns = value;
+    return 0;
+  }
+  if (strcmp(name, "epi_sleep_ns") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= 60000, -1, "set_option: epi_sleep_ns out of range");
+    g_opt_epi_sleep_ns = value;
     return 0;
   }
   if (strcmp(name, "concat_staged") == 0) {

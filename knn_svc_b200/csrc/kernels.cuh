@@ -9,6 +9,7 @@ namespace knnsvc {
 int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
+int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
 int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
 
 // ---- rows.cu

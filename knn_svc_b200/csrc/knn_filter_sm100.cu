@@ -371,7 +371,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int pt = t0; pt < t1; ++pt) {
           const int p_row = pt * BN + (int)cta_rank * L::B_ROWS;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait_backoff(sbase + L::empty_bar + stage * 8, phase ^ 1, spin_ns);
+            mbar_wait_backoff(sbase + L::empty_bar + stage * 8, phase ^ 1, spin_ns & 0xffffu);
             const uint32_t full_local = sbase + L::full_bar + stage * 8;
             uint32_t full = full_local;
             if constexpr (CTAS == 2) {
@@ -403,11 +403,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int pt = t0; pt < t1; ++pt, ++tile_n) {
           const uint32_t buf = tile_n & 1;
           const uint32_t buf_phase = (tile_n >> 1) & 1;
-          mbar_wait_backoff(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1, spin_ns);
+          mbar_wait_backoff(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1, spin_ns & 0xffffu);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait_backoff(sbase + L::full_bar + stage * 8, phase, spin_ns);
+            mbar_wait_backoff(sbase + L::full_bar + stage * 8, phase, spin_ns & 0xffffu);
             tcgen05_fence_after();
             const uint32_t a_addr = sbase + L::ring + stage * L::STAGE_BYTES;
             const uint64_t da = make_smem_desc(a_addr);
@@ -474,7 +474,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int pt = t0; pt < t1; ++pt, ++tile_n) {
         const uint32_t buf = tile_n & 1;
         const uint32_t buf_phase = (tile_n >> 1) & 1;
-        mbar_wait(sbase + L::tmem_full_bar + buf * 8, buf_phase);
+        mbar_wait_backoff(sbase + L::tmem_full_bar + buf * 8, buf_phase, spin_ns >> 16);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
         const int col0 = pt * BN;
@@ -653,7 +653,7 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS, MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
                               pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
-                              seg_flag, idesc, (uint32_t)opt_spin_ns(), mask_lo, mask_hi, q_err, p_err));
+                              seg_flag, idesc, (uint32_t)opt_spin_ns() | ((uint32_t)opt_epi_sleep_ns() << 16), mask_lo, mask_hi, q_err, p_err));
   return 0;
 }
 
