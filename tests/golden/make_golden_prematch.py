@@ -162,6 +162,39 @@ def main():
             for k2 in ("nearest_nbrs", "nearest_nbrs_f0_priority", "harmonics_best_weight_para", "amp_ratio"):
                 out[f"pm_u{i}_{k2}"] = np.asarray(d[k2])
 
+    # ------------------------------------------------------------------ a12: the reference's KNeighborsVC itself
+    import ddsp_matcher as ref_matcher          # (reference)
+    from tests.util import FakeWavLM, fake_waveform
+
+    class Cfg:
+        sampling_rate = 16000
+
+    class FakeVocoder(torch.nn.Module):
+        def forward(self, c, f0=None, harm=None):
+            y = c.sum(-1)
+            if f0 is not None:
+                y = y + f0[..., 0]
+            if harm is not None:
+                y = y + harm.sum(-1)
+            return y[:, None, :]
+
+    knn = ref_matcher.KNeighborsVC(FakeWavLM(), FakeVocoder(), Cfg(), device="cpu")
+    wav = fake_waveform()
+    out["a12_weighting"] = knn.weighting.numpy()
+    f_fast, _ = quiet(knn.get_features, wav, None, 0)
+    out["a12_feats_fast"] = f_fast.numpy()
+    w2 = torch.linspace(0.0, 1.0, 25, dtype=torch.float64)[:, None]
+    f_slow, _ = quiet(knn.get_features, wav, w2, 0)
+    out["a12_feats_weighted"] = f_slow.numpy()
+    ms, _ = quiet(knn.get_matching_set, [wav, wav[:16000]], None, 0)
+    out["a12_matching_set"] = ms.numpy()
+    c = torch.from_numpy(synth.randn_frames(12, 16, seed=77))[None]
+    f0v = torch.from_numpy(synth.f0_track(12, seed=78))[None, :, None]
+    hv = torch.from_numpy(synth.harmonics_pool(12, seed=79))[None]
+    out["a12_vocode_plain"] = knn.vocode(c).numpy()
+    out["a12_vocode_f0"] = knn.vocode(c, f0v).numpy()
+    out["a12_vocode_mix"] = knn.vocode(c, f0v, hv).numpy()
+
     np.savez_compressed(HERE / "prematch_outputs.npz", **out)
     print({k: (v.shape, str(v.dtype)) for k, v in out.items()})
     print("bytes", os.path.getsize(HERE / "prematch_outputs.npz"))

@@ -47,3 +47,37 @@ def pool_builder_inputs(golden_pm):
     T = golden_pm["pb_spec"].shape[0]
     layer_feats = synth.randn_frames(25 * T, 64, seed=71).reshape(25, T, 64)
     return x, layer_feats, golden_pm["pb_f0"][:T]
+
+
+class FakeWavLM:
+    """Deterministic stand-in for the WavLM encoder (the checkpoint is not available): conv-stack
+    framing (400-sample window, hop 320) followed by fixed per-layer projections.  Used by the
+    fixture script with the REFERENCE's KNeighborsVC and by the tests with ours."""
+
+    class cfg:
+        encoder_layers = 24
+
+    def __init__(self, dim=16, seed=5):
+        import torch
+        g = torch.Generator().manual_seed(seed)
+        self.proj = torch.randn((25, 400, dim), generator=g) * 0.05
+        self.calls = []
+
+    def eval(self):
+        return self
+
+    def extract_features(self, wav, output_layer=None, ret_layer_results=False):
+        import torch
+        self.calls.append((tuple(wav.shape), output_layer, ret_layer_results))
+        frames = wav[0].unfold(0, 400, 320)                         # [T, 400]
+        layers = [torch.tanh(frames @ self.proj[l]) for l in range(25)]      # 25 x [T, dim]
+        if ret_layer_results:
+            return ((layers[-1][None], [(l[:, None, :], None) for l in layers]), None)
+        return (layers[output_layer][None], None)
+
+
+def fake_waveform(n=16000 * 2, seed=3):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n) / 16000.0
+    return (0.3 * torch.sin(2 * np.pi * 220.0 * t) + 0.02 * torch.randn(n, generator=g)).float()
