@@ -148,70 +148,91 @@ class KNeighborsVC(nn.Module):
         return self.vocode(out_feats[None], f0).squeeze()
 
     def _convert(self, src_wav_file, ref_wav_file, topk, device, prioritize_f0, ckpt_type, post_opt, **kw):
+        """match_at_inference_time as the reference's special_match / bulk_match call it: the
+        `mix` branch forwards `post_opt` (:959, :1091), the `wavlm_only` / `no_harm_no_amp` branch
+        does NOT (:970, :1112), so those checkpoints always run with "no_post_opt"."""
         from .ddsp_prematch_dataset import match_at_inference_time
-        res = match_at_inference_time(Path(src_wav_file), Path(ref_wav_file), self.wavlm, match_weights=self.weighting,
-                                      synth_weights=self.weighting, topk=topk, device=device,
-                                      prioritize_f0=prioritize_f0, ckpt_type=ckpt_type, post_opt=post_opt, **kw)
-        return res
+        if "wavlm_only" in ckpt_type or "no_harm_no_amp" in ckpt_type:
+            post_opt = "no_post_opt"
+        return match_at_inference_time(Path(src_wav_file), Path(ref_wav_file), self.wavlm, match_weights=self.weighting,
+                                       synth_weights=self.weighting, topk=topk, device=device,
+                                       prioritize_f0=prioritize_f0, ckpt_type=ckpt_type, post_opt=post_opt, **kw)
+
+    def _vocode_item(self, res, item, ckpt_type, device):
+        """reference :961-983 / :1093-1128: which vocoder inputs each checkpoint type gets"""
+        if "wavlm_only" not in ckpt_type and "no_harm_no_amp" not in ckpt_type:
+            feats, harm, _, f0 = res
+            return self.vocode(feats[item][None].to(device), f0[item][None, :, None], harm[item][None]).squeeze()
+        feats, _, f0 = res
+        if "wavlm_only_original" in ckpt_type:                      # the original kNN-VC vocoder takes no f0
+            return self.vocode(feats[item][None].to(device)).squeeze()
+        return self.vocode(feats[item][None].to(device), f0[item][None, :, None].to(device)).squeeze()
 
     def special_match(self, src_wav_file, ref_wav_file, topk: int = 4, device=None, prioritize_f0=True,
                       ckpt_type="wavlm_only", tgt_loudness_db=-16, post_opt="no_post_opt", save=True) -> Tensor:
         """One source file converted with one reference file (reference :937-1023).  Returns the
         waveform; like the reference it writes `<src>_to_<ref>_knn_<ckpt>_<post_opt>.wav` next to the
         source (the reference then calls sys.exit(), which is not reproduced)."""
+        from .lib_ongaku_test import save_audio
         device = torch.device(device) if device is not None else self.device
         res = self._convert(src_wav_file, ref_wav_file, topk, device, prioritize_f0, ckpt_type, post_opt)
-        key = Path(src_wav_file)
-        pick = lambda d: d[key] if key in d else d[src_wav_file]  # noqa: E731
-        if "wavlm_only" not in ckpt_type and "no_harm_no_amp" not in ckpt_type:
-            feats, harm, _, f0 = res
-            pred = self.vocode(pick(feats)[None].to(device), pick(f0)[None, :, None], pick(harm)[None]).squeeze()
-        else:
-            feats, _, f0 = res
-            pred = self.vocode(pick(feats)[None].to(device), pick(f0)[None, :, None].to(device)).squeeze()
+        key = Path(src_wav_file) if Path(src_wav_file) in res[0] else src_wav_file
+        pred = self._vocode_item(res, key, ckpt_type, device)
         if save:
-            import torchaudio
             src_id = os.path.basename(src_wav_file).split(".")[0]
             ref_id = os.path.basename(ref_wav_file).split(".")[0]
             out = str(Path(src_wav_file).parent) + "/" + src_id + "_to_" + ref_id + f"_knn_{ckpt_type}_{post_opt}.wav"
-            torchaudio.save(out, pred.detach().cpu()[None].float(), 16000)
+            print("->", out)
+            save_audio(out, pred.detach().cpu().numpy(), sample_rate=16000)                 # :1017
         return pred
 
     def bulk_match(self, src_dataset_path, tgt_dataset_path, converted_audio_dir, topk: int = 4, device=None,
                    prioritize_f0=True, ckpt_type="mix", tgt_loudness_db=-16, required_subset_file=None,
                    post_opt="no_post_opt", duration_limit=None, cache_pools: bool = True):
         """Dataset -> dataset conversion over (source speaker, target speaker) folder pairs
-        (reference :1027-1150).  The split file lists `<utt>/<tgt_spk>` pairs in column 2 of
-        rows labelled "0".  `cache_pools` keeps every speaker's pool (WavLM features, and for
-        targets the HBM-resident prepared pool) across the pair loop instead of rebuilding both
-        for each pair as the reference does (:1073-1112); results are identical."""
+        (reference :1027-1155): speaker folders are the sub-directories of the dataset roots
+        (`f0_cache*` skipped), a speaker is not converted to itself when both roots are the same,
+        the split file (header row skipped) lists `<utt>/<tgt_spk>` in column 2 of the rows whose
+        LAST column is "0" (:1050-1054), and each prediction is written to
+        `<out>/<src_spk>/<utt>/<tgt_spk>.<ext of the source file>` (:1133).  `cache_pools` keeps
+        every speaker's pool (WavLM features, and for targets the HBM-resident prepared pool) across
+        the pair loop instead of rebuilding both for each pair as the reference does (:1073-1112);
+        results are identical.  Returns the list of files written."""
         import csv
-        import torchaudio
         from .ddsp_prematch_dataset import PoolCache
+        from .lib_ongaku_test import save_audio
+        assert os.path.isdir(src_dataset_path) and os.path.isdir(tgt_dataset_path)
         device = torch.device(device) if device is not None else self.device
-        cache = PoolCache() if cache_pools else None
+        Path(converted_audio_dir).mkdir(parents=True, exist_ok=True)
+        src_spk_folders = sorted(i for i in Path(src_dataset_path).iterdir() if i.is_dir() and "f0_cache" not in i.name)
+        tgt_spk_folders = sorted(i for i in Path(tgt_dataset_path).iterdir() if i.is_dir() and "f0_cache" not in i.name)
+        if src_dataset_path != tgt_dataset_path:
+            assert len(set(src_spk_folders).intersection(set(tgt_spk_folders))) == 0
+        assert len(src_spk_folders) > 0, [f"Are you sure {src_dataset_path} is a FOLDER containing speaker folders, i.e. dataset root"]
+        assert len(tgt_spk_folders) > 0, [f"Are you sure {tgt_dataset_path} is a FOLDER containing speaker folders, i.e. dataset root"]
         required = None
-        if required_subset_file is not None:
-            with open(required_subset_file) as fh:
-                required = {row[2] for row in csv.reader(fh) if len(row) > 2 and row[0] == "0"}
+        if required_subset_file:
+            with open(required_subset_file, "r") as fp:
+                reader = csv.reader(fp, delimiter=",", quotechar='"')
+                required = [row[2] for row_idx, row in enumerate(reader) if row_idx != 0 and row[-1] == "0"]
+        cache = PoolCache(max_entries=len(src_spk_folders) + len(tgt_spk_folders)) if cache_pools else None
         written = []
-        for src_spk in sorted(os.listdir(src_dataset_path)):
-            for tgt_spk in sorted(os.listdir(tgt_dataset_path)):
-                s_dir, t_dir = os.path.join(src_dataset_path, src_spk), os.path.join(tgt_dataset_path, tgt_spk)
-                if not (os.path.isdir(s_dir) and os.path.isdir(t_dir)):
+        for i, spk_folder in enumerate(src_spk_folders):
+            for j, tgt_spk_folder in enumerate(tgt_spk_folders):
+                if src_dataset_path == tgt_dataset_path and i == j:      # avoid self to self
                     continue
-                res = self._convert(s_dir, t_dir, topk, device, prioritize_f0, ckpt_type, post_opt,
+                print(f"{spk_folder} -> {tgt_spk_folder}")
+                res = self._convert(spk_folder, tgt_spk_folder, topk, device, prioritize_f0, ckpt_type, post_opt,
                                     src_dataset_path=src_dataset_path, tgt_dataset_path=tgt_dataset_path,
                                     required_subset=required, duration_limit=duration_limit, pool_cache=cache)
-                feats, f0 = res[0], res[-1]
-                harm = res[1] if len(res) == 4 else None
-                for item in feats:
-                    h = None if harm is None else harm[item][None]
-                    pred = self.vocode(feats[item][None].to(device), f0[item][None, :, None].to(device), h).squeeze()
-                    utt = os.path.basename(str(item)).split(".")[0]
-                    out_dir = os.path.join(converted_audio_dir, src_spk, utt)
-                    os.makedirs(out_dir, exist_ok=True)
-                    out = os.path.join(out_dir, tgt_spk + ".wav")
-                    torchaudio.save(out, pred.detach().cpu()[None].float(), 16000)
+                for item in res[0]:
+                    pred = self._vocode_item(res, item, ckpt_type, device)
+                    assert len(pred.shape) == 1
+                    name = os.path.basename(str(item))
+                    out = os.path.join(converted_audio_dir, os.path.basename(spk_folder), name.split(".")[0],
+                                       os.path.basename(tgt_spk_folder) + "." + name.split(".")[-1])
+                    Path(out).parent.mkdir(parents=True, exist_ok=True)
+                    save_audio(out, pred[None, :].cpu().numpy(), sample_rate=self.sr)       # :1150
                     written.append(out)
+                print(f"{os.path.basename(spk_folder)}, {os.path.basename(tgt_spk_folder)} -> {converted_audio_dir}")
         return written

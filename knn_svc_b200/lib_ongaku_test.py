@@ -60,3 +60,35 @@ def knn_with_concat_cost(target_feature_indices, src_elements, tgt_elements, shi
                                     shifted_src_f0 if shifted_src_f0 is not None else None,
                                     tgt_f0 if shifted_src_f0 is not None else None,
                                     concat_weight=concat_weight)
+
+
+def save_audio(filename, waveform, sample_rate):
+    """reference lib_ongaku_test.py:89-145: float audio in [-1, 1] (rescaled by its peak when it
+    exceeds 1) to 32-bit PCM.  `.wav` is written as PCM_32 with the standard library (the reference
+    uses soundfile, same bytes on disk: RIFF/WAVE, 32-bit signed little-endian); `.mp3` / `.flac`
+    need pydub + ffmpeg as in the reference and raise if pydub is missing."""
+    import numpy as np
+    if isinstance(waveform, torch.Tensor):
+        waveform = waveform.detach().cpu().numpy()
+    if waveform.dtype == np.float32 or waveform.dtype == np.float64:
+        peak = np.max(np.abs(waveform)) if waveform.size else 0.0
+        if peak > 1:
+            waveform = waveform / peak
+        waveform = (waveform * (2 ** 31 - 1)).astype(np.int32)
+    else:
+        assert waveform.dtype == np.int32
+    if waveform.ndim == 2 and waveform.shape[0] in {1, 2}:
+        waveform = waveform.T                                    # [samples, channels]
+    channels = 1 if waveform.ndim == 1 else waveform.shape[1]
+    if filename.endswith(".wav"):
+        import wave
+        with wave.open(filename, "wb") as w:
+            w.setnchannels(channels)
+            w.setsampwidth(4)
+            w.setframerate(int(sample_rate))
+            w.writeframes(np.ascontiguousarray(waveform).astype("<i4").tobytes())
+        return
+    assert filename.split(".")[-1] in {"mp3", "flac"}
+    from pydub import AudioSegment                                # as the reference (:137-145)
+    AudioSegment(waveform.tobytes(), frame_rate=sample_rate, sample_width=4, channels=channels).export(
+        filename, format=filename.split(".")[-1], bitrate="320k")

@@ -2,6 +2,7 @@
 amp-scaled weight fit, the pool-builder tensor ops and the offline prematch driver, against the
 CPU oracle and the outputs of the reference itself (tests/golden/prematch_outputs.npz).
 Run on the B200 box: pytest -m gpu."""
+import os
 import pickle
 
 import numpy as np
@@ -325,3 +326,123 @@ def test_pool_cache_builds_each_speaker_once_and_changes_nothing(ops, golden):
             assert a.keys() == b.keys()
             for item in a:
                 assert (a[item] is None and b[item] is None) or torch.equal(a[item], b[item])
+
+
+# ----------------------------------------------------------------------------- special_match / bulk_match (a12)
+class _Cfg:
+    sampling_rate = 16000
+
+
+class _FakeVocoder(torch.nn.Module):
+    """stands in for the HiFi-GAN/DDSP vocoder: 320 samples per frame from the inputs it is given"""
+
+    def forward(self, c, f0=None, harm=None):
+        y = torch.tanh(c.float().mean(-1))
+        if f0 is not None:
+            y = y + 1e-4 * f0[..., 0].to(y)
+        if harm is not None:
+            y = y + harm.float().sum(-1).to(y)
+        return (0.1 * y).repeat_interleave(320, dim=1)[:, None, :]
+
+
+def _dataset(tmp_path, golden):
+    """2 source speakers (2 utterances each) and 2 target speakers under tmp_path/{src,tgt};
+    returns a producer stub keyed by folder"""
+    f0q, f0p = torch.from_numpy(golden["pipe_f0_src"]), torch.from_numpy(golden["pipe_f0_tgt"])
+    for root, spks in (("src", ("s0", "s1")), ("tgt", ("t0", "t1", "f0_cache_16000"))):
+        for s in spks:
+            (tmp_path / root / s).mkdir(parents=True)
+    calls = []
+
+    def fake_pool(path, *a, **k):
+        path = str(path)
+        calls.append(path)
+        seed = int(path[-1])
+        out = [dict() for _ in range(6)]
+        if "/src/" in path:
+            for u, ext in ((0, "wav"), (1, "wav")):      # (.flac/.mp3 outputs need pydub, as in the reference)
+                n = 60 + 20 * u
+                key = f"{path}/s{seed}utt{u}.{ext}"          # utterance names are unique across speakers, as in real datasets
+                feats = torch.from_numpy(synth.ar1_frames(n, seed=500 + 10 * seed + u, reset_every=50)).to(DEV)
+                vals = (feats, feats, torch.zeros(n, 320), torch.ones(n, 201), f0q[:n].clone(), torch.zeros(n, 49))
+                for d, v in zip(out, vals):
+                    d[key] = v
+        else:
+            n, key = 400, f"{path}/ref.wav"
+            feats = torch.from_numpy(synth.ar1_frames(n, seed=600 + seed)).to(DEV)
+            vals = (feats, feats, torch.zeros(n, 320), torch.ones(n, 201), f0p, torch.from_numpy(synth.harmonics_pool(n, seed=700 + seed)))
+            for d, v in zip(out, vals):
+                d[key] = v
+        return tuple(out)
+
+    return fake_pool, calls
+
+
+def test_bulk_match_writes_one_file_per_required_pair(ops, golden, tmp_path):
+    import wave
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    from knn_svc_b200.ddsp_matcher import KNeighborsVC
+    fake_pool, calls = _dataset(tmp_path, golden)
+    split = tmp_path / "split.txt"
+    split.write_text("src_speaker,tgt_speaker,x_path,y_path,label\n"
+                     "s0,t0,s0utt0/t0,t0/ref,0\n"
+                     "s0,t1,s0utt1/t1,t1/ref,0\n"
+                     "s1,t0,s1utt0/t0,t0/ref,0\n"
+                     "s1,t1,s1utt0/t1,t1/ref,1\n")            # label 1: not a conversion row
+    knn = KNeighborsVC(None, _FakeVocoder(), _Cfg(), device=DEV)
+    old = pm.get_complete_spk_pool
+    pm.get_complete_spk_pool = fake_pool
+    try:
+        written = knn.bulk_match(str(tmp_path / "src"), str(tmp_path / "tgt"), str(tmp_path / "out"), ckpt_type="mix",
+                                 required_subset_file=str(split), post_opt="post_opt_0.2")
+    finally:
+        pm.get_complete_spk_pool = old
+    rel = sorted(os.path.relpath(w, tmp_path / "out") for w in written)
+    assert rel == ["s0/s0utt0/t0.wav", "s0/s0utt1/t1.wav", "s1/s1utt0/t0.wav"]
+    assert len(calls) == 4                                   # 2 + 2 speakers, each pool built once (f0_cache* skipped)
+    with wave.open(str(tmp_path / "out" / "s0" / "s0utt0" / "t0.wav"), "rb") as w:
+        assert (w.getframerate(), w.getsampwidth(), w.getnchannels(), w.getnframes()) == (16000, 4, 1, 60 * 320)
+
+
+def test_special_match_returns_the_vocoded_conversion(ops, golden, tmp_path):
+    import wave
+    from pathlib import Path
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    from knn_svc_b200.ddsp_matcher import KNeighborsVC
+    qf, pf = synth.ar1_frames(120, seed=51, reset_every=50), synth.ar1_frames(400, seed=52)
+    hp = synth.harmonics_pool(400, seed=53)
+    f0q, f0p = torch.from_numpy(golden["pipe_f0_src"]), torch.from_numpy(golden["pipe_f0_tgt"])
+    src, ref = tmp_path / "src.wav", tmp_path / "ref.wav"
+    src.touch(); ref.touch()
+
+    def fake_pool(wav, *a, **k):
+        if "src" in str(wav):
+            feats, f0, n, harm = torch.from_numpy(qf).double().to(DEV), f0q, 120, torch.zeros(120, 49)
+        else:
+            feats, f0, n, harm = torch.from_numpy(pf).double().to(DEV), f0p, 400, torch.from_numpy(hp)
+        key = Path(wav)
+        return ({key: feats}, {key: feats}, {key: torch.zeros(n, 320)}, {key: torch.ones(n, 201)}, {key: f0}, {key: harm})
+
+    voc = _FakeVocoder()
+    knn = KNeighborsVC(None, voc, _Cfg(), device=DEV)
+    old = pm.get_complete_spk_pool
+    pm.get_complete_spk_pool = fake_pool
+    try:
+        pred = knn.special_match(str(src), str(ref), ckpt_type="mix", post_opt="no_post_opt")
+        feats, harm, _, sf0 = pm.match_at_inference_time(Path(src), Path(ref), None, None, None, device=DEV,
+                                                         prioritize_f0=True, ckpt_type="mix", post_opt="no_post_opt")
+        pred_w = knn.special_match(str(src), str(ref), ckpt_type="wavlm_only", post_opt="post_opt_0.2", save=False)
+        plain = pm.match_at_inference_time(Path(src), Path(ref), None, None, None, device=DEV, prioritize_f0=True,
+                                           ckpt_type="wavlm_only", post_opt="no_post_opt")
+    finally:
+        pm.get_complete_spk_pool = old
+    want = voc(feats[Path(src)][None], sf0[Path(src)][None, :, None], harm[Path(src)][None]).squeeze()
+    assert pred.shape == (120 * 320,) and torch.equal(pred, want)
+    out = tmp_path / "src_to_ref_knn_mix_no_post_opt.wav"                    # reference :1014
+    with wave.open(str(out), "rb") as w:
+        assert (w.getframerate(), w.getsampwidth(), w.getnframes()) == (16000, 4, 120 * 320)
+        pcm = np.frombuffer(w.readframes(120 * 320), dtype="<i4")
+    assert np.array_equal(pcm, (pred.cpu().numpy() * (2 ** 31 - 1)).astype(np.int32))
+    # wavlm_only: the reference does not forward post_opt on this branch (:970) -> plain mean of the top-4
+    want_w = voc(plain[0][Path(src)][None], plain[2][Path(src)][None, :, None].to(DEV)).squeeze()
+    assert torch.equal(pred_w, want_w)
