@@ -12,6 +12,8 @@ import torch
 from . import _lib
 
 MAX_K = 32
+WORKSPACE_BUDGET = 16 << 30    # bytes of search scratch above which the query rows are chunked
+_MIN_CHUNK = 128 * 148         # one query tile per SM
 _HALF_ALIGN = 64   # the tcgen05 filter consumes the feature dimension in 64-element slabs
 
 
@@ -144,15 +146,26 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
             raise ValueError("mask_lo / mask_hi must have one entry per query row")
     if T > 0:
         with torch.cuda.device(dev):
-            nbytes = lib.knnsvc_knn_workspace_bytes(T, pool.n, query.dim_pad, k)
-            ws = _workspace(nbytes, dev)
-            _lib.check(lib.knnsvc_knn_search_masked(query.rows.data_ptr(), query.half.data_ptr(),
-                                                    query.norms.data_ptr(), T, pool.rows.data_ptr(),
-                                                    pool.half.data_ptr(), pool.norms.data_ptr(), pool.n, query.dim,
-                                                    query.dim_pad, k, index_offset, _ptr(query.err), _ptr(pool.err),
-                                                    _ptr(mask_lo), _ptr(mask_hi),
-                                                    dist.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                    stats.data_ptr(), _stream()), "knn_search")
+            # The candidate log is sized for the worst case (rows x segments x cap); very large query
+            # sets are searched in row chunks so the scratch buffer stays below WORKSPACE_BUDGET.
+            chunk = T
+            while chunk > _MIN_CHUNK and lib.knnsvc_knn_workspace_bytes(chunk, pool.n, query.dim_pad, k) > WORKSPACE_BUDGET:
+                chunk = max(_MIN_CHUNK, (chunk // 2 + _MIN_CHUNK - 1) // _MIN_CHUNK * _MIN_CHUNK)
+            ws = _workspace(lib.knnsvc_knn_workspace_bytes(chunk, pool.n, query.dim_pad, k), dev)
+            part_stats = torch.zeros((8,), dtype=torch.int32, device=dev) if chunk < T else stats
+            for a in range(0, T, chunk):
+                n = min(chunk, T - a)
+                _lib.check(lib.knnsvc_knn_search_masked(
+                    query.rows[a:].data_ptr(), query.half[a:].data_ptr(), query.norms[a:].data_ptr(), n,
+                    pool.rows.data_ptr(), pool.half.data_ptr(), pool.norms.data_ptr(), pool.n, query.dim,
+                    query.dim_pad, k, index_offset, _ptr(query.err), _ptr(pool.err),
+                    None if mask_lo is None else mask_lo[a:].data_ptr(),
+                    None if mask_hi is None else mask_hi[a:].data_ptr(),
+                    dist[a:].data_ptr(), idx[a:].data_ptr(), ws.data_ptr(), ws.numel(), part_stats.data_ptr(),
+                    _stream()), "knn_search")
+                if chunk < T:
+                    stats[:3] += part_stats[:3]          # flagged rows, logged candidates, survivors
+                    stats[3:] = part_stats[3:]
     if return_stats:
         return dist, idx, stats
     return dist, idx

@@ -483,3 +483,17 @@ def test_matcher_match_api(ops):
     assert np.abs(out.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max()
     out2 = m.match(torch.from_numpy(q), torch.from_numpy(p), topk=4, without_vocode=True, post_opt="post_opt_0.2")
     assert out2.shape == out.shape and torch.isfinite(out2).all()
+
+
+def test_knn_search_row_chunking_changes_nothing(ops, monkeypatch):
+    """query sets whose candidate log would exceed the scratch budget are searched in row chunks:
+    same results, same statistics totals, masks and index offsets honoured per chunk"""
+    q, p = synth.ar1_frames(1000, seed=71, reset_every=300), synth.ar1_frames(1500, seed=72)
+    qp, pp = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p))
+    lo = np.repeat(np.arange(0, 1000, 100), 100).astype(np.int64); hi = lo + 50
+    d0, i0, s0 = ops.knn_search(qp, pp, 32, index_offset=7, return_stats=True, mask_lo=dev(lo), mask_hi=dev(hi))
+    monkeypatch.setattr(ops, "_MIN_CHUNK", 256)
+    monkeypatch.setattr(ops, "WORKSPACE_BUDGET", 1)
+    d1, i1, s1 = ops.knn_search(qp, pp, 32, index_offset=7, return_stats=True, mask_lo=dev(lo), mask_hi=dev(hi))
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert s0[0].item() == s1[0].item() and s0[2].item() == s1[2].item()    # flagged rows, survivors (plan-independent)
