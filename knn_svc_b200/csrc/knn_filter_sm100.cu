@@ -244,16 +244,12 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&r)[32], int j) {
   return (j & 16) ? d[1] : d[0];
 }
 
-// Rare path: one accumulator value passed the register threshold.  Logs it and,
-// if it also beats the running k-th best, replaces that entry of the row's
-// UNSORTED top-k list in shared memory ([slot][row]: the 32 rows of a warp hit
-// 32 banks) and takes the minimum over the 32 slot keys — independent loads and a
-// min tree instead of an insertion sort's dependent chain.
-__device__ __noinline__ RowState filter_insert(RowState st, float v, int col, int* __restrict__ keys_row, int k,
-                                               float* __restrict__ log_val, int* __restrict__ log_idx, int cap,
-                                               float window_scaled) {
+// Rare path, part 1 (slow): the row's log is full.  Compact it in place — entries below the
+// current threshold can never be needed (tau only rises) — then append, or mark a genuine
+// overflow (more than `cap` candidates inside the window: the exact kernel will decide the row).
+__device__ __noinline__ RowState filter_log_full(RowState st, float v, int col, float* __restrict__ log_val,
+                                                 int* __restrict__ log_idx, int cap) {
   if (st.cnt == cap) {
-    // compact in place: entries below the current threshold can never be needed (tau only rises)
     int n = 0;
     for (int e0 = 0; e0 < cap; e0 += 8) {
       float lv[8];
@@ -279,21 +275,46 @@ __device__ __noinline__ RowState filter_insert(RowState st, float v, int col, in
     log_idx[st.cnt] = col;
     ++st.cnt;
   } else {
-    st.cnt = cap + 1;  // genuine overflow: more than `cap` candidates inside the window
+    st.cnt = cap + 1;  // genuine overflow
   }
-  if (v > st.kth) {
-    keys_row[st.kpos * BM] = pack_key(v, st.kpos);
-    int key[kSlots];
+  return st;
+}
+
+// Rare path, part 2: the value also beats the running k-th best.  It replaces that entry of the
+// row's UNSORTED top-k list in shared memory ([slot][row]: the 32 rows of a warp hit 32 banks)
+// and the minimum over the 32 slot keys is retaken — independent loads and a min tree instead of
+// an insertion sort's dependent chain.
+__device__ __noinline__ RowState filter_list_update(RowState st, float v, int* __restrict__ keys_row,
+                                                    float window_scaled) {
+  keys_row[st.kpos * BM] = pack_key(v, st.kpos);
+  int key[kSlots];
 #pragma unroll
-    for (int j = 0; j < kSlots; ++j) key[j] = keys_row[j * BM];
+  for (int j = 0; j < kSlots; ++j) key[j] = keys_row[j * BM];
 #pragma unroll
-    for (int w = kSlots / 2; w > 0; w >>= 1)
+  for (int w = kSlots / 2; w > 0; w >>= 1)
 #pragma unroll
-      for (int j = 0; j < w; ++j) key[j] = min(key[j], key[j + w]);
-    st.kth = key_value(key[0]);
-    st.kpos = key[0] & 31;
-    st.tau_lo = st.kth - window_scaled;  // stays ~-3e38 until k values have been seen
+    for (int j = 0; j < w; ++j) key[j] = min(key[j], key[j + w]);
+  st.kth = key_value(key[0]);
+  st.kpos = key[0] & 31;
+  st.tau_lo = st.kth - window_scaled;  // stays ~-3e38 until k values have been seen
+  return st;
+}
+
+// One accumulator value passed the register threshold: log it (inline fast path — on rows with
+// dense neighbourhoods most passing values sit inside the error window but below the k-th best and
+// need nothing else) and update the top-k list only if it beats the k-th best.
+__device__ __forceinline__ RowState filter_insert(RowState st, float v, int col, int* __restrict__ keys_row, int k,
+                                                  float* __restrict__ log_val, int* __restrict__ log_idx, int cap,
+                                                  float window_scaled) {
+  (void)k;
+  if (st.cnt < cap) {
+    log_val[st.cnt] = v * kDotUnscale;
+    log_idx[st.cnt] = col;
+    ++st.cnt;
+  } else {
+    st = filter_log_full(st, v, col, log_val, log_idx, cap);
   }
+  if (v > st.kth) st = filter_list_update(st, v, keys_row, window_scaled);
   return st;
 }
 
