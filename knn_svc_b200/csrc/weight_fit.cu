@@ -30,48 +30,88 @@ __host__ __device__ constexpr int wf_c(int i, int j) { return 26 + (i <= j ? wf_
 constexpr int WF_THREADS = 512;
 constexpr int WF_SMEM_FRAMES = 10240;  // frames whose weights fit in shared memory
 
-// ---- Gram build: one CTA per frame pair t (frames t, t+1); warp i owns row i of both blocks
-__global__ void __launch_bounds__(WF_V * 32) weight_gram_kernel(const int64_t* __restrict__ idx,
-                                                                const float* __restrict__ synth, int64_t n_pool,
-                                                                int dim, int64_t n_query, double* __restrict__ gram) {
-  const int64_t t = blockIdx.x;
+// ---- Gram build: one WARP per frame pair t (frames t, t+1).  For each of the two blocks the lane
+// loads its columns of all 8 rows ONCE (8 loads) and forms the 36 unique products of the
+// symmetric 8x8 Gram from registers: 36 DFMA per 8 loads, so the kernel runs at the fp64 pipe's
+// rate instead of the L1 load-issue rate (the first version re-read the 8 rows in every warp:
+// 9 loads per 8 DFMA, 5x slower at D = 1024).  Both blocks accumulate into the same 36 sums
+// (G_t is their sum).  Products of two fp32 values are exact in fp64.
+constexpr int WG_WARPS = 8;
+
+__device__ __forceinline__ void wg_accumulate(const double (&v)[WF_V], double (&acc)[WF_E]) {
+#pragma unroll
+  for (int i = 0; i < WF_K; ++i)           // A: rows 0..3 x rows i..3      (entries 0..9)
+#pragma unroll
+    for (int j = i; j < WF_K; ++j) acc[wf_tri(i, j)] = fma(v[i], v[j], acc[wf_tri(i, j)]);
+#pragma unroll
+  for (int i = 0; i < WF_K; ++i)           // B: rows 0..3 x rows 4..7      (entries 10..25)
+#pragma unroll
+    for (int j = 0; j < WF_K; ++j) acc[wf_b(i, j)] = fma(v[i], v[WF_K + j], acc[wf_b(i, j)]);
+#pragma unroll
+  for (int i = 0; i < WF_K; ++i)           // C: rows 4..7 x rows 4+i..7    (entries 26..35)
+#pragma unroll
+    for (int j = i; j < WF_K; ++j) acc[26 + wf_tri(i, j)] = fma(v[WF_K + i], v[WF_K + j], acc[26 + wf_tri(i, j)]);
+}
+
+__global__ void __launch_bounds__(WG_WARPS * 32) weight_gram_kernel(const int64_t* __restrict__ idx,
+                                                                    const float* __restrict__ synth, int64_t n_pool,
+                                                                    int dim, int64_t n_query, double* __restrict__ gram) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ int64_t rows[2][WF_V];
-  if (threadIdx.x < WF_V) {
-    const int j = threadIdx.x;
-    const int64_t base = (j < WF_K) ? idx[(t + 1) * WF_K + j] : idx[t * WF_K + (j - WF_K)];
-    // block 0: (S_-1[t+1], S_0[t]); block 1: (S_0[t+1], S_+1[t])
+  const int64_t n_pairs = n_query - 1;
+  const int64_t t = (int64_t)blockIdx.x * WG_WARPS + warp;
+  if (t >= n_pairs) return;
+  // rows of the two blocks: block 0 = (S_-1[t+1,k], S_0[t,k]), block 1 = (S_0[t+1,k], S_+1[t,k])
+  const float* rows[2][WF_V];
+#pragma unroll
+  for (int j = 0; j < WF_V; ++j) {
+    const int64_t base = (j < WF_K) ? __ldg(idx + (t + 1) * WF_K + j) : __ldg(idx + t * WF_K + (j - WF_K));
     int64_t r0 = base + ((j < WF_K) ? -1 : 0);
     int64_t r1 = base + ((j < WF_K) ? 0 : 1);
     r0 = r0 < 0 ? 0 : (r0 >= n_pool ? n_pool - 1 : r0);
     r1 = r1 < 0 ? 0 : (r1 >= n_pool ? n_pool - 1 : r1);
-    rows[0][j] = r0;
-    rows[1][j] = r1;
+    rows[0][j] = synth + r0 * dim;
+    rows[1][j] = synth + r1 * dim;
   }
-  __syncthreads();
-  double acc[WF_V];
+  double acc[WF_E];
 #pragma unroll
-  for (int j = 0; j < WF_V; ++j) acc[j] = 0.0;
+  for (int e = 0; e < WF_E; ++e) acc[e] = 0.0;
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(synth) & 15) == 0);
+#pragma unroll
   for (int b = 0; b < 2; ++b) {
-    const float* mine = synth + rows[b][warp] * dim;
-    for (int c = lane; c < dim; c += 32) {
-      const double a = (double)__ldg(mine + c);
+    if (vec) {
+#pragma unroll 1
+      for (int c = lane; c < dim / 4; c += 32) {
+        float4 x[WF_V];
 #pragma unroll
-      for (int j = 0; j < WF_V; ++j) acc[j] += a * (double)__ldg(synth + rows[b][j] * dim + c);
+        for (int j = 0; j < WF_V; ++j) x[j] = __ldg(reinterpret_cast<const float4*>(rows[b][j]) + c);
+        double v[WF_V];
+#pragma unroll
+        for (int j = 0; j < WF_V; ++j) v[j] = (double)x[j].x;
+        wg_accumulate(v, acc);
+#pragma unroll
+        for (int j = 0; j < WF_V; ++j) v[j] = (double)x[j].y;
+        wg_accumulate(v, acc);
+#pragma unroll
+        for (int j = 0; j < WF_V; ++j) v[j] = (double)x[j].z;
+        wg_accumulate(v, acc);
+#pragma unroll
+        for (int j = 0; j < WF_V; ++j) v[j] = (double)x[j].w;
+        wg_accumulate(v, acc);
+      }
+    } else {
+#pragma unroll 1
+      for (int c = lane; c < dim; c += 32) {
+        double v[WF_V];
+#pragma unroll
+        for (int j = 0; j < WF_V; ++j) v[j] = (double)__ldg(rows[b][j] + c);
+        wg_accumulate(v, acc);
+      }
     }
   }
-  const int64_t n_pairs = n_query - 1;
 #pragma unroll
-  for (int j = 0; j < WF_V; ++j) {
-    const double v = warp_sum(acc[j]);
-    if (lane == 0) {
-      const int i = warp;
-      int e = -1;
-      if (i < 4 && j < 4 && j >= i) e = wf_tri(i, j);
-      else if (i < 4 && j >= 4) e = wf_b(i, j - 4);
-      else if (i >= 4 && j >= i) e = 26 + wf_tri(i - 4, j - 4);
-      if (e >= 0) gram[(int64_t)e * n_pairs + t] = v;
-    }
+  for (int e = 0; e < WF_E; ++e) {
+    const double v = warp_sum(acc[e]);
+    if (lane == (e & 31)) gram[(int64_t)e * n_pairs + t] = v;   // 36 entries over 32 lanes
   }
 }
 
@@ -334,7 +374,8 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   const int64_t n_pairs_total = n_query - 1;
   if (n_pairs_total > 0) {
     // pairs that straddle two utterances are computed too (same pool, in-range rows) and never read
-    weight_gram_kernel<<<(unsigned)n_pairs_total, WF_V * 32, 0, stream>>>(idx, synth, n_pool, dim, n_query, gram);
+    weight_gram_kernel<<<(unsigned)ceil_div64(n_pairs_total, WG_WARPS), WG_WARPS * 32, 0, stream>>>(idx, synth, n_pool,
+                                                                                                 dim, n_query, gram);
     KNN_LAUNCH_CHECK();
   }
   const int smem_frames = longest <= WF_SMEM_FRAMES ? (int)longest : 0;   // all utterances or none use smem weights

@@ -1,0 +1,119 @@
+"""Turn one capture run's scratch files (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
+
+    python tools/make_profiles.py r1g          # tag of the capture run
+
+Inputs (all produced under gpurun on a B200):
+  <tag>_launches_bench_full.csv   ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum --clock-control none
+                                  on `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`
+  <tag>_filter_full.ncu-rep       ncu --set full of the tcgen05 filter (32768 x 2M)
+  <tag>_rescore_full.ncu-rep      ncu --set full of the re-scoring kernel
+  <tag>_small_kernels.csv         ncu metrics of tools/profile_small_kernels.py
+  <tag>_bench_*.jsonl / .json     CUDA-event timed microbenches and the bench lines
+"""
+import collections
+import csv
+import json
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
+sys.path.insert(0, str(ROOT / "tools"))
+import ncu_summary  # noqa: E402
+
+
+def launch_list(tag):
+    rows = list(csv.reader(open(OUT / f"{tag}_launches_bench_full.csv")))
+    hdr, agg = None, collections.OrderedDict()
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            try:
+                v = float(d["Metric Value"].replace(",", ""))
+            except ValueError:
+                continue
+            agg.setdefault(d["Kernel Name"][:70], {}).setdefault(d["Metric Name"], []).append(v)
+    tot = sum(sum(m["gpu__time_duration.sum"]) for m in agg.values())
+    lines = ["# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (100k x 10M, N=1), per kernel:",
+             "# launches, total device time, share of all device time, DRAM read+write per launch (mean)",
+             f"# raw csv: profiles/r1_launches_bench_100kx10M.csv (ncu --metrics gpu__time_duration.sum,"
+             "dram__bytes_read.sum,dram__bytes_write.sum --clock-control none)"]
+    traffic = None
+    for k, m in agg.items():
+        t, rd, wr = m["gpu__time_duration.sum"], m.get("dram__bytes_read.sum", [0]), m.get("dram__bytes_write.sum", [0])
+        lines.append(f"{k:72s} n={len(t):3d} total_ms={sum(t) / 1e6:10.3f} share={sum(t) / tot:.4f} "
+                     f"dram_GB_per_launch={(sum(rd) + sum(wr)) / len(t) / 1e9:9.3f}")
+        if "knn_filter" in k:
+            traffic = {"kernel": "knn_filter_kernel<1,false>", "query_frames": 100000, "pool_frames_per_gpu": 10000000,
+                       "dim": 1024, "topk": 4, "dram_bytes_per_launch": (sum(rd) + sum(wr)) / len(t),
+                       "dram_bytes_read_per_launch": sum(rd) / len(rd), "dram_bytes_write_per_launch": sum(wr) / len(wr),
+                       "launches_measured": len(t), "kernel_ms_under_ncu": [x / 1e6 for x in t],
+                       "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on `python "
+                                 "bench.py --steps 2 --warmup 1 --no-cpu-baseline` (profiles/r1_launches_bench_100kx10M.txt)",
+                       "note": "the fp16 pool operand is 20.5 GB; 3-5% of the 23.5 TB of TMA operand loads per launch miss "
+                               "the 126 MB L2 (the 148 CTAs of a wave drift apart while streaming a 1.25 GB pool segment), so "
+                               "it is re-read from DRAM ~35-55x per launch = 0.45-0.7 TB/s, <= 10% of HBM peak; launch-to-"
+                               "launch spread 0.75-1.2 TB"}
+    (PROF / "r1_launches_bench_100kx10M.txt").write_text("\n".join(lines) + "\n")
+    shutil.copy(OUT / f"{tag}_launches_bench_full.csv", PROF / "r1_launches_bench_100kx10M.csv")
+    if traffic:
+        (PROF / "filter_traffic.json").write_text(json.dumps(traffic, indent=1))
+
+
+def small_kernels(tag):
+    rows = list(csv.reader(open(OUT / f"{tag}_small_kernels.csv")))
+    hdr, recs = None, collections.OrderedDict()
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            recs.setdefault((d["ID"], d["Kernel Name"][:52]), {})[d["Metric Name"]] = (d["Metric Value"], d["Metric Unit"])
+    names = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+             "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size",
+             "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+    out = ["# ncu per-kernel metrics of tools/profile_small_kernels.py (every non-GEMM kernel at bench_kernels.py sizes; the",
+           "# second launch of each is shown).  ncu --metrics <columns> --clock-control none",
+           " | ".join(["kernel", "time", "dram_read", "dram_write", "dram_%peak", "sm_%peak", "regs", "warps_active_%", "grid",
+                       "issue_active_%"])]
+    seen = collections.Counter()
+    for (_, k), m in recs.items():
+        if k.startswith("void at") or "at_cuda_detail" in k or "compute_cuda_kernel" in k or "softmax_warp" in k:
+            continue
+        key = (k, m.get("launch__grid_size", ("", ""))[0])
+        seen[key] += 1
+        tiny = "exact" in k or "write_plan" in k
+        if (tiny and seen[key] != 1) or (not tiny and seen[key] != 2):
+            continue
+        out.append(" | ".join([k] + [" ".join(m.get(n, ("", ""))) for n in names]))
+    (PROF / "r1_small_kernels_ncu.txt").write_text("\n".join(out) + "\n")
+
+
+def main():
+    tag = sys.argv[1]
+    PROF.mkdir(exist_ok=True)
+    launch_list(tag)
+    small_kernels(tag)
+    for rep, dst in ((f"{tag}_filter_full.ncu-rep", "r1_filter_ncu_full_32768x2M.txt"),
+                     (f"{tag}_rescore_full.ncu-rep", "r1_rescore_ncu_full.txt")):
+        if (OUT / rep).exists():
+            (PROF / dst).write_text(f"#### {rep}\n" + ncu_summary.rep_summary(str(OUT / rep)) + "\n")
+    for src, dst in ((f"{tag}_bench_kernels.jsonl", "r1_bench_kernels.jsonl"), (f"{tag}_bench_search.jsonl", "r1_bench_search.jsonl"),
+                     (f"{tag}_bench_n1.json", "r1_bench_n1.json"), (f"{tag}_bench_ref.json", "r1_bench_reference_arm.json")):
+        if (OUT / src).exists():
+            shutil.copy(OUT / src, PROF / dst)
+    parts = [OUT / f"{tag}_bench_pipeline.jsonl", OUT / f"{tag}_bench_cfg5.jsonl"]
+    if all(p.exists() for p in parts):
+        (PROF / "r1_bench_pipeline_cfg5.jsonl").write_text("".join(p.read_text() for p in parts))
+    print("profiles/ refreshed from", tag)
+
+
+if __name__ == "__main__":
+    main()
