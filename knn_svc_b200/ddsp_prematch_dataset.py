@@ -123,9 +123,15 @@ def shift_query_f0_batched(f0_list, matching_f0_median: torch.Tensor):
     dev = matching_f0_median.device
     lens = [int(len(f)) for f in f0_list]
     U, L = len(lens), max(lens + [1])
-    pad = torch.zeros((U, L), dtype=f0_list[0].dtype if U else torch.float32, device=dev)
-    for u, f in enumerate(f0_list):
-        pad[u, :lens[u]] = f.to(dev)
+    if U and all(f.device.type == "cpu" for f in f0_list):
+        # f0 tracks live on the host (reference :373-382): pad there, ONE host-to-device copy
+        pad = torch.nn.utils.rnn.pad_sequence(list(f0_list), batch_first=True).to(dev, non_blocking=True)
+        if pad.shape[1] < L:
+            pad = torch.nn.functional.pad(pad, (0, L - pad.shape[1]))
+    else:
+        pad = torch.zeros((U, L), dtype=f0_list[0].dtype if U else torch.float32, device=dev)
+        for u, f in enumerate(f0_list):
+            pad[u, :lens[u]] = f.to(dev)
     voiced = pad != 0
     logf = torch.log(torch.where(voiced, pad, torch.ones_like(pad)))
     med = _lower_median_rows(logf, voiced)                      # NaN-free even for all-unvoiced rows
@@ -219,10 +225,14 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
     for t in (prio, idx_h, harm):
         if t is not None:
             t.record_stream(main)
+    # the reference hands the shifted f0 back on the device its f0 came from (the host): one copy
+    f0_devs = {f.device for f in query_f0s}
+    shifted_host = shifted_f0.to(next(iter(f0_devs))) if len(f0_devs) == 1 else None
     results = []
     for u in range(len(lens)):
         a, b = offs[u], offs[u + 1]
-        r = {"out_feats": out_feats[a:b], "shifted_f0": shifted_f0[a:b].to(query_f0s[u].device),
+        r = {"out_feats": out_feats[a:b],
+             "shifted_f0": shifted_host[a:b] if shifted_host is not None else shifted_f0[a:b].to(query_f0s[u].device),
              "wavlm_indices": idx_w[a:b], "nearest_nbrs": nearest_nbrs[a:b], "harm_indices": idx_h[a:b]}
         if harm is not None:
             r["harmonics"] = harm[a:b]
