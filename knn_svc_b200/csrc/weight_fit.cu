@@ -29,6 +29,7 @@ __host__ __device__ constexpr int wf_b(int i, int j) { return 10 + i * 4 + j; } 
 __host__ __device__ constexpr int wf_c(int i, int j) { return 26 + (i <= j ? wf_tri(i, j) : wf_tri(j, i)); }
 constexpr int WF_THREADS = 512;
 constexpr int WF_SMEM_FRAMES = 10240;  // frames whose weights fit in shared memory
+constexpr int WF_STATE_FRAMES = 1900;  // frames whose weights AND optimiser state (7 x 16 B per frame) fit
 
 // ---- Gram build: one WARP per frame pair t (frames t, t+1).  For each of the two blocks the lane
 // loads its columns of all 8 rows ONCE (8 loads) and forms the 36 unique products of the
@@ -144,7 +145,7 @@ template <bool AMP>
 __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double* __restrict__ gram_all,
                                                                    const int64_t* __restrict__ utt_offsets,
                                                                    int64_t n_pairs_total, int dim, double loss_scale,
-                                                                   int max_iters, WfState st_all, int smem_frames,
+                                                                   int max_iters, WfState st_all, int smem_floats,
                                                                    const float* __restrict__ amp_all,
                                                                    float* __restrict__ out_weights_all,
                                                                    double* __restrict__ info_all) {
@@ -166,17 +167,22 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
     if (tid == 0 && info) info[0] = info[1] = info[2] = info[3] = 0.0;
     return;
   }
+  // Storage by utterance length (the arithmetic is the same in all three cases, so results do not
+  // depend on it): weights + the whole optimiser state in shared memory (every phase then runs at
+  // shared-memory latency instead of L2 round trips), weights only, or everything in global memory.
+  const int64_t T4 = T * 4;
+  const bool state_smem = 7 * T4 <= (int64_t)smem_floats;
+  const bool use_smem = state_smem || T4 <= (int64_t)smem_floats;
   WfState st;
-  st.theta = st_all.theta + f_begin * 4;
-  st.m = st_all.m + f_begin * 4;
-  st.v = st_all.v + f_begin * 4;
-  st.vmax = st_all.vmax + f_begin * 4;
-  st.best = st_all.best + f_begin * 4;
-  st.grad = st_all.grad + f_begin * 4;
+  st.theta = state_smem ? s_w_dyn + 1 * T4 : st_all.theta + f_begin * 4;
+  st.m = state_smem ? s_w_dyn + 2 * T4 : st_all.m + f_begin * 4;
+  st.v = state_smem ? s_w_dyn + 3 * T4 : st_all.v + f_begin * 4;
+  st.vmax = state_smem ? s_w_dyn + 4 * T4 : st_all.vmax + f_begin * 4;
+  st.best = state_smem ? s_w_dyn + 5 * T4 : st_all.best + f_begin * 4;
+  st.grad = state_smem ? s_w_dyn + 6 * T4 : st_all.grad + f_begin * 4;
   st.wglob = st_all.wglob + f_begin * 4;
   const double* gram = gram_all + f_begin;   // entry e of pair (t, t+1): gram[e * n_pairs_total + t]
   const float* amp = AMP ? amp_all + f_begin * 4 : nullptr;
-  const int use_smem = T <= smem_frames;
   volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
   const double norm = loss_scale / ((double)(T - 1) * (double)dim);
   const float lr = 0.1f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
@@ -348,12 +354,8 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   if (n_utt == 0) return 0;
   const int64_t n_query = utt_offsets_host[n_utt];
   KNN_CHECK_ARG(utt_offsets_host[0] == 0, -1, "weight_fit: utterance offsets must start at 0");
-  int64_t longest = 0;
-  for (int u = 0; u < n_utt; ++u) {
-    const int64_t len = utt_offsets_host[u + 1] - utt_offsets_host[u];
-    KNN_CHECK_ARG(len >= 0, -1, "weight_fit: utterance offsets must be non-decreasing");
-    longest = len > longest ? len : longest;
-  }
+  for (int u = 0; u < n_utt; ++u)
+    KNN_CHECK_ARG(utt_offsets_host[u + 1] >= utt_offsets_host[u], -1, "weight_fit: utterance offsets must be non-decreasing");
   if (n_query == 0) return 0;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   double* gram = reinterpret_cast<double*>(ws);
@@ -378,23 +380,28 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
                                                                                                  dim, n_query, gram);
     KNN_LAUNCH_CHECK();
   }
-  const int smem_frames = longest <= WF_SMEM_FRAMES ? (int)longest : 0;   // all utterances or none use smem weights
-  const size_t smem = smem_frames ? (size_t)smem_frames * 4 * sizeof(float) : 16;
+  // shared memory of the launch: the largest need over its utterances (each CTA picks its own mode)
+  int64_t smem_floats = 4;
+  for (int u = 0; u < n_utt; ++u) {
+    const int64_t len = utt_offsets_host[u + 1] - utt_offsets_host[u];
+    const int64_t need = len <= WF_STATE_FRAMES ? 28 * len : (len <= WF_SMEM_FRAMES ? 4 * len : 0);
+    smem_floats = need > smem_floats ? need : smem_floats;
+  }
+  const size_t smem = (size_t)smem_floats * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  WF_SMEM_FRAMES * 4 * (int)sizeof(float)));
+    const int max_bytes = WF_STATE_FRAMES * 28 * (int)sizeof(float);   // 212.8 KB > 10240 * 16 B
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
     attr_done = true;
   }
   if (amp)
     weight_fit_kernel<true><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
-                                                                 dim, loss_scale, max_iters, st, smem_frames, amp,
+                                                                 dim, loss_scale, max_iters, st, (int)smem_floats, amp,
                                                                  out_weights, info);
   else
     weight_fit_kernel<false><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
-                                                                  dim, loss_scale, max_iters, st, smem_frames, nullptr,
+                                                                  dim, loss_scale, max_iters, st, (int)smem_floats, nullptr,
                                                                   out_weights, info);
   KNN_LAUNCH_CHECK();
   return 0;
