@@ -104,7 +104,10 @@ long long knnsvc_launch_count(void);
  * "bf16_operands" = 0|1 (bf16 instead of fp16 tensor-core operands; measurement only,
  * the error window is sized for fp16), "concat_staged" = 1|0 (shared-memory staged K5
  * kernel where the row shape allows it, or the general kernel only),
- * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes). */
+ * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes),
+ * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
+ * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static
+ * instead of dynamic unit scheduling). */
 int knnsvc_set_option(const char* name, int value);
 int knnsvc_filter_timing(int enable);
 int knnsvc_filter_timing_collect(float* ms_host, int max_n);

@@ -29,6 +29,10 @@ int opt_cta_group() {
   return g_opt_cta_group;
 }
 int opt_bf16() { return g_opt_bf16; }
+static int g_opt_filter_flags = 1;
+int opt_filter_flags() { return g_opt_filter_flags; }
+static int g_opt_block_tiles = 0;
+int opt_block_tiles() { return g_opt_block_tiles; }
 static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
 int opt_spin_ns() { return g_opt_spin_ns; }
 static int g_opt_epi_sleep_ns = 0;
@@ -160,7 +164,7 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   const bool timed = g_timing && g_ev_n < kTimingSlots;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                             w.seg_kth, w.seg_flag, mask_lo, mask_hi, q_err, p_err, stream);
+                             w.seg_kth, w.seg_flag, mask_lo, mask_hi, q_err, p_err, w.counters + 12, stream);
   if (rc) return rc;
   if (timed) {
     KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));
@@ -202,6 +206,16 @@ int knnsvc_set_option(const char* name, int value) {
   }
   if (strcmp(name, "concat_staged") == 0) {
     g_opt_concat_staged = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "filter_flags") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= 7, -1, "set_option: filter_flags out of range");
+    g_opt_filter_flags = value;
+    return 0;
+  }
+  if (strcmp(name, "block_tiles") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: block_tiles out of range");
+    g_opt_block_tiles = value;
     return 0;
   }
   if (strcmp(name, "bf16_operands") == 0) {

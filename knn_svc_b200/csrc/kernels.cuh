@@ -8,6 +8,8 @@ namespace knnsvc {
 // ---- tuning options (capi.cu): diagnostic switches, see knnsvc_set_option
 int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
+int opt_filter_flags();   // bit0: L2 prefetch of the next unit's query tile, bit2: static unit schedule (bit1 unused)
+int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
 int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
@@ -27,13 +29,13 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
 
 // ---- knn_filter_sm100.cu
 struct FilterPlan {
-  int ctas, n_qtiles, n_ptiles, n_seg, n_units, grid, cap;
+  int ctas, n_qtiles, n_ptiles, n_seg, n_blk, n_units, grid, cap;
 };
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
                       float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
-                      const float* q_err, const float* p_err, cudaStream_t stream);
+                      const float* q_err, const float* p_err, int* unit_counter, cudaStream_t stream);
 size_t filter_flag_count(const FilterPlan& pl);
 
 // ---- knn_select.cu

@@ -16,9 +16,17 @@
 //   warps 2-5 : epilogue, one thread per query row (TMEM lane), tcgen05.ld 32x32b
 //   Operands: TMA, SWIZZLE_128B, K-major.
 //
-// A work unit is (query tile, pool segment): the CTA keeps its 128 rows and walks
-// the segment's pool tiles, so each epilogue thread carries one row's running
-// threshold in a register across the whole segment.
+// A CHAIN is (query tile, pool segment): its 128 rows walk the segment's pool tiles with one
+// running threshold per row.  A chain is cut into BLOCKS of ~96 pool tiles (an L2-sized piece of
+// the fp16 pool) and a work unit is (chain, block).  Units are ordered block-major and CLAIMED
+// DYNAMICALLY from a global counter (the producer lane claims, a 4-deep shared-memory queue hands
+// the unit to the MMA lane and the epilogue warps): SMs differ by up to ~14% in sustained tensor
+// rate under the power cap, so with a static split the fast ones idled at the end and the CTAs
+// drifted GBs apart in the pool (it was re-read ~50x per launch); now a faster SM simply takes
+// more units and all CTAs stay on the same pool block.  Inside a unit each epilogue thread carries
+// its row's state in registers; between the blocks of a chain the state (top-k list, log count)
+// goes through global memory, ordered by a per-warp block counter (consecutive blocks of a chain
+// may run on different SMs, never concurrently).
 //
 // Filter rule (rigorous, DESIGN.md "exact top-k from an fp16 GEMM"): operands are
 // unit-normalised rows cast to fp16, so the accumulator is the cosine similarity
@@ -43,6 +51,7 @@ constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
+constexpr int kSchedDepth = 4;   // units the producer may run ahead of the slowest consumer warp
 
 template <int CTAS>
 struct Cfg {
@@ -58,7 +67,10 @@ struct Cfg {
   static constexpr int tmem_full_bar = empty_bar + STAGES * 8;          // [2]
   static constexpr int tmem_empty_bar = tmem_full_bar + 2 * 8;          // [2]
   static constexpr int tmem_ptr = tmem_empty_bar + 2 * 8;               // uint32
-  static constexpr int total = tmem_ptr + 16;
+  static constexpr int sched_full_bar = tmem_ptr + 16;                  // [kSchedDepth]  unit queue (dynamic scheduling)
+  static constexpr int sched_empty_bar = sched_full_bar + kSchedDepth * 8;
+  static constexpr int sched_unit = sched_empty_bar + kSchedDepth * 8;  // int [kSchedDepth]
+  static constexpr int total = sched_unit + kSchedDepth * 4;
   static constexpr int SMEM_BYTES = total + 1024;  // slack for manual 1024 B alignment
 };
 
@@ -143,6 +155,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
   }
+}
+// L2 prefetch of one TMA box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -256,8 +272,8 @@ __device__ __noinline__ RowState filter_log_full(RowState st, float v, int col, 
       int li[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        lv[u] = log_val[e0 + u];
-        li[u] = log_idx[e0 + u];
+        lv[u] = __ldcg(log_val + e0 + u);   // L2: an earlier block of the chain may have run on another SM
+        li[u] = __ldcg(log_idx + e0 + u);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -318,6 +334,24 @@ __device__ __forceinline__ RowState filter_insert(RowState st, float v, int col,
   return st;
 }
 
+// Work unit u -> (block, segment, query tile) and the unit's pool-tile range.  Block-major order:
+// all chains' block 0, then all chains' block 1, ...
+struct Unit {
+  int qt, seg, blk, t0, t1;
+};
+__device__ __forceinline__ Unit decode_unit(int u, int n_qtiles, int n_seg, int n_blk, int n_ptiles) {
+  const int n_chains = n_qtiles * n_seg;
+  Unit w;
+  w.blk = u / n_chains;
+  const int c = u - w.blk * n_chains;
+  w.seg = c / n_qtiles;
+  w.qt = c - w.seg * n_qtiles;
+  const int s0 = (int)((int64_t)w.seg * n_ptiles / n_seg), s1 = (int)((int64_t)(w.seg + 1) * n_ptiles / n_seg);
+  w.t0 = s0 + (int)((int64_t)(s1 - s0) * w.blk / n_blk);
+  w.t1 = s0 + (int)((int64_t)(s1 - s0) * (w.blk + 1) / n_blk);
+  return w;
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------- kernel
@@ -329,11 +363,11 @@ template <int CTAS, bool MASKED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
-                  int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
+                  int n_blk, int cap, float* __restrict__ log_val, int* __restrict__ log_idx, int* __restrict__ log_cnt,
                   float* __restrict__ seg_top, float* __restrict__ seg_kth, int* __restrict__ seg_flag,
                   uint32_t idesc, uint32_t spin_ns, const int64_t* __restrict__ mask_lo,
                   const int64_t* __restrict__ mask_hi, const float* __restrict__ q_err,
-                  const float* __restrict__ p_err) {
+                  const float* __restrict__ p_err, int* __restrict__ unit_counter, int prefetch) {
   using L = Cfg<CTAS>;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
@@ -341,11 +375,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_units = n_qtiles * n_seg;
+  const int n_units = n_qtiles * n_seg * n_blk;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
   const int worker = blockIdx.x / CTAS;        // index of this CTA (pair) among the persistent workers
   const int n_workers = gridDim.x / CTAS;
+  // dynamic unit scheduling (single-CTA shape): units are claimed from a global counter in index order
+  const bool dyn = CTAS == 1 && !(prefetch & 4);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -357,6 +393,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int b = 0; b < 2; ++b) {
       mbar_init(sbase + L::tmem_full_bar + b * 8, 1);
       mbar_init(sbase + L::tmem_empty_bar + b * 8, 4 * CTAS);  // one arrive per epilogue warp of the pair
+    }
+    for (int i = 0; i < kSchedDepth; ++i) {
+      mbar_init(sbase + L::sched_full_bar + i * 8, 1);
+      mbar_init(sbase + L::sched_empty_bar + i * 8, 5);   // the MMA lane + four epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -385,11 +425,54 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = worker; u < n_units; u += n_workers) {
-        const int seg = u / n_qtiles, qt = u % n_qtiles;
-        const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
-        const int q_row = (qt * CTAS + (int)cta_rank) * BM;
-        for (int pt = t0; pt < t1; ++pt) {
+      int it = 0, sq = 0;
+      uint32_t sq_phase = 0;
+      // next unit of this worker: claimed from the global counter (dynamic: a faster SM simply takes
+      // more units and all CTAs stay on the same pool block) or the static stride
+      auto claim = [&]() -> int {
+        int u;
+        if (dyn) u = atomicAdd(unit_counter, 1);
+        else u = worker + (it++) * n_workers;
+        return u < n_units ? u : -1;
+      };
+      int u_next = claim();
+      for (;;) {
+        const int u = u_next;
+        if (dyn) {   // hand the unit to the MMA lane and the epilogue warps (-1 = no more work)
+          mbar_wait(sbase + L::sched_empty_bar + sq * 8, sq_phase ^ 1);
+          *reinterpret_cast<volatile int*>(smem + L::sched_unit + sq * 4) = u;
+          mbar_arrive(sbase + L::sched_full_bar + sq * 8);
+          if (++sq == kSchedDepth) {
+            sq = 0;
+            sq_phase ^= 1;
+          }
+        }
+        if (u < 0) break;
+        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
+        const int q_row = (un.qt * CTAS + (int)cta_rank) * BM;
+        const int n_t = un.t1 - un.t0;
+        // The next unit is claimed four tiles before this one ends (not at its start: CTAs that
+        // launch first would grab second units before the last CTAs have taken their first), and
+        // its query tile is prefetched into L2 over those tiles, a few k-slab boxes per tile —
+        // otherwise every unit would start with 16 dependent DRAM round trips.
+        const int a_span = n_t < 4 ? n_t : 4, a_first = n_t - a_span;
+        int nq_row = -1;
+        bool claimed = false;
+        for (int pt = un.t0; pt < un.t1; ++pt) {
+          const int ti = pt - un.t0;
+          if (ti == a_first) {
+            u_next = claim();
+            claimed = true;
+            if ((prefetch & 1) && u_next >= 0) {
+              const Unit nx = decode_unit(u_next, n_qtiles, n_seg, n_blk, n_ptiles);
+              if (nx.qt != un.qt) nq_row = (nx.qt * CTAS + (int)cta_rank) * BM;
+            }
+          }
+          if (nq_row >= 0) {
+            const int j = ti - a_first;
+            for (int kb = j * k_blocks / a_span; kb < (j + 1) * k_blocks / a_span; ++kb)
+              tma_prefetch_2d(&map_q, kb * BK, nq_row);
+          }
           const int p_row = pt * BN + (int)cta_rank * L::B_ROWS;
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait_backoff(sbase + L::empty_bar + stage * 8, phase ^ 1, spin_ns & 0xffffu);
@@ -410,6 +493,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
           }
         }
+        if (!claimed) u_next = claim();   // empty unit
       }
     }
   } else if (warp == 1) {
@@ -418,10 +502,25 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_n = 0;
-      for (int u = worker; u < n_units; u += n_workers) {
-        const int seg = u / n_qtiles;
-        const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
-        for (int pt = t0; pt < t1; ++pt, ++tile_n) {
+      int it = 0, sq = 0;
+      uint32_t sq_phase = 0;
+      for (;;) {
+        int u;
+        if (dyn) {
+          mbar_wait(sbase + L::sched_full_bar + sq * 8, sq_phase);
+          u = *reinterpret_cast<volatile int*>(smem + L::sched_unit + sq * 4);
+          mbar_arrive(sbase + L::sched_empty_bar + sq * 8);
+          if (++sq == kSchedDepth) {
+            sq = 0;
+            sq_phase ^= 1;
+          }
+        } else {
+          u = worker + (it++) * n_workers;
+          if (u >= n_units) u = -1;
+        }
+        if (u < 0) break;
+        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
+        for (int pt = un.t0; pt < un.t1; ++pt, ++tile_n) {
           const uint32_t buf = tile_n & 1;
           const uint32_t buf_phase = (tile_n >> 1) & 1;
           mbar_wait_backoff(sbase + L::tmem_empty_bar + buf * 8, buf_phase ^ 1, spin_ns & 0xffffu);
@@ -455,22 +554,63 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     int* keys_row = reinterpret_cast<int*>(smem + L::topv) + row_in_tile;   // [kSlots][BM] packed keys
     const float window_scaled = 2.0f * filter_eps(q_err, p_err) * kDotScale;
     uint32_t tile_n = 0;
-    for (int u = worker; u < n_units; u += n_workers) {
-      const int seg = u / n_qtiles, qt = u % n_qtiles;
-      const int t0 = (int)((int64_t)seg * n_ptiles / n_seg), t1 = (int)((int64_t)(seg + 1) * n_ptiles / n_seg);
+    int it = 0, sq = 0;
+    uint32_t sq_phase = 0;
+    for (;;) {
+      int u;
+      if (dyn) {
+        mbar_wait(sbase + L::sched_full_bar + sq * 8, sq_phase);
+        u = *reinterpret_cast<volatile int*>(smem + L::sched_unit + sq * 4);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + L::sched_empty_bar + sq * 8);
+        if (++sq == kSchedDepth) {
+          sq = 0;
+          sq_phase ^= 1;
+        }
+      } else {
+        u = worker + (it++) * n_workers;
+        if (u >= n_units) u = -1;
+      }
+      if (u < 0) break;
+      const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
+      const int seg = un.seg, qt = un.qt, t0 = un.t0, t1 = un.t1;
       const int64_t row = (int64_t)(qt * CTAS + (int)cta_rank) * BM + row_in_tile;
       const bool row_ok = row < n_query;
-      for (int j = 0; j < kSlots; ++j) keys_row[j * BM] = j < k ? pack_key(kEmpty, j) : INT_MAX;
-      RowState st;
-      st.kth = kEmpty;
-      st.kpos = 0;
-      st.cnt = 0;
-      // Warm start: any finished segment's k-th best similarity is a lower bound of the row's
-      // global k-th best, so nothing more than 2*eps below it can be a true neighbour.  Units are
-      // ordered segment-major, so by the time segment s of a row tile starts, its earlier segments
-      // have usually been published (flag written after the values, both fenced).
-      float known = kEmpty;
       const int flag_base = ((qt * CTAS + (int)cta_rank) * 4 + quad) * n_seg;
+      const int64_t slot = row * n_seg + seg;
+      RowState st;
+      if (un.blk > 0) {
+        // The chain's earlier blocks ran as earlier units, possibly on another SM.  Wait until the
+        // last of them has published (this warp's counter of finished blocks; in steady state it
+        // has, long ago), then pick the rows' state up from global memory.  The wait always ends:
+        // a unit only waits for a LOWER unit index, units are claimed in index order by CTAs that
+        // are already running, and the lowest unfinished unit therefore never waits.
+        if (lane == 0) {
+          while (*reinterpret_cast<volatile int*>(seg_flag + flag_base + seg) < un.blk) __nanosleep(200);
+        }
+        __syncwarp();
+        __threadfence();
+      }
+      if (un.blk > 0 && row_ok) {
+        int kmin = INT_MAX;
+        for (int j = 0; j < kSlots; ++j) {
+          const int key = j < k ? pack_key(__ldcg(seg_top + slot * k + j) * kDotScale, j) : INT_MAX;
+          keys_row[j * BM] = key;
+          kmin = min(kmin, key);
+        }
+        st.kth = key_value(kmin);
+        st.kpos = kmin & 31;
+        st.cnt = __ldcg(log_cnt + slot);
+      } else {
+        for (int j = 0; j < kSlots; ++j) keys_row[j * BM] = j < k ? pack_key(kEmpty, j) : INT_MAX;
+        st.kth = kEmpty;
+        st.kpos = 0;
+        st.cnt = 0;
+      }
+      // Warm start: the k-th best similarity any OTHER segment of this row has published is a lower
+      // bound of the row's global k-th best, so nothing more than 2*eps below it can be a true
+      // neighbour (counter written after the values, both fenced).
+      float known = kEmpty;
       if (row_ok) {
         for (int s2 = 0; s2 < n_seg; ++s2) {
           if (s2 == seg) continue;
@@ -480,8 +620,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
         }
       }
-      st.tau_lo = row_ok ? known * kDotScale - window_scaled : INFINITY;
-      const float warm_lo = st.tau_lo;
+      const float warm_lo = row_ok ? known * kDotScale - window_scaled : INFINITY;
+      st.tau_lo = fmaxf(warm_lo, st.kth - window_scaled);
       int m_lo = 0, m_hi = 0;   // masked column range of this row (empty unless MASKED)
       if constexpr (MASKED) {
         if (row_ok) {
@@ -489,7 +629,6 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           m_hi = (int)mask_hi[row];
         }
       }
-      const int64_t slot = row * n_seg + seg;
       float* lv = log_val + (row_ok ? slot * cap : 0);
       int* li = log_idx + (row_ok ? slot * cap : 0);
       for (int pt = t0; pt < t1; ++pt, ++tile_n) {
@@ -550,7 +689,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       __threadfence();
       __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(seg_flag + flag_base + seg) = 1;
+      if (lane == 0) *reinterpret_cast<volatile int*>(seg_flag + flag_base + seg) = un.blk + 1;
     }
   }
 
@@ -623,22 +762,41 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   pl.n_qtiles = (int)ceil_div64(n_query, BM * pl.ctas);
   pl.n_ptiles = (int)ceil_div64(n_pool, BN);
   const int workers = num_sms() / pl.ctas;
-  // choose the number of pool segments: minimise waves*tiles_per_unit, with a
-  // small penalty per segment (each one restarts the running threshold -> more log traffic)
-  int best_s = 1;
+  // Blocks of <= blk pool tiles (default 96 tiles = 24576 rows = 48 MB of fp16 operand at 1024 dims).
+  // Measured on B200 (tools/block_ab.py, 100k x 2M..10M): speed is flat from 64 tiles up; DRAM
+  // traffic per launch has a shallow minimum around 96-192 tiles (larger blocks: fewer query-tile
+  // re-reads, but the block itself stops surviving in L2 between rounds).
+  const int blk = opt_block_tiles() > 0 ? opt_block_tiles() : 96;
+  // Number of pool segments (independent chains per query tile): only needed to find work for all
+  // CTAs when there are few query tiles.  Cost model: units run `par` at a time (the blocks of a
+  // chain are serial, so no more than one unit per chain at once); every segment restarts the
+  // running threshold (more log traffic), hence the small per-segment penalty.
+  int best_s = 1, best_nb = 1;
   double best_cost = 1e300;
   const int max_s = pl.n_ptiles < 16 ? pl.n_ptiles : 16;
   for (int s = 1; s <= max_s; ++s) {
-    double waves = (double)ceil_div64((int64_t)pl.n_qtiles * s, workers);
-    double tiles = (double)ceil_div64(pl.n_ptiles, s) + 1.0;  // +1: pipeline fill per unit
-    double cost = waves * tiles * (1.0 + 0.004 * s);
+    const int64_t seg_tiles = ceil_div64(pl.n_ptiles, s);
+    const int64_t nb = ceil_div64(seg_tiles, blk);
+    const int64_t chains = (int64_t)pl.n_qtiles * s;
+    const int64_t par = chains < workers ? chains : workers;
+    const int64_t units = chains * nb;
+    const double tiles = (double)ceil_div64(seg_tiles, nb) + 0.25;  // + state hand-over per unit
+    // dynamic claiming (single-CTA shape): no whole-wave quantisation, about half a unit of tail
+    double rounds = pl.ctas == 1 ? (units > par ? (double)units / (double)par + 0.5 : 1.0)
+                                 : (double)ceil_div64(units, par);
+    double cost = rounds * tiles * (1.0 + 0.004 * s);
+    // with fewer than two chains per CTA the next block of a chain is usually claimed before its
+    // predecessor has finished, and the round proceeds at the pace of the slowest SM
+    if (nb > 1 && chains < 2 * (int64_t)workers) cost *= 1.10;
     if (cost < best_cost) {
       best_cost = cost;
       best_s = s;
+      best_nb = (int)nb;
     }
   }
   pl.n_seg = best_s;
-  pl.n_units = pl.n_qtiles * pl.n_seg;
+  pl.n_blk = best_nb;
+  pl.n_units = pl.n_qtiles * pl.n_seg * pl.n_blk;
   pl.grid = (pl.n_units < workers ? pl.n_units : workers) * pl.ctas;
   pl.cap = 64 * k < 256 ? 256 : 64 * k;
   return pl;
@@ -650,7 +808,8 @@ template <int CTAS, bool MASKED>
 static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
                           int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
                           float* seg_top, float* seg_kth, int* seg_flag, const int64_t* mask_lo,
-                          const int64_t* mask_hi, const float* q_err, const float* p_err, cudaStream_t stream) {
+                          const int64_t* mask_hi, const float* q_err, const float* p_err, int* unit_counter,
+                          cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -673,16 +832,18 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
   // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
   const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS, MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
-                              pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
-                              seg_flag, idesc, (uint32_t)opt_spin_ns() | ((uint32_t)opt_epi_sleep_ns() << 16), mask_lo, mask_hi, q_err, p_err));
+                              pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.n_blk, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
+                              seg_flag, idesc, (uint32_t)opt_spin_ns() | ((uint32_t)opt_epi_sleep_ns() << 16), mask_lo, mask_hi, q_err, p_err,
+                              unit_counter, opt_filter_flags()));
   return 0;
 }
 
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
                       float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
-                      const float* q_err, const float* p_err, cudaStream_t stream) {
+                      const float* q_err, const float* p_err, int* unit_counter, cudaStream_t stream) {
   KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -3, "mask_lo and mask_hi must be given together");
+  KNN_CHECK_ARG(unit_counter != nullptr, -3, "unit counter missing");
   KNN_CHECK_ARG(dim_pad % BK == 0 && dim_pad > 0, -3, "dim_pad %d must be a positive multiple of %d", dim_pad, BK);
   KNN_CHECK_ARG(k >= 1 && k <= kMaxK, -3, "k=%d outside [1,%d]", k, kMaxK);
   KNN_CHECK_ARG(n_pool < (int64_t)1 << 31, -3, "pool shard of %lld rows exceeds int32 column indices", (long long)n_pool);
@@ -693,7 +854,7 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   if (rc) return rc;
 #define KNN_FILTER_GO(C, M)                                                                                   \
   return launch_variant<C, M>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top, \
-                              seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, stream)
+                              seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, unit_counter, stream)
   if (pl.ctas == 2) {
     if (mask_lo) KNN_FILTER_GO(2, true);
     KNN_FILTER_GO(2, false);
