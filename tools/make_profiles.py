@@ -55,10 +55,11 @@ def launch_list(tag):
                        "launches_measured": len(t), "kernel_ms_under_ncu": [x / 1e6 for x in t],
                        "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on `python "
                                  "bench.py --steps 2 --warmup 1 --no-cpu-baseline` (profiles/r1_launches_bench_100kx10M.txt)",
-                       "note": "the fp16 pool operand is 20.5 GB; 3-5% of the 23.5 TB of TMA operand loads per launch miss "
-                               "the 126 MB L2 (the 148 CTAs of a wave drift apart while streaming a 1.25 GB pool segment), so "
-                               "it is re-read from DRAM ~35-55x per launch = 0.45-0.7 TB/s, <= 10% of HBM peak; launch-to-"
-                               "launch spread 0.75-1.2 TB"}
+                       "note": "fp16 operands: pool 20.5 GB + queries 0.2 GB.  Blocked traversal (96-tile = 48 MB pool blocks, "
+                               "dynamic unit claiming): every (query tile, block) unit re-reads its 256 KB query tile "
+                               "(782 x 407 units = 83 GB) and a pool block is re-read about once per round of 148 units "
+                               "(5.3 rounds x 20.5 GB = 108 GB): ~0.23 TB per launch = 0.14 TB/s, 2% of HBM peak.  Before "
+                               "(static split, GB-sized segments) the CTAs drifted apart and a launch moved 0.75-1.2 TB."}
     (PROF / "r1_launches_bench_100kx10M.txt").write_text("\n".join(lines) + "\n")
     shutil.copy(OUT / f"{tag}_launches_bench_full.csv", PROF / "r1_launches_bench_100kx10M.csv")
     if traffic:
@@ -66,6 +67,8 @@ def launch_list(tag):
 
 
 def small_kernels(tag):
+    if not (OUT / f"{tag}_small_kernels.csv").exists():
+        return
     rows = list(csv.reader(open(OUT / f"{tag}_small_kernels.csv")))
     hdr, recs = None, collections.OrderedDict()
     for r in rows:
@@ -99,7 +102,8 @@ def small_kernels(tag):
 def main():
     tag = sys.argv[1]
     PROF.mkdir(exist_ok=True)
-    launch_list(tag)
+    if (OUT / f"{tag}_launches_bench_full.csv").exists():
+        launch_list(tag)
     small_kernels(tag)
     for rep, dst in ((f"{tag}_filter_full.ncu-rep", "r1_filter_ncu_full_32768x2M.txt"),
                      (f"{tag}_rescore_full.ncu-rep", "r1_rescore_ncu_full.txt")):
