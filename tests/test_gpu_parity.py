@@ -497,3 +497,75 @@ def test_knn_search_row_chunking_changes_nothing(ops, monkeypatch):
     d1, i1, s1 = ops.knn_search(qp, pp, 32, index_offset=7, return_stats=True, mask_lo=dev(lo), mask_hi=dev(hi))
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
     assert s0[0].item() == s1[0].item() and s0[2].item() == s1[2].item()    # flagged rows, survivors (plan-independent)
+
+
+@pytest.fixture
+def filter_options():
+    """set filter traversal options for one test and restore the defaults afterwards"""
+    from knn_svc_b200 import _lib
+    lib = _lib.load()
+
+    def set_(block_tiles=0, flags=1, cta_group=1):
+        _lib.check(lib.knnsvc_set_option(b"block_tiles", block_tiles), "set_option")
+        _lib.check(lib.knnsvc_set_option(b"filter_flags", flags), "set_option")
+        _lib.check(lib.knnsvc_set_option(b"cta_group", cta_group), "set_option")
+    yield set_
+    set_()
+
+
+@pytest.mark.parametrize("block_tiles,flags,cta_group", [(1, 1, 1), (2, 1, 1), (3, 0, 1), (1, 5, 1), (2, 5, 2), (1, 1, 2)])
+def test_knn_search_block_traversal_changes_nothing(ops, filter_options, block_tiles, flags, cta_group):
+    """The filter walks the pool in L2-sized blocks, handing each row's state (top-k list, candidate
+    log) from block to block through global memory, with units claimed dynamically or split statically,
+    by one CTA or a CTA pair.  Tiny blocks (256-768 pool rows) force several hand-overs per chain on sets
+    with dense neighbourhoods, exact ties, masked ranges and overflowing logs: results must be
+    bit-identical to the default traversal (whose parity with the oracle the tests above establish)."""
+    q, p = synth.ar1_frames(700, seed=81, reset_every=250), synth.ar1_frames(20000, seed=82)
+    p[1000:1040] = p[17]                     # exact ties spanning several blocks' worth of duplicates
+    p[3000:3700] = p[23]                     # more candidates inside the window than the log holds -> exact fallback
+    q[5] = p[17]; q[6] = p[23]
+    qp, pp = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p))
+    lo = dev(np.repeat(np.arange(0, 700, 100) * 8, 100).astype(np.int64)); hi = lo + 300
+    ref = {}
+    for k in (4, 32):
+        ref[k] = ops.knn_search(qp, pp, k, return_stats=True)
+        ref[k, "m"] = ops.knn_search(qp, pp, k, mask_lo=lo, mask_hi=hi)
+    o_idx, o_val = orc.knn(q, p, 5)
+    rows = set_rows(o_val, 4)
+    assert np.array_equal(np.sort(ref[4][1].cpu().numpy()[rows], 1), np.sort(o_idx[rows, :4], 1))
+    filter_options(block_tiles, flags, cta_group)
+    for k in (4, 32):
+        d, i, st = ops.knn_search(qp, pp, k, return_stats=True)
+        assert torch.equal(i, ref[k][1]) and torch.equal(d, ref[k][0])
+        n_qtiles = -(-700 // (128 * cta_group))
+        assert int(st[4]) > n_qtiles * int(st[3]), "expected chains of several blocks"
+        dm, im = ops.knn_search(qp, pp, k, mask_lo=lo, mask_hi=hi)
+        assert torch.equal(im, ref[k, "m"][1]) and torch.equal(dm, ref[k, "m"][0])
+
+
+def test_knn_search_cfg4_shard_size_properties(ops):
+    """One 8-GPU shard of BASELINE cfg 4 (1.25 M pool frames; 20k of the 100k query frames): 51 blocks per
+    chain.  Too big for any oracle, so: sortedness, index range, returned distances are the true fp64
+    distances of the returned indices, the result equals the merge of two half-shard searches, and a
+    sample of rows is checked against a brute-force fp64 top-k."""
+    g = torch.Generator(device=DEV); g.manual_seed(4)
+    T, NP, k = 20000, 1_250_000, 4
+    q = torch.randn((T, 1024), device=DEV, generator=g)
+    p = torch.randn((NP, 1024), device=DEV, generator=g)
+    qp, pp = ops.prepare_rows(q), ops.prepare_rows(p)
+    dist, idx, stats = ops.knn_search(qp, pp, k, return_stats=True)
+    assert int(stats[0]) == 0 and int(stats[4]) >= 157 * 51
+    assert torch.all(dist[:, 1:] >= dist[:, :-1]) and idx.min() >= 0 and idx.max() < NP
+    rows = torch.arange(0, T, 313, device=DEV)
+    pn, qn = p.double().norm(dim=1), q[rows].double().norm(dim=1)
+    true_d = torch.empty((len(rows), NP), dtype=torch.float64, device=DEV)
+    for a in range(0, NP, 250_000):
+        true_d[:, a:a + 250_000] = 1 - (q[rows].double() @ p[a:a + 250_000].double().T) / (qn[:, None] * pn[None, a:a + 250_000])
+    assert torch.allclose(torch.gather(true_d, 1, idx[rows]).float(), dist[rows], atol=1e-6, rtol=0)
+    t_val, t_idx = true_d.topk(k + 1, largest=False)
+    check_knn_against_oracle(idx[rows].cpu().numpy(), dist[rows].cpu().numpy(), t_idx.cpu().numpy(), t_val.cpu().numpy(), k)
+    del true_d
+    half = NP // 2
+    parts = [ops.knn_search(qp, ops.prepare_rows(p[:half]), k), ops.knn_search(qp, ops.prepare_rows(p[half:]), k, index_offset=half)]
+    d_m, i_m = ops.merge_topk(torch.stack([d for d, _ in parts]), torch.stack([i for _, i in parts]))
+    assert torch.equal(i_m, idx) and torch.equal(d_m, dist)
