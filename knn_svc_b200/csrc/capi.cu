@@ -32,6 +32,8 @@ int opt_cta_group() {
 int opt_bf16() { return g_opt_bf16; }
 static int g_opt_filter_flags = 1;
 int opt_filter_flags() { return g_opt_filter_flags; }
+static int g_opt_wf_cluster = 1;
+int opt_weight_fit_cluster() { return g_opt_wf_cluster; }
 static int g_opt_block_tiles = 0;
 int opt_block_tiles() { return g_opt_block_tiles; }
 static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
@@ -236,6 +238,10 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "filter_flags") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 7, -1, "set_option: filter_flags out of range");
     g_opt_filter_flags = value;
+    return 0;
+  }
+  if (strcmp(name, "weight_fit_cluster") == 0) {
+    g_opt_wf_cluster = value != 0;
     return 0;
   }
   if (strcmp(name, "block_tiles") == 0) {

@@ -9,6 +9,7 @@ namespace knnsvc {
 int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
 int opt_filter_flags();   // bit0: L2 prefetch of the next unit's query tile, bit2: static unit schedule (bit1 unused)
+int opt_weight_fit_cluster();   // 1 (default): few long utterances are fitted by a cluster of 8 CTAs each
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier

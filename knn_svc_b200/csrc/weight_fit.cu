@@ -12,12 +12,16 @@
 // fp32 and the update is torch.optim.Adam(amsgrad=True)'s single-tensor form;
 // the loss and dL/dw are fp64 and cast to fp32 at w, as on the reference's real
 // (float64) path.  Stop rules: ddsp_prematch_dataset.py:644-663.
+#include <cooperative_groups.h>
+#include <limits.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace knnsvc {
 
 constexpr int WF_K = 4;
+constexpr int kWcMaxSmem = 220 * 1024;   // dynamic shared memory the cluster kernel may ask for
 constexpr int WF_V = 2 * WF_K;         // vectors per Gram block
 // The 8x8 Gram block [[A, B], [B', C]] is symmetric: 10 + 16 + 10 = 36 unique entries, stored
 // ENTRY-MAJOR (gram[e * n_pairs + t]) so that consecutive threads (frames) read consecutive
@@ -124,6 +128,7 @@ struct WfState {
   float* best;
   float* grad;   // dL/dw scratch
   float* wglob;  // [T,4] softmax weights when they do not fit in shared memory
+  double* chunk; // [T/32 + n_utt] loss sums of 32-frame chunks when they do not fit in shared memory
 };
 
 __device__ __forceinline__ void softmax4(const float* th, float* w) {
@@ -137,6 +142,99 @@ __device__ __forceinline__ void softmax4(const float* th, float* w) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = e[k] / s;
 }
+
+// ---- pieces shared by the one-CTA and the cluster kernel, so that both run the same arithmetic
+// in the same order (an utterance's result must not depend on which of the two fitted it).
+
+// Frame t's share e_t of the quadratic form and dL/d(a.w) of its four weights.  wt / wp / wn are the
+// (amp-scaled) weights of frames t, t-1, t+1 in fp64; gp(e) / gc(e) return entry e of the Gram
+// blocks of pairs (t-1, t) and (t, t+1).
+template <class GramPrev, class GramCur>
+__device__ __forceinline__ double wf_frame(bool has_prev, bool has_next, const double (&wt)[4], const double (&wp)[4],
+                                           const double (&wn)[4], GramPrev gp, GramCur gc, double (&g)[4]) {
+  double e_t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) g[k] = 0.0;
+  if (has_prev) {  // pair t-1: this frame is the "t+1" member -> rows 0..3 of G u = A w[t] - B w[t-1]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double y = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y += gp(wf_a(r, c)) * wt[c] - gp(wf_b(r, c)) * wp[c];
+      e_t += wt[r] * y;
+      g[r] += y;
+    }
+  }
+  if (has_next) {  // pair t: this frame is the "t" member -> rows 4..7 of G u = B' w[t+1] - C w[t]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double y = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y += gc(wf_b(c, r)) * wn[c] - gc(wf_c(r, c)) * wt[c];
+      e_t -= wt[r] * y;
+      g[r] -= y;
+    }
+  }
+  return e_t;
+}
+
+// torch.optim.Adam(amsgrad=True), single-tensor form, on the four logits of one frame
+__device__ __forceinline__ void wf_adam4(float* theta, float* m_, float* v_, float* vmax_, const float (&w)[4],
+                                         const float (&gw)[4], float step_size, float bc2_sqrt) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  float dotgw = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dotgw += gw[k] * w[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float gth = w[k] * (gw[k] - dotgw);  // softmax backward
+    float m = m_[k], v = v_[k], vm = vmax_[k];
+    m = m + (gth - m) * (1.0f - b1);
+    v = v * b2 + (1.0f - b2) * gth * gth;
+    vm = fmaxf(vm, v);
+    const float denom = sqrtf(vm) / bc2_sqrt + eps;
+    theta[k] = theta[k] - step_size * (m / denom);
+    m_[k] = m;
+    v_[k] = v;
+    vmax_[k] = vm;
+  }
+}
+
+// The reference's stop rules (ddsp_prematch_dataset.py:644-663) and Adam's bias corrections, run by
+// one thread per CTA.  update() returns bit0: stop, bit1: snapshot the logits.
+struct WfControl {
+  double min_loss = 20000.0, converge_min_loss = 20000.0, first_loss = 0.0, last_loss = 0.0;
+  int since_improve = 0, stop_iter;
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  __device__ explicit WfControl(int max_iters) : stop_iter(max_iters) {}
+  __device__ int update(double loss, int it) {
+    if (it == 0) first_loss = loss;
+    last_loss = loss;
+    int ctl = 0;
+    if (it % 100 == 1) {
+      if (fabs(min_loss - converge_min_loss) < 1e-5) ctl |= 1;
+      else converge_min_loss = min_loss;
+    }
+    if (!(ctl & 1)) {
+      if (loss < min_loss) {
+        min_loss = loss;
+        ctl |= 2;
+        since_improve = 0;
+      } else {
+        ++since_improve;
+      }
+      if (since_improve >= 1000) ctl |= 1;
+    }
+    if (ctl & 1) stop_iter = it;
+    const int step = it + 1;
+    step_size = (float)((double)0.1 / (1.0 - pow((double)0.9, (double)step)));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)0.999, (double)step));
+    return ctl;
+  }
+};
+
+// The loss is reduced in ONE order everywhere: e_t summed over chunks of 32 consecutive frames by a
+// warp shuffle tree (frames past the end count as 0), then the chunk sums added in index order.
 
 // AMP: every candidate row is scaled by amp[t,k] before mixing (compute_weight_with_amp,
 // ddsp_prematch_dataset.py:684-803: `synth_set[...] * amp_ratio[:, :, None]` for all three
@@ -152,8 +250,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
   // one CTA per utterance: frames [f_begin, f_end) of the concatenated batch; every array is
   // indexed by the global frame number, so the CTA just offsets its bases
   extern __shared__ __align__(16) float s_w_dyn[];
-  __shared__ double s_red[WF_THREADS / 32];
-  __shared__ double s_loss;
+  __shared__ double s_chunk[WF_SMEM_FRAMES / 32];
   __shared__ int s_ctl;  // bit0: stop, bit1: snapshot
   __shared__ float s_step_size, s_bc2_sqrt;
   const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
@@ -181,11 +278,12 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
   st.best = state_smem ? s_w_dyn + 5 * T4 : st_all.best + f_begin * 4;
   st.grad = state_smem ? s_w_dyn + 6 * T4 : st_all.grad + f_begin * 4;
   st.wglob = st_all.wglob + f_begin * 4;
+  const int64_t n_chunks = (T + 31) / 32;
+  volatile double* chunk = n_chunks <= WF_SMEM_FRAMES / 32 ? s_chunk : st_all.chunk + f_begin / 32 + blockIdx.x;
   const double* gram = gram_all + f_begin;   // entry e of pair (t, t+1): gram[e * n_pairs_total + t]
   const float* amp = AMP ? amp_all + f_begin * 4 : nullptr;
   volatile float* wbuf = use_smem ? s_w_dyn : st.wglob;
   const double norm = loss_scale / ((double)(T - 1) * (double)dim);
-  const float lr = 0.1f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
 
   for (int64_t t = tid; t < T; t += WF_THREADS)
 #pragma unroll
@@ -196,8 +294,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       st.vmax[t * 4 + k] = 0.f;
       st.best[t * 4 + k] = 0.f;
     }
-  double min_loss = 20000.0, converge_min_loss = 20000.0, first_loss = 0.0;
-  int since_improve = 0, stop_iter = max_iters;
+  WfControl ctrl(max_iters);
   __syncthreads();
 
   for (int it = 0; it < max_iters; ++it) {
@@ -211,78 +308,43 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       for (int k = 0; k < 4; ++k) wbuf[t * 4 + k] = w[k];
     }
     __syncthreads();
-    // ---- loss and dL/dw from the Gram blocks
+    // ---- loss and dL/dw from the Gram blocks (a warp holds 32 consecutive frames: one chunk)
     const int64_t NP = n_pairs_total;
-    double part = 0.0;
-    for (int64_t t = tid; t < T; t += WF_THREADS) {
-      double wt[4], at[4];
+    for (int64_t tb = 0; tb < T; tb += WF_THREADS) {
+      const int64_t t = tb + tid;
+      double e_t = 0.0;
+      if (t < T) {
+        double wt[4], wp[4] = {0.0, 0.0, 0.0, 0.0}, wn[4] = {0.0, 0.0, 0.0, 0.0}, at[4], g[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        at[k] = AMP ? (double)amp[t * 4 + k] : 1.0;
-        wt[k] = (double)wbuf[t * 4 + k] * at[k];
-      }
-      double g[4] = {0.0, 0.0, 0.0, 0.0};
-      if (t >= 1) {  // pair t-1: this frame is the "t+1" member -> rows 0..3 of G u = A w[t] - B w[t-1]
-        const double* G = gram + (t - 1);
-        double wp[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) wp[k] = (double)wbuf[(t - 1) * 4 + k] * (AMP ? (double)amp[(t - 1) * 4 + k] : 1.0);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double y = 0.0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) y += G[(int64_t)wf_a(r, c) * NP] * wt[c] - G[(int64_t)wf_b(r, c) * NP] * wp[c];
-          part += wt[r] * y;
-          g[r] += y;
+        for (int k = 0; k < 4; ++k) {
+          at[k] = AMP ? (double)amp[t * 4 + k] : 1.0;
+          wt[k] = (double)wbuf[t * 4 + k] * at[k];
         }
+        const bool has_prev = t >= 1, has_next = t + 1 < T;
+        if (has_prev)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wp[k] = (double)wbuf[(t - 1) * 4 + k] * (AMP ? (double)amp[(t - 1) * 4 + k] : 1.0);
+        if (has_next)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wn[k] = (double)wbuf[(t + 1) * 4 + k] * (AMP ? (double)amp[(t + 1) * 4 + k] : 1.0);
+        const double* Gp = gram + (t - 1);
+        const double* Gc = gram + t;
+        e_t = wf_frame(has_prev, has_next, wt, wp, wn, [&](int e) { return Gp[(int64_t)e * NP]; },
+                       [&](int e) { return Gc[(int64_t)e * NP]; }, g);
+        // gradient wrt w, cast to fp32 where the fp64 graph meets the fp32 softmax output
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st.grad[t * 4 + k] = (float)(2.0 * norm * g[k] * at[k]);
       }
-      if (t + 1 < T) {  // pair t: this frame is the "t" member -> rows 4..7 of G u = B' w[t+1] - C w[t]
-        const double* G = gram + t;
-        double wn[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) wn[k] = (double)wbuf[(t + 1) * 4 + k] * (AMP ? (double)amp[(t + 1) * 4 + k] : 1.0);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double y = 0.0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) y += G[(int64_t)wf_b(c, r) * NP] * wn[c] - G[(int64_t)wf_c(r, c) * NP] * wt[c];
-          part -= wt[r] * y;
-          g[r] -= y;
-        }
-      }
-      // gradient wrt w, cast to fp32 where the fp64 graph meets the fp32 softmax output
-#pragma unroll
-      for (int k = 0; k < 4; ++k) st.grad[t * 4 + k] = (float)(2.0 * norm * g[k] * at[k]);
+      e_t = warp_sum(e_t);
+      if (lane == 0 && tb + warp * 32 < T) chunk[(tb >> 5) + warp] = e_t;
     }
-    part = warp_sum(part);
-    if (lane == 0) s_red[warp] = part;
     __syncthreads();
     if (tid == 0) {
       double s = 0.0;
-      for (int w = 0; w < WF_THREADS / 32; ++w) s += s_red[w];
-      const double loss = s * norm;
-      if (it == 0) first_loss = loss;
-      int ctl = 0;
-      if (it % 100 == 1) {
-        if (fabs(min_loss - converge_min_loss) < 1e-5) ctl |= 1;
-        else converge_min_loss = min_loss;
-      }
-      if (!(ctl & 1)) {
-        if (loss < min_loss) {
-          min_loss = loss;
-          ctl |= 2;
-          since_improve = 0;
-        } else {
-          ++since_improve;
-        }
-        if (since_improve >= 1000) ctl |= 1;
-      }
-      if (ctl & 1) stop_iter = it;
-      s_ctl = ctl;
-      s_loss = loss;
-      const int step = it + 1;
-      s_step_size = (float)((double)0.1 / (1.0 - pow((double)0.9, (double)step)));
-      s_bc2_sqrt = (float)sqrt(1.0 - pow((double)0.999, (double)step));
+      for (int64_t c = 0; c < n_chunks; ++c) s += chunk[c];
+      s_ctl = ctrl.update(s * norm, it);
+      s_step_size = ctrl.step_size;
+      s_bc2_sqrt = ctrl.bc2_sqrt;
     }
     __syncthreads();
     const int ctl = s_ctl;
@@ -293,29 +355,14 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
     if (ctl & 1) break;
     // ---- Adam (amsgrad) step on the logits
     const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    (void)lr;
     for (int64_t t = tid; t < T; t += WF_THREADS) {
       float w[4], gw[4];
-      float dotgw = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         w[k] = wbuf[t * 4 + k];
         gw[k] = st.grad[t * 4 + k];
-        dotgw += gw[k] * w[k];
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float gth = w[k] * (gw[k] - dotgw);  // softmax backward
-        float m = st.m[t * 4 + k], v = st.v[t * 4 + k], vm = st.vmax[t * 4 + k];
-        m = m + (gth - m) * (1.0f - b1);
-        v = v * b2 + (1.0f - b2) * gth * gth;
-        vm = fmaxf(vm, v);
-        const float denom = sqrtf(vm) / bc2_sqrt + eps;
-        st.theta[t * 4 + k] = st.theta[t * 4 + k] - step_size * (m / denom);
-        st.m[t * 4 + k] = m;
-        st.v[t * 4 + k] = v;
-        st.vmax[t * 4 + k] = vm;
-      }
+      wf_adam4(st.theta + t * 4, st.m + t * 4, st.v + t * 4, st.vmax + t * 4, w, gw, step_size, bc2_sqrt);
     }
     __syncthreads();
   }
@@ -329,24 +376,207 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
     for (int k = 0; k < 4; ++k) out_weights[t * 4 + k] = w[k];
   }
   if (tid == 0 && info) {
-    info[0] = (double)stop_iter;
-    info[1] = min_loss;
-    info[2] = first_loss;
-    info[3] = s_loss;
+    info[0] = (double)ctrl.stop_iter;
+    info[1] = ctrl.min_loss;
+    info[2] = ctrl.first_loss;
+    info[3] = ctrl.last_loss;
   }
+}
+
+// ---- Cluster variant for a FEW LONG utterances (single-utterance conversion, BASELINE cfg 2): the
+// one-CTA kernel walks a 3001-frame utterance at ~35 us per Adam iteration (six frames per thread,
+// every Gram entry an L2 round trip).  Here a cluster of 8 CTAs splits the utterance into
+// contiguous runs of 32-frame chunks; each CTA keeps its run's Gram blocks, weights and optimiser
+// state in shared memory, exchanges the two boundary weights and its chunk sums with its peers
+// through distributed shared memory, and every CTA runs the (deterministic) stop rule itself —
+// two cluster barriers per iteration, nothing touches L2 inside the loop.  Same arithmetic, same
+// reduction order as the one-CTA kernel: results are bit-identical.
+constexpr int WC_C = 8;            // CTAs per cluster (portable maximum)
+constexpr int WC_THREADS = 256;
+constexpr int WC_MIN_FRAMES = 512; // every rank gets at least two chunks
+
+__host__ __device__ inline int64_t wc_first_chunk(int64_t n_chunks, int rank) { return n_chunks * rank / WC_C; }
+
+template <bool AMP>
+__global__ void __cluster_dims__(WC_C, 1, 1) __launch_bounds__(WC_THREADS, 1)
+weight_fit_cluster_kernel(const double* __restrict__ gram_all, const int64_t* __restrict__ utt_offsets,
+                          int64_t n_pairs_total, int dim, double loss_scale, int max_iters, int gram_in_smem,
+                          const float* __restrict__ amp_all, float* __restrict__ out_weights_all,
+                          double* __restrict__ info_all) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char wc_smem[];
+  __shared__ int s_ctl;
+  __shared__ float s_step_size, s_bc2_sqrt;
+  const int rank = (int)cluster.block_rank();
+  const int utt = blockIdx.x / WC_C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f_begin = utt_offsets[utt], f_end = utt_offsets[utt + 1];
+  const int64_t T = f_end - f_begin;                 // >= WC_MIN_FRAMES (host-checked)
+  const int64_t n_chunks = (T + 31) / 32;
+  const int64_t c0 = wc_first_chunk(n_chunks, rank), c1 = wc_first_chunk(n_chunks, rank + 1);
+  const int64_t f0 = c0 * 32, f1 = c1 * 32 < T ? c1 * 32 : T;   // this CTA's frames [f0, f1) of the utterance
+  const int n_loc = (int)(f1 - f0);
+  const int64_t p0 = f0 > 0 ? f0 - 1 : 0, p1 = f1 - 1 < T - 2 ? f1 - 1 : T - 2;   // Gram pairs p0..p1 (inclusive)
+  const int np_loc = (int)(p1 - p0 + 1);
+  // shared-memory carve-up (the same offsets in every CTA of the cluster, sized for the largest rank)
+  const int max_loc = (int)(((n_chunks + WC_C - 1) / WC_C + 1) * 32);
+  double* s_chunk = reinterpret_cast<double*>(wc_smem);                       // [n_chunks] all chunk sums of the utterance
+  float* s_w = reinterpret_cast<float*>(s_chunk + n_chunks);                  // [(max_loc + 2) * 4] halo | local | halo
+  float* s_theta = s_w + (size_t)(max_loc + 2) * 4;
+  float* s_m = s_theta + (size_t)max_loc * 4;
+  float* s_v = s_m + (size_t)max_loc * 4;
+  float* s_vmax = s_v + (size_t)max_loc * 4;
+  float* s_best = s_vmax + (size_t)max_loc * 4;
+  float* s_grad = s_best + (size_t)max_loc * 4;
+  double* s_gram = reinterpret_cast<double*>(s_grad + (size_t)max_loc * 4);  // [WF_E][np_loc] when gram_in_smem
+  const double* gram = gram_all + f_begin;
+  const float* amp = AMP ? amp_all + f_begin * 4 : nullptr;
+  float* out_weights = out_weights_all + f_begin * 4;
+  const double norm = loss_scale / ((double)(T - 1) * (double)dim);
+  const int64_t NP = n_pairs_total;
+
+  if (gram_in_smem)
+    for (int e = 0; e < WF_E; ++e)
+      for (int p = tid; p < np_loc; p += WC_THREADS) s_gram[e * np_loc + p] = gram[(int64_t)e * NP + p0 + p];
+  for (int i = tid; i < n_loc * 4; i += WC_THREADS) {
+    s_theta[i] = 0.f;
+    s_m[i] = 0.f;
+    s_v[i] = 0.f;
+    s_vmax[i] = 0.f;
+    s_best[i] = 0.f;
+  }
+  WfControl ctrl(max_iters);
+  // peers' views: the left neighbour's right halo and the right neighbour's left halo
+  float* left_halo = nullptr;
+  float* right_halo = nullptr;
+  if (rank > 0) {
+    const int64_t lc0 = wc_first_chunk(n_chunks, rank - 1);
+    const int left_n = (int)(f0 - lc0 * 32);
+    left_halo = cluster.map_shared_rank(s_w, rank - 1) + (size_t)(left_n + 1) * 4;
+  }
+  if (rank + 1 < WC_C) right_halo = cluster.map_shared_rank(s_w, rank + 1);
+  cluster.sync();   // every CTA's shared memory is live before anybody writes into it
+
+  for (int it = 0; it < max_iters; ++it) {
+    // ---- w = softmax(theta); boundary frames also go into the neighbours' halos
+    for (int tl = tid; tl < n_loc; tl += WC_THREADS) {
+      float th[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) th[k] = s_theta[tl * 4 + k];
+      softmax4(th, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_w[(tl + 1) * 4 + k] = w[k];
+      if (tl == 0 && left_halo)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) left_halo[k] = w[k];
+      if (tl == n_loc - 1 && right_halo)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) right_halo[k] = w[k];
+    }
+    cluster.sync();
+    // ---- loss and dL/dw; chunk sums go to every CTA of the cluster
+    for (int tb = 0; tb < n_loc; tb += WC_THREADS) {
+      const int tl = tb + tid;
+      const int64_t t = f0 + tl;
+      double e_t = 0.0;
+      if (tl < n_loc) {
+        double wt[4], wp[4] = {0.0, 0.0, 0.0, 0.0}, wn[4] = {0.0, 0.0, 0.0, 0.0}, at[4], g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          at[k] = AMP ? (double)amp[t * 4 + k] : 1.0;
+          wt[k] = (double)s_w[(tl + 1) * 4 + k] * at[k];
+        }
+        const bool has_prev = t >= 1, has_next = t + 1 < T;
+        if (has_prev)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wp[k] = (double)s_w[tl * 4 + k] * (AMP ? (double)amp[(t - 1) * 4 + k] : 1.0);
+        if (has_next)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wn[k] = (double)s_w[(tl + 2) * 4 + k] * (AMP ? (double)amp[(t + 1) * 4 + k] : 1.0);
+        if (gram_in_smem) {
+          const double* Gp = s_gram + (t - 1 - p0);
+          const double* Gc = s_gram + (t - p0);
+          e_t = wf_frame(has_prev, has_next, wt, wp, wn, [&](int e) { return Gp[e * np_loc]; },
+                         [&](int e) { return Gc[e * np_loc]; }, g);
+        } else {
+          const double* Gp = gram + (t - 1);
+          const double* Gc = gram + t;
+          e_t = wf_frame(has_prev, has_next, wt, wp, wn, [&](int e) { return Gp[(int64_t)e * NP]; },
+                         [&](int e) { return Gc[(int64_t)e * NP]; }, g);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_grad[tl * 4 + k] = (float)(2.0 * norm * g[k] * at[k]);
+      }
+      e_t = warp_sum(e_t);
+      const int64_t ch = c0 + (tb >> 5) + warp;
+      if (ch < c1 && lane < WC_C) cluster.map_shared_rank(s_chunk, lane)[ch] = e_t;   // lane r -> CTA r
+    }
+    cluster.sync();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int64_t c = 0; c < n_chunks; ++c) s += s_chunk[c];
+      s_ctl = ctrl.update(s * norm, it);
+      s_step_size = ctrl.step_size;
+      s_bc2_sqrt = ctrl.bc2_sqrt;
+    }
+    __syncthreads();
+    const int ctl = s_ctl;
+    if (ctl & 2)
+      for (int i = tid; i < n_loc * 4; i += WC_THREADS) s_best[i] = s_theta[i];
+    if (ctl & 1) break;
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    for (int tl = tid; tl < n_loc; tl += WC_THREADS) {
+      float w[4], gw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = s_w[(tl + 1) * 4 + k];
+        gw[k] = s_grad[tl * 4 + k];
+      }
+      wf_adam4(s_theta + tl * 4, s_m + tl * 4, s_v + tl * 4, s_vmax + tl * 4, w, gw, step_size, bc2_sqrt);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int tl = tid; tl < n_loc; tl += WC_THREADS) {
+    float th[4], w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) th[k] = s_best[tl * 4 + k];
+    softmax4(th, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out_weights[(f0 + tl) * 4 + k] = w[k];
+  }
+  if (rank == 0 && tid == 0 && info_all) {
+    double* info = info_all + (int64_t)utt * 4;
+    info[0] = (double)ctrl.stop_iter;
+    info[1] = ctrl.min_loss;
+    info[2] = ctrl.first_loss;
+    info[3] = ctrl.last_loss;
+  }
+  cluster.sync();   // nobody leaves while a peer could still address its shared memory
+}
+
+static size_t wc_smem_bytes(int64_t T, bool gram_in_smem) {
+  const int64_t n_chunks = (T + 31) / 32;
+  const int64_t max_loc = ((n_chunks + WC_C - 1) / WC_C + 1) * 32;
+  size_t b = (size_t)n_chunks * sizeof(double) + (size_t)(max_loc + 2) * 16 + (size_t)max_loc * 16 * 6;
+  if (gram_in_smem) b += (size_t)(max_loc + 1) * WF_E * sizeof(double);
+  return b + 16;
 }
 
 size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt) {
   if (n_query < 1) return 256;
   size_t gram = (size_t)n_query * WF_E * sizeof(double);
   size_t state = (size_t)n_query * k * sizeof(float) * 7;  // theta, m, v, vmax, best, grad scratch, wglob
+  size_t chunk = ((size_t)n_query / 32 + (size_t)n_utt + 2) * sizeof(double);
   size_t offs = ((size_t)(n_utt + 1) * sizeof(int64_t) + 255) / 256 * 256;
-  return gram + state + offs + 1024;
+  return gram + state + chunk + offs + 1024;
 }
 
 // Batched launch: utterance u owns frames [utt_offsets_host[u], utt_offsets_host[u+1]) of the
 // concatenated idx / out_weights; one CTA runs one utterance's whole optimisation, so a batch of
-// utterances (BASELINE cfg 5) fills the SMs.  info: double[n_utt][4].
+// utterances (BASELINE cfg 5) fills the SMs; a launch of few, long utterances gives each of them a
+// cluster of 8 CTAs instead.  info: double[n_utt][4].
 int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
                       const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
                       const float* amp, float* out_weights, double* info, void* workspace, cudaStream_t stream) {
@@ -359,7 +589,8 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   if (n_query == 0) return 0;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   double* gram = reinterpret_cast<double*>(ws);
-  float* f = reinterpret_cast<float*>(ws + (size_t)n_query * WF_E * sizeof(double));
+  double* chunk = gram + (size_t)n_query * WF_E;
+  float* f = reinterpret_cast<float*>(chunk + ((size_t)n_query / 32 + (size_t)n_utt + 2));
   WfState st;
   const size_t n4 = (size_t)n_query * 4;
   st.theta = f;
@@ -369,6 +600,7 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   st.best = f + 4 * n4;
   st.grad = f + 5 * n4;
   st.wglob = f + 6 * n4;
+  st.chunk = chunk;
   int64_t* d_off = reinterpret_cast<int64_t*>(f + 7 * n4);
   d_off = reinterpret_cast<int64_t*>((reinterpret_cast<uintptr_t>(d_off) + 255) & ~(uintptr_t)255);
   KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
@@ -380,6 +612,36 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
                                                                                                  dim, n_query, gram);
     KNN_LAUNCH_CHECK();
   }
+  int64_t min_len = INT64_MAX, max_len = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    const int64_t len = utt_offsets_host[u + 1] - utt_offsets_host[u];
+    min_len = len < min_len ? len : min_len;
+    max_len = len > max_len ? len : max_len;
+  }
+  const int64_t np_arg = n_pairs_total > 0 ? n_pairs_total : 1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int max_bytes = WF_STATE_FRAMES * 28 * (int)sizeof(float);   // 212.8 KB > 10240 * 16 B
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcMaxSmem));
+    KNN_CUDA(cudaFuncSetAttribute(weight_fit_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcMaxSmem));
+    attr_done = true;
+  }
+  // few, long utterances: a cluster per utterance (its state has to fit the cluster's shared memory)
+  if (opt_weight_fit_cluster() && n_utt * WC_C <= 144 && min_len >= WC_MIN_FRAMES &&
+      wc_smem_bytes(max_len, false) <= (size_t)kWcMaxSmem) {
+    const bool gram_in_smem = wc_smem_bytes(max_len, true) <= (size_t)kWcMaxSmem;
+    const size_t smem = wc_smem_bytes(max_len, gram_in_smem);
+    if (amp)
+      weight_fit_cluster_kernel<true><<<n_utt * WC_C, WC_THREADS, smem, stream>>>(
+          gram, d_off, np_arg, dim, loss_scale, max_iters, (int)gram_in_smem, amp, out_weights, info);
+    else
+      weight_fit_cluster_kernel<false><<<n_utt * WC_C, WC_THREADS, smem, stream>>>(
+          gram, d_off, np_arg, dim, loss_scale, max_iters, (int)gram_in_smem, nullptr, out_weights, info);
+    KNN_LAUNCH_CHECK();
+    return 0;
+  }
   // shared memory of the launch: the largest need over its utterances (each CTA picks its own mode)
   int64_t smem_floats = 4;
   for (int u = 0; u < n_utt; ++u) {
@@ -388,21 +650,12 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
     smem_floats = need > smem_floats ? need : smem_floats;
   }
   const size_t smem = (size_t)smem_floats * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    const int max_bytes = WF_STATE_FRAMES * 28 * (int)sizeof(float);   // 212.8 KB > 10240 * 16 B
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    attr_done = true;
-  }
   if (amp)
-    weight_fit_kernel<true><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
-                                                                 dim, loss_scale, max_iters, st, (int)smem_floats, amp,
-                                                                 out_weights, info);
+    weight_fit_kernel<true><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, np_arg, dim, loss_scale, max_iters, st,
+                                                                 (int)smem_floats, amp, out_weights, info);
   else
-    weight_fit_kernel<false><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, n_pairs_total > 0 ? n_pairs_total : 1,
-                                                                  dim, loss_scale, max_iters, st, (int)smem_floats, nullptr,
-                                                                  out_weights, info);
+    weight_fit_kernel<false><<<n_utt, WF_THREADS, smem, stream>>>(gram, d_off, np_arg, dim, loss_scale, max_iters, st,
+                                                                  (int)smem_floats, nullptr, out_weights, info);
   KNN_LAUNCH_CHECK();
   return 0;
 }

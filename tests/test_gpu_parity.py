@@ -388,6 +388,39 @@ def test_weight_fit_batched_equals_per_utterance(ops):
             assert got < orc.smoothness_loss(np.full((n, 4), 0.25), rows, 0.1)
 
 
+@pytest.mark.parametrize("lens,amp", [([3001], False), ([700, 512, 1900], False), ([5000], False), ([1200, 640], True)])
+def test_weight_fit_cluster_equals_one_cta(ops, lens, amp):
+    """few long utterances are fitted by a cluster of 8 CTAs each (state and Gram blocks in shared
+    memory, boundary weights and chunk sums through distributed shared memory): bit-identical to
+    the one-CTA kernel — same weights, same stop iteration, same losses — and the loss it reports
+    is the true loss of the weights it returns"""
+    from knn_svc_b200 import _lib
+    lib = _lib.load()
+    pool = synth.ar1_frames(900, seed=83)
+    rs = np.random.RandomState(9)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    base = rs.randint(0, 900, size=(offs[-1], 1))
+    idx = np.clip(base + rs.randint(-3, 4, size=(offs[-1], 4)), 0, 899).astype(np.int64)
+    ratio = dev((0.5 + rs.rand(offs[-1], 4)).astype(np.float32)) if amp else None
+    outs = []
+    try:
+        for cluster in (1, 0):
+            _lib.check(lib.knnsvc_set_option(b"weight_fit_cluster", cluster), "set_option")
+            w, info = ops.weight_fit(dev(idx), dev(pool), 0.1, return_info=True, utt_offsets=offs.tolist(), amp_ratio=ratio)
+            outs.append((w.cpu().numpy(), info.cpu().numpy()))
+    finally:
+        lib.knnsvc_set_option(b"weight_fit_cluster", 1)
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    w, info = outs[0]
+    assert np.all(info[:, 0] >= 101) and np.allclose(w.sum(1), 1, atol=1e-6)
+    if not amp:
+        a, b = offs[0], offs[1]
+        rows = orc._neighbour_rows(idx[a:b], np.asarray(pool, np.float64))
+        got = orc.smoothness_loss(w[a:b].astype(np.float64), rows, 0.1)
+        assert abs(info[0, 1] - got) <= 1e-6 * abs(got) + 1e-9
+
+
 # ----------------------------------------------------------------------------- K7
 def test_harmonic_bank_matches_reference(ops, golden):
     from knn_svc_b200.ddsp_prematch_dataset import f0_sinusoid, get_bulk_dsp_choral
