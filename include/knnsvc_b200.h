@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless it says "host";
- *   - the caller owns all memory, including workspaces (sizes are queried);
+ *   - the caller owns all memory, including workspaces (sizes are queried); the one exception
+ *     is the small stream-ordered scratch of knnsvc_concat_cost_reselect (see there);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), on the
  *     current device; nothing synchronises the host;
  *   - return value 0 = ok, >0 = cudaError_t, <0 = argument error;
@@ -107,7 +108,8 @@ long long knnsvc_launch_count(void);
  * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes),
  * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
  * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static
- * instead of dynamic unit scheduling). */
+ * instead of dynamic unit scheduling), "weight_fit_cluster" = 1|0 (K6: a cluster of 8 CTAs per
+ * utterance for launches of few long utterances, or always one CTA per utterance; same results). */
 int knnsvc_set_option(const char* name, int value);
 int knnsvc_filter_timing(int enable);
 int knnsvc_filter_timing_collect(float* ms_host, int max_n);
@@ -141,7 +143,9 @@ int knnsvc_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
 /* ---- K5: greedy concatenation-cost re-selection ---------------------------
  * knn_with_concat_cost — lib_ongaku_test.py:270-369, K = 4 candidates per frame.
  * Utterance u owns query rows [utt_offsets[u], utt_offsets[u+1]) (host array);
- * one CTA walks one utterance.  src_f0/pool_f0 NULL selects the no-f0 branch. */
+ * one CTA walks one utterance.  src_f0/pool_f0 NULL selects the no-f0 branch.
+ * The only call that allocates: (n_utt + 1) offsets + 2 doubles per frame of stream-ordered
+ * scratch from a private cudaMemPool (kept across synchronisations, freed on the stream). */
 int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const float* pool,
                                 int64_t n_pool, int dim, const float* shifted_src_f0,
                                 const float* pool_f0, float concat_weight,

@@ -107,7 +107,8 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (the library never allocates)."""
+    """Grow-only per-device scratch buffer (the search never allocates; the library's only internal
+    allocation is K5's small per-call scratch, from its own stream-ordered pool)."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
