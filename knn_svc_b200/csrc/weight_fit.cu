@@ -205,7 +205,6 @@ __device__ __forceinline__ void wf_adam4(float* theta, float* m_, float* v_, flo
 struct WfControl {
   double min_loss = 20000.0, converge_min_loss = 20000.0, first_loss = 0.0, last_loss = 0.0;
   int since_improve = 0, stop_iter;
-  float step_size = 0.f, bc2_sqrt = 1.f;
   __device__ explicit WfControl(int max_iters) : stop_iter(max_iters) {}
   __device__ int update(double loss, int it) {
     if (it == 0) first_loss = loss;
@@ -226,15 +225,26 @@ struct WfControl {
       if (since_improve >= 1000) ctl |= 1;
     }
     if (ctl & 1) stop_iter = it;
-    const int step = it + 1;
-    step_size = (float)((double)0.1 / (1.0 - pow((double)0.9, (double)step)));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)0.999, (double)step));
     return ctl;
   }
 };
+// Adam's bias corrections of iteration `it` (lr / (1 - b1^step) and sqrt(1 - b2^step)): a function of
+// the iteration number alone, so another warp evaluates the two pow() while the loss is being formed.
+__device__ __forceinline__ void wf_bias(int it, float* step_size, float* bc2_sqrt) {
+  const int step = it + 1;
+  *step_size = (float)((double)0.1 / (1.0 - pow((double)0.9, (double)step)));
+  *bc2_sqrt = (float)sqrt(1.0 - pow((double)0.999, (double)step));
+}
+// Sum of the chunk sums in the one canonical order: lane l adds chunks l, l+32, l+64, ... in that
+// order, then the 32 lane sums go through the warp shuffle tree.  Called by one full warp.
+__device__ __forceinline__ double wf_sum_chunks(const volatile double* chunk, int64_t n_chunks, int lane) {
+  double s = 0.0;
+  for (int64_t c = lane; c < n_chunks; c += 32) s += chunk[c];
+  return warp_sum(s);
+}
 
 // The loss is reduced in ONE order everywhere: e_t summed over chunks of 32 consecutive frames by a
-// warp shuffle tree (frames past the end count as 0), then the chunk sums added in index order.
+// warp shuffle tree (frames past the end count as 0), then the chunk sums by wf_sum_chunks.
 
 // AMP: every candidate row is scaled by amp[t,k] before mixing (compute_weight_with_amp,
 // ddsp_prematch_dataset.py:684-803: `synth_set[...] * amp_ratio[:, :, None]` for all three
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
 #pragma unroll
       for (int k = 0; k < 4; ++k) wbuf[t * 4 + k] = w[k];
     }
+    if (tid == 32) wf_bias(it, &s_step_size, &s_bc2_sqrt);
     __syncthreads();
     // ---- loss and dL/dw from the Gram blocks (a warp holds 32 consecutive frames: one chunk)
     const int64_t NP = n_pairs_total;
@@ -339,12 +350,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
       if (lane == 0 && tb + warp * 32 < T) chunk[(tb >> 5) + warp] = e_t;
     }
     __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int64_t c = 0; c < n_chunks; ++c) s += chunk[c];
-      s_ctl = ctrl.update(s * norm, it);
-      s_step_size = ctrl.step_size;
-      s_bc2_sqrt = ctrl.bc2_sqrt;
+    if (warp == 0) {
+      const double s = wf_sum_chunks(chunk, n_chunks, lane);
+      if (lane == 0) s_ctl = ctrl.update(s * norm, it);
     }
     __syncthreads();
     const int ctl = s_ctl;
@@ -474,6 +482,7 @@ weight_fit_cluster_kernel(const double* __restrict__ gram_all, const int64_t* __
 #pragma unroll
         for (int k = 0; k < 4; ++k) right_halo[k] = w[k];
     }
+    if (tid == WC_THREADS - 32) wf_bias(it, &s_step_size, &s_bc2_sqrt);
     cluster.sync();
     // ---- loss and dL/dw; chunk sums go to every CTA of the cluster
     for (int tb = 0; tb < n_loc; tb += WC_THREADS) {
@@ -513,12 +522,9 @@ weight_fit_cluster_kernel(const double* __restrict__ gram_all, const int64_t* __
       if (ch < c1 && lane < WC_C) cluster.map_shared_rank(s_chunk, lane)[ch] = e_t;   // lane r -> CTA r
     }
     cluster.sync();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int64_t c = 0; c < n_chunks; ++c) s += s_chunk[c];
-      s_ctl = ctrl.update(s * norm, it);
-      s_step_size = ctrl.step_size;
-      s_bc2_sqrt = ctrl.bc2_sqrt;
+    if (warp == 0) {
+      const double s = wf_sum_chunks(s_chunk, n_chunks, lane);
+      if (lane == 0) s_ctl = ctrl.update(s * norm, it);
     }
     __syncthreads();
     const int ctl = s_ctl;
