@@ -74,6 +74,9 @@ int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t 
  *             segments, units, grid, log cap, reserved}
  */
 size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, int k);
+/* The traversal the search would use for this shape (host-only, no GPU work): plan_host int[8] <-
+ * {CTAs per MMA, query tiles, pool tiles, pool segments, blocks per chain, work units, grid, log cap}. */
+int knnsvc_knn_plan(int64_t n_query, int64_t n_pool, int k, int* plan_host);
 int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query,
                       const float* p, const void* ph, const float* pn, int64_t n_pool,
                       int dim, int dim_pad, int k, int64_t index_offset,

@@ -22,6 +22,7 @@ SIGNATURES = {
     "knnsvc_prepare_rows": (i32, [vp, i64, i32, i64, vp, i32, vp, vp, vp, vp]),
     "knnsvc_cosine_dist": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "knnsvc_knn_workspace_bytes": (sz, [i64, i64, i32, i32]),
+    "knnsvc_knn_plan": (i32, [i64, i64, i32, vp]),
     "knnsvc_knn_search": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, sz, vp,
                                 vp]),
     "knnsvc_knn_search_masked": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp,

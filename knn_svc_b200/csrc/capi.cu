@@ -162,6 +162,15 @@ size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, 
   return carve(nullptr, n_query, n_pool, k, pl).total;
 }
 
+int knnsvc_knn_plan(int64_t n_query, int64_t n_pool, int k, int* plan_host) {
+  KNN_CHECK_ARG(plan_host != nullptr, -1, "knn_plan: null output");
+  KNN_CHECK_ARG(n_query >= 1 && n_pool >= 1 && k >= 1 && k <= kMaxK, -1, "knn_plan: bad shape");
+  const FilterPlan pl = plan_filter(n_query, n_pool, k);
+  const int v[8] = {pl.ctas, pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.n_blk, pl.n_units, pl.grid, pl.cap};
+  for (int i = 0; i < 8; ++i) plan_host[i] = v[i];
+  return 0;
+}
+
 int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
                       const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
                       int64_t index_offset, const float* q_err, const float* p_err, float* out_dist,

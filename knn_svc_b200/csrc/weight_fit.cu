@@ -634,8 +634,27 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
     KNN_CUDA(cudaFuncSetAttribute(weight_fit_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcMaxSmem));
     attr_done = true;
   }
-  // few, long utterances: a cluster per utterance (its state has to fit the cluster's shared memory)
-  if (opt_weight_fit_cluster() && n_utt * WC_C <= 144 && min_len >= WC_MIN_FRAMES &&
+  // few, long utterances: a cluster per utterance (its state has to fit the cluster's shared memory,
+  // and the device — or the SM partition this context runs in — has to be able to host a cluster)
+  static int cluster_ok = -1;
+  if (cluster_ok < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(WC_C);
+    cfg.blockDim = dim3(WC_THREADS);
+    cfg.dynamicSmemBytes = kWcMaxSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = WC_C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, weight_fit_cluster_kernel<false>, &cfg);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    cluster_ok = (e == cudaSuccess && n_clusters >= 1) ? 1 : 0;
+  }
+  if (cluster_ok && opt_weight_fit_cluster() && n_utt * WC_C <= 144 && min_len >= WC_MIN_FRAMES &&
       wc_smem_bytes(max_len, false) <= (size_t)kWcMaxSmem) {
     const bool gram_in_smem = wc_smem_bytes(max_len, true) <= (size_t)kWcMaxSmem;
     const size_t smem = wc_smem_bytes(max_len, gram_in_smem);

@@ -29,6 +29,39 @@ def test_library_exports_every_declared_symbol():
     assert lib.knnsvc_weight_fit_workspace_bytes(100, 4) > 0
 
 
+def test_filter_traversal_plan_invariants():
+    """knnsvc_knn_plan is pure host logic: chains (query tile x pool segment) cut into L2-sized blocks.
+    Every shape must give a plan that covers the problem, fits the grid and matches the workspace query."""
+    import ctypes
+    from knn_svc_b200 import _lib
+    lib = _lib.load()
+    shapes = [(1, 33, 4), (20, 257, 32), (3000, 30000, 4), (3001, 3001, 32), (100_000, 30_000, 32), (1500, 30_000, 4),
+              (100_000, 1_250_000, 4), (100_000, 10_000_000, 4), (3000, 10_000_000, 32), (262_144, 262_144, 32),
+              (129, 513, 8), (148 * 128, 256, 1), (148 * 128 + 1, 24_577, 4)]
+    for T, NP, k in shapes:
+        out = (ctypes.c_int * 8)()
+        _lib.check(lib.knnsvc_knn_plan(T, NP, k, ctypes.cast(out, ctypes.c_void_p)), "knn_plan")
+        ctas, n_qt, n_pt, n_seg, n_blk, units, grid, cap = list(out)
+        assert ctas == 1 and n_qt == -(-T // 128) and n_pt == -(-NP // 256)
+        assert 1 <= n_seg <= min(16, n_pt) and n_blk >= 1 and units == n_qt * n_seg * n_blk
+        assert 1 <= grid <= 148 and grid == min(units, 148)
+        assert cap == max(256, 64 * k)
+        seg_tiles = -(-n_pt // n_seg)
+        assert -(-seg_tiles // n_blk) <= 96, "a block holds at most 96 pool tiles (48 MB of fp16 operand)"
+        if n_qt >= 148:
+            assert n_seg <= 12, "many query tiles: segments are not needed to fill the SMs"
+        if n_qt * n_seg < 148:
+            assert n_blk == 1 or n_qt * 16 < 148, "few chains: blocks of a chain would serialise"
+        ws = lib.knnsvc_knn_workspace_bytes(T, NP, 1024, k)
+        assert ws >= T * n_seg * cap * 8 and ws < T * n_seg * cap * 8 + T * n_seg * (k + 3) * 4 + (1 << 26)
+    # the headline shape: one segment, 407 blocks of 96 tiles per chain
+    out = (ctypes.c_int * 8)()
+    lib.knnsvc_knn_plan(100_000, 10_000_000, 4, ctypes.cast(out, ctypes.c_void_p))
+    assert list(out)[3:6] == [1, 407, 782 * 407]
+    with pytest.raises(ValueError):
+        _lib.check(lib.knnsvc_knn_plan(0, 10, 4, ctypes.cast(out, ctypes.c_void_p)), "knn_plan")
+
+
 def test_ops_refuse_cpu_tensors():
     from knn_svc_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
