@@ -137,3 +137,19 @@ def test_sharded_exchange_gloo_world_size_2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("-ok") == 2, r.stdout
+
+
+def test_bench_reference_arm_runs_on_host_cores():
+    """`bench.py --impl reference` times the reference's CPU matcher (the oracle port) on the host cores and
+    prints one JSON line with the contract's keys; it never touches the GPU library."""
+    import json
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-queries", "8", "--cpu-pool", "3000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "query frames/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("cfg4")
