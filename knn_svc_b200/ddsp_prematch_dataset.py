@@ -188,9 +188,19 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
     into the batch tensors)."""
     assert prioritize_f0                                                     # reference :1375
     dev = pool.device
-    lens = [int(q.shape[0]) for q in query_seqs]
-    if not lens:
+    if not len(query_seqs):
         return []
+    # K5 and K6 run one CTA per utterance and the GPU hands CTAs out in index order: with more
+    # utterances than SMs, longest-first keeps the tail of the launch short.  Results go back in
+    # the caller's order (and do not depend on the order: every utterance is independent).
+    order = list(range(len(query_seqs)))
+    if len(order) > 1 and os.environ.get("KNNSVC_BATCH_ORDER", "longest_first") == "longest_first":
+        order.sort(key=lambda u: -int(query_seqs[u].shape[0]))
+    place = {u: pos for pos, u in enumerate(order)}
+    caller_f0s = query_f0s
+    query_seqs = [query_seqs[u] for u in order]
+    query_f0s = [query_f0s[u] for u in order]
+    lens = [int(q.shape[0]) for q in query_seqs]
     offs = [0]
     for n in lens:
         offs.append(offs[-1] + n)
@@ -229,10 +239,10 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
     f0_devs = {f.device for f in query_f0s}
     shifted_host = shifted_f0.to(next(iter(f0_devs))) if len(f0_devs) == 1 else None
     results = []
-    for u in range(len(lens)):
-        a, b = offs[u], offs[u + 1]
+    for u in range(len(lens)):                      # u: the caller's index; its data sits at position place[u]
+        a, b = offs[place[u]], offs[place[u] + 1]
         r = {"out_feats": out_feats[a:b],
-             "shifted_f0": shifted_host[a:b] if shifted_host is not None else shifted_f0[a:b].to(query_f0s[u].device),
+             "shifted_f0": shifted_host[a:b] if shifted_host is not None else shifted_f0[a:b].to(caller_f0s[u].device),
              "wavlm_indices": idx_w[a:b], "nearest_nbrs": nearest_nbrs[a:b], "harm_indices": idx_h[a:b]}
         if harm is not None:
             r["harmonics"] = harm[a:b]
