@@ -145,6 +145,7 @@ int knnsvc_version(void) { return 100; }
 int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad, float* norms,
                         int* bad_rows, float* max_err, void* stream) {
   KNN_CHECK_ARG(rows >= 0 && dim >= 1 && ld >= dim && dim_pad >= dim, -1, "prepare_rows: bad shape");
+  if (rows == 0) return 0;   // an empty row set has no storage to point at
   KNN_CHECK_ARG(x && half_out && norms && bad_rows, -1, "prepare_rows: null pointer");
   return launch_prepare_rows(x, rows, dim, ld, half_out, dim_pad, norms, bad_rows, max_err, (cudaStream_t)stream);
 }

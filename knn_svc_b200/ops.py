@@ -80,9 +80,10 @@ def prepare_rows(x: torch.Tensor, check: bool = True) -> PreparedRows:
     scal = torch.zeros((2,), dtype=torch.int32, device=x.device)     # [0] bad-row counter, [1] max error (float bits)
     bad, err = scal[0:1], scal[1:2].view(torch.float32)
     lib = _lib.load()
-    with torch.cuda.device(x.device):
-        _lib.check(lib.knnsvc_prepare_rows(x.data_ptr(), n, dim, dim, half.data_ptr(), dim_pad, norms.data_ptr(),
-                                           bad.data_ptr(), err.data_ptr(), _stream()), "prepare_rows")
+    if n > 0:
+        with torch.cuda.device(x.device):
+            _lib.check(lib.knnsvc_prepare_rows(x.data_ptr(), n, dim, dim, half.data_ptr(), dim_pad, norms.data_ptr(),
+                                               bad.data_ptr(), err.data_ptr(), _stream()), "prepare_rows")
     if check and n > 0 and int(bad.item()) != 0:
         raise ValueError(f"{int(bad.item())} zero-norm or non-finite feature rows: cosine distance undefined "
                          "(the reference exits with 'containing nan')")

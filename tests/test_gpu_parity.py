@@ -577,19 +577,19 @@ def test_knn_search_block_traversal_changes_nothing(ops, filter_options, block_t
 
 
 def test_knn_search_cfg4_shard_size_properties(ops):
-    """One 8-GPU shard of BASELINE cfg 4 (1.25 M pool frames; 20k of the 100k query frames): 51 blocks per
-    chain.  Too big for any oracle, so: sortedness, index range, returned distances are the true fp64
+    """One 8-GPU shard of BASELINE cfg 4 at its full per-GPU size (all 100k query frames against 1.25 M pool
+    frames): 51 blocks per chain.  Too big for any oracle, so: sortedness, index range, returned distances are the true fp64
     distances of the returned indices, the result equals the merge of two half-shard searches, and a
     sample of rows is checked against a brute-force fp64 top-k."""
     g = torch.Generator(device=DEV); g.manual_seed(4)
-    T, NP, k = 20000, 1_250_000, 4
+    T, NP, k = 100_000, 1_250_000, 4
     q = torch.randn((T, 1024), device=DEV, generator=g)
     p = torch.randn((NP, 1024), device=DEV, generator=g)
     qp, pp = ops.prepare_rows(q), ops.prepare_rows(p)
     dist, idx, stats = ops.knn_search(qp, pp, k, return_stats=True)
-    assert int(stats[0]) == 0 and int(stats[4]) >= 157 * 51
+    assert int(stats[0]) == 0 and int(stats[4]) >= 782 * 51
     assert torch.all(dist[:, 1:] >= dist[:, :-1]) and idx.min() >= 0 and idx.max() < NP
-    rows = torch.arange(0, T, 313, device=DEV)
+    rows = torch.arange(0, T, 1567, device=DEV)
     pn, qn = p.double().norm(dim=1), q[rows].double().norm(dim=1)
     true_d = torch.empty((len(rows), NP), dtype=torch.float64, device=DEV)
     for a in range(0, NP, 250_000):
@@ -602,3 +602,36 @@ def test_knn_search_cfg4_shard_size_properties(ops):
     parts = [ops.knn_search(qp, ops.prepare_rows(p[:half]), k), ops.knn_search(qp, ops.prepare_rows(p[half:]), k, index_offset=half)]
     d_m, i_m = ops.merge_topk(torch.stack([d for d, _ in parts]), torch.stack([i for _, i in parts]))
     assert torch.equal(i_m, idx) and torch.equal(d_m, dist)
+
+
+def test_knn_search_edge_cases(ops):
+    """empty query set, k at its bounds, k equal to the pool size, a one-row pool, argument errors"""
+    p = synth.ar1_frames(40, seed=95)
+    pp = ops.prepare_rows(dev(p))
+    empty = ops.prepare_rows(torch.empty((0, 1024), device=DEV))
+    d, i = ops.knn_search(empty, pp, 4)
+    assert d.shape == (0, 4) and i.shape == (0, 4) and i.dtype == torch.int64
+    q = synth.ar1_frames(9, seed=96)
+    qp = ops.prepare_rows(dev(q))
+    o_idx, o_val = orc.knn(q, p, 33)
+    d, i = ops.knn_search(qp, pp, 32)                       # k = KNNSVC_MAX_K
+    assert np.abs(d.cpu().numpy() - o_val[:, :32]).max() < 2e-6
+    d1, i1 = ops.knn_search(qp, pp, 1)                      # k = 1
+    assert torch.equal(i1[:, 0], i[:, 0]) and torch.equal(d1[:, 0], d[:, 0])
+    small = ops.prepare_rows(dev(p[:7]))
+    d7, i7 = ops.knn_search(qp, small, 7)                   # k == pool size: every row, ascending
+    assert torch.all(torch.sort(i7, 1).values == torch.arange(7, device=DEV)[None])
+    assert torch.all(d7[:, 1:] >= d7[:, :-1])
+    one = ops.prepare_rows(dev(p[:1]))
+    d0, i0 = ops.knn_search(qp, one, 1)                     # one-row pool
+    assert torch.all(i0 == 0)
+    assert np.abs(d0.cpu().numpy()[:, 0] - orc.knn(q, p[:1], 1)[1][:, 0]).max() < 2e-6
+    for bad_k in (0, 33):
+        with pytest.raises(ValueError):
+            ops.knn_search(qp, pp, bad_k)
+    with pytest.raises(ValueError):
+        ops.knn_search(qp, small, 8)                        # k exceeds the pool
+    with pytest.raises(ValueError):
+        ops.knn_search(qp, ops.prepare_rows(dev(synth.randn_frames(10, d=512, seed=1))), 4)   # dimensions differ
+    with pytest.raises(ValueError):
+        ops.knn_search(qp, pp, 4, mask_lo=torch.zeros(9, dtype=torch.int64, device=DEV))       # mask_hi missing
