@@ -187,9 +187,9 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
     results do not depend on what else is in the batch.  Returns a list of result dicts (views
     into the batch tensors)."""
     assert prioritize_f0                                                     # reference :1375
-    dev = pool.device
     if not len(query_seqs):
         return []
+    dev = pool.device
     # K5 and K6 run one CTA per utterance and the GPU hands CTAs out in index order: with more
     # utterances than SMs, longest-first keeps the tail of the launch short.  Results go back in
     # the caller's order (and do not depend on the order: every utterance is independent).

@@ -200,6 +200,8 @@ def merge_topk(gathered_dist: torch.Tensor, gathered_idx: torch.Tensor):
     dist = torch.empty((T, k), dtype=torch.float32, device=gd.device)
     idx = torch.empty((T, k), dtype=torch.int64, device=gd.device)
     lib = _lib.load()
+    if T == 0:
+        return dist, idx
     with torch.cuda.device(gd.device):
         _lib.check(lib.knnsvc_merge_topk(gd.data_ptr(), gi.data_ptr(), R, T, k, dist.data_ptr(), idx.data_ptr(),
                                          _stream()), "merge_topk")
@@ -214,6 +216,8 @@ def gather_mix(pool: torch.Tensor, idx: torch.Tensor, weights: torch.Tensor | No
     w = None if weights is None else _f32c(weights.to(pool.device))
     out = torch.empty((T, pool.shape[1]), dtype=torch.float32, device=pool.device)
     lib = _lib.load()
+    if T == 0:
+        return out
     with torch.cuda.device(pool.device):
         _lib.check(lib.knnsvc_gather_mix(pool.data_ptr(), pool.shape[0], pool.shape[1], idx.data_ptr(), _ptr(w), T, k,
                                          out.data_ptr(), _stream()), "gather_mix")
@@ -229,6 +233,8 @@ def f0_rerank(expected_f0: torch.Tensor, pool_f0: torch.Tensor, idx: torch.Tenso
         raise ValueError("expected_f0 and indices disagree on the number of frames")
     out = torch.empty_like(idx)
     lib = _lib.load()
+    if T == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(lib.knnsvc_f0_rerank(e.data_ptr(), f.data_ptr(), idx.data_ptr(), T, k, out.data_ptr(), _stream()),
                    "f0_rerank")
@@ -253,6 +259,8 @@ def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tenso
     arr = (ctypes.c_int64 * len(offs))(*offs)
     out = torch.empty_like(idx)
     lib = _lib.load()
+    if T == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(lib.knnsvc_concat_cost_reselect(idx.data_ptr(), src.data_ptr(), pool.data_ptr(), pool.shape[0],
                                                    pool.shape[1], _ptr(sf), _ptr(pf), float(concat_weight),
@@ -314,6 +322,8 @@ def harmonic_bank(f0: torch.Tensor, amp: torch.Tensor | None, sample_rate: int =
     out = torch.empty((B, T * hop), dtype=torch.float32, device=f0.device)
     ws = torch.empty((max(B * T, 1),), dtype=torch.float64, device=f0.device)
     lib = _lib.load()
+    if B * T == 0:
+        return out
     with torch.cuda.device(f0.device):
         _lib.check(lib.knnsvc_harmonic_bank(f0.data_ptr(), _ptr(amp), B, T, H, int(sample_rate), int(hop),
                                             out.data_ptr(), ws.data_ptr(), _stream()), "harmonic_bank")
@@ -343,6 +353,8 @@ def layer_mix(feats: torch.Tensor, weights_a, weights_b=None):
             raise ValueError("one weight per layer expected")
         out_b = torch.empty_like(out_a)
     lib = _lib.load()
+    if T * D == 0:
+        return out_a if weights_b is None else (out_a, out_b)
     with torch.cuda.device(feats.device):
         _lib.check(lib.knnsvc_layer_mix(feats.data_ptr(), L, T, D, wa.ctypes.data_as(ctypes.c_void_p),
                                         None if wb is None else wb.ctypes.data_as(ctypes.c_void_p),
@@ -361,6 +373,8 @@ def stft_magnitude(audio: torch.Tensor, frames: int | None = None, n_fft: int = 
         raise AssertionError("spectrogram shorter than the feature sequence")       # reference :362
     out = torch.empty((frames, n_fft // 2), dtype=torch.float32, device=x.device)
     lib = _lib.load()
+    if frames == 0:
+        return out
     with torch.cuda.device(x.device):
         _lib.check(lib.knnsvc_stft_magnitude(x.data_ptr(), n, frames, n_fft, hop, out.data_ptr(), _stream()),
                    "stft_magnitude")
@@ -379,6 +393,8 @@ def harmonic_amplitudes(spec: torch.Tensor, f0: torch.Tensor, n_harm: int = 49, 
         raise AssertionError([sample_rate / (2 * S)])                                # reference :392
     out = torch.empty((T, n_harm), dtype=torch.float32, device=spec.device)
     lib = _lib.load()
+    if T == 0:
+        return out
     with torch.cuda.device(spec.device):
         _lib.check(lib.knnsvc_harmonic_amplitudes(spec.data_ptr(), f0.data_ptr(), T, S, n_harm, int(sample_rate),
                                                   out.data_ptr(), _stream()), "harmonic_amplitudes")
@@ -391,6 +407,8 @@ def row_l1(x: torch.Tensor) -> torch.Tensor:
     x = _f32c(x)
     out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
     lib = _lib.load()
+    if x.shape[0] == 0:
+        return out
     with torch.cuda.device(x.device):
         _lib.check(lib.knnsvc_row_l1(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "row_l1")
     return out
@@ -406,6 +424,8 @@ def amp_ratio(l1_query: torch.Tensor, l1_pool: torch.Tensor, idx: torch.Tensor) 
         raise ValueError("one query norm per index row expected")
     out = torch.empty((T, k), dtype=torch.float32, device=dev)
     lib = _lib.load()
+    if T == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(lib.knnsvc_amp_ratio(q.data_ptr(), p.data_ptr(), idx.data_ptr(), T, k, p.shape[0], out.data_ptr(),
                                         _stream()), "amp_ratio")

@@ -635,3 +635,21 @@ def test_knn_search_edge_cases(ops):
         ops.knn_search(qp, ops.prepare_rows(dev(synth.randn_frames(10, d=512, seed=1))), 4)   # dimensions differ
     with pytest.raises(ValueError):
         ops.knn_search(qp, pp, 4, mask_lo=torch.zeros(9, dtype=torch.int64, device=DEV))       # mask_hi missing
+
+
+def test_ops_accept_empty_inputs(ops):
+    """zero frames in, zero frames out, for every op of the path (an utterance trimmed to nothing, an empty
+    shard): shapes and dtypes as for non-empty inputs, no library call on a null pointer"""
+    pool = dev(synth.ar1_frames(20, seed=97))
+    e_idx = torch.empty((0, 4), dtype=torch.int64, device=DEV)
+    assert ops.gather_mix(pool, e_idx, None).shape == (0, 1024)
+    assert ops.f0_rerank(torch.empty(0), torch.rand(20) + 100, torch.empty((0, 32), dtype=torch.int64, device=DEV)).shape == (0, 32)
+    assert ops.concat_cost_reselect(e_idx, torch.empty((0, 1024), device=DEV), pool).shape == (0, 4)
+    assert ops.weight_fit(e_idx, pool, 0.1).shape == (0, 4)
+    assert ops.harmonic_bank(torch.empty((1, 0), device=DEV), torch.empty((1, 0, 49), device=DEV)).shape == (1, 0)
+    assert ops.row_l1(torch.empty((0, 200), device=DEV)).shape == (0,)
+    assert ops.amp_ratio(torch.empty(0, device=DEV), torch.rand(20, device=DEV), e_idx).shape == (0, 4)
+    d, i = ops.merge_topk(torch.empty((2, 0, 4), device=DEV), torch.empty((2, 0, 4), dtype=torch.int64, device=DEV))
+    assert d.shape == (0, 4) and i.shape == (0, 4)
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    assert pm.match_utterances([], [], None) == []
