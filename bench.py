@@ -159,9 +159,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL prints its "NCCL version ..." banner on stdout at communicator creation, whatever NCCL_DEBUG
+        # says; the JSON line below is the LAST line of rank 0's stdout)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     T, NP = args.queries, args.pool
