@@ -653,3 +653,43 @@ def test_ops_accept_empty_inputs(ops):
     assert d.shape == (0, 4) and i.shape == (0, 4)
     from knn_svc_b200 import ddsp_prematch_dataset as pm
     assert pm.match_utterances([], [], None) == []
+
+
+def test_edge_branches_match_reference(ops):
+    """the CUDA path on the edge-branch fixtures made by the reference (tests/golden/make_golden_edges.py):
+    greedy re-selection at the end of the pool (prev+1 clamped) at three concat weights with unvoiced frames in
+    both f0 tracks, both K5 kernels; f0 re-rank and f0 shift with unvoiced frames; harmonic bank above Nyquist
+    and on an all-unvoiced track"""
+    from pathlib import Path
+    from knn_svc_b200 import _lib
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    e = dict(np.load(Path(__file__).resolve().parent / "golden" / "reference_outputs_edges.npz"))
+    lib = _lib.load()
+    T, Np = 60, 300
+    q, p = synth.ar1_frames(T, seed=111, reset_every=25), synth.ar1_frames(Np, seed=112)
+    f0q, f0p = synth.f0_track(T, seed=113, unvoiced=0.3), synth.f0_track(Np, seed=114, unvoiced=0.3)
+    idx = dev(e["k5e_idx"])
+    try:
+        for staged in (1, 0):
+            _lib.check(lib.knnsvc_set_option(b"concat_staged", staged), "set_option")
+            for w, tag in ((0.2, "w0p2"), (0.1, "w0p1"), (0.3, "w0p3")):
+                got = ops.concat_cost_reselect(idx, dev(q), dev(p), concat_weight=w).cpu().numpy()
+                assert np.array_equal(got, e[f"k5e_nof0_{tag}_f64"]), (staged, tag)
+                got = ops.concat_cost_reselect(idx, dev(q), dev(p), dev(f0q), dev(f0p), concat_weight=w).cpu().numpy()
+                assert np.array_equal(got, e[f"k5e_f0_{tag}_f64"]), (staged, tag)
+            two = ops.concat_cost_reselect(idx[:2], dev(q[:2]), dev(p), concat_weight=0.2).cpu().numpy()
+            assert np.array_equal(two, e["k5e_two_frames"])
+    finally:
+        lib.knnsvc_set_option(b"concat_staged", 1)
+    prio = ops.f0_rerank(dev(f0q), dev(f0p), dev(e["k4e_nbrs"])).cpu().numpy()
+    assert np.array_equal(prio, e["k4e_prio"])
+    pool_med = torch.median(torch.log(dev(f0p)[dev(f0p) != 0]))
+    shifted = pm.shift_query_f0_batched([torch.from_numpy(f0q)], pool_med).cpu().numpy()
+    assert np.array_equal(shifted == 0, e["a6e_shifted"] == 0)
+    assert np.abs(shifted - e["a6e_shifted"]).max() <= 1e-5 * e["a6e_shifted"].max()
+    f0hi = np.linspace(700.0, 1000.0, 16).astype(np.float32); f0hi[5:8] = 0.0
+    amp = synth.harmonics_pool(16, seed=115)
+    sig = pm.get_bulk_dsp_choral(dev(f0hi)[None, :, None], dev(amp)[None]).cpu().numpy()
+    assert np.abs(sig - e["k7e_hi"]).max() <= 1e-4 * np.abs(e["k7e_hi"]).max()
+    zero = pm.get_bulk_dsp_choral(torch.zeros((1, 16, 1), device=DEV), dev(amp)[None]).cpu().numpy()
+    assert np.abs(zero - e["k7e_zero"]).max() <= 1e-6
