@@ -20,36 +20,43 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_opt_cta_group = 0;  // 0 = unset -> env KNNSVC_CTA_GROUP or default
-static int g_opt_bf16 = 0;
+// Tuning options: process-wide diagnostic switches (knnsvc_set_option).  Each is one relaxed atomic
+// read at launch time, so setting one from another thread is well defined; none of them changes
+// results, only which kernel shape / schedule produces them.
+static std::atomic<int> g_opt_cta_group{0};  // 0 = unset -> env KNNSVC_CTA_GROUP or default
+static std::atomic<int> g_opt_bf16{0};
 int opt_cta_group() {
-  if (g_opt_cta_group == 0) {
+  int v = g_opt_cta_group.load(std::memory_order_relaxed);
+  if (v == 0) {
     const char* e = getenv("KNNSVC_CTA_GROUP");
-    g_opt_cta_group = (e && e[0] == '2') ? 2 : 1;
+    v = (e && e[0] == '2') ? 2 : 1;
+    g_opt_cta_group.store(v, std::memory_order_relaxed);
   }
-  return g_opt_cta_group;
+  return v;
 }
-int opt_bf16() { return g_opt_bf16; }
-static int g_opt_filter_flags = 1;
-int opt_filter_flags() { return g_opt_filter_flags; }
-static int g_opt_wf_cluster = 1;
-int opt_weight_fit_cluster() { return g_opt_wf_cluster; }
-static int g_opt_block_tiles = 0;
-int opt_block_tiles() { return g_opt_block_tiles; }
-static int g_opt_spin_ns = 40;  // measured: ~3% faster than a pure spin under the power cap
-int opt_spin_ns() { return g_opt_spin_ns; }
-static int g_opt_epi_sleep_ns = 0;
-int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns; }
+int opt_bf16() { return g_opt_bf16.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_filter_flags{1};
+int opt_filter_flags() { return g_opt_filter_flags.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_wf_cluster{1};
+int opt_weight_fit_cluster() { return g_opt_wf_cluster.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_block_tiles{0};
+int opt_block_tiles() { return g_opt_block_tiles.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_spin_ns{40};  // measured: ~3% faster than a pure spin under the power cap
+int opt_spin_ns() { return g_opt_spin_ns.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_epi_sleep_ns{0};
+int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns.load(std::memory_order_relaxed); }
 
-static int g_opt_concat_staged = 1;
-int opt_concat_staged() { return g_opt_concat_staged; }
+static std::atomic<int> g_opt_concat_staged{1};
+int opt_concat_staged() { return g_opt_concat_staged.load(std::memory_order_relaxed); }
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Optional device-side timing of the dominant kernel (the tcgen05 filter): when
 // enabled, knn_search brackets that one launch with CUDA events on its stream.
+// The event table is guarded by a mutex (searches may come from several host threads).
 constexpr int kTimingSlots = 256;
+static std::mutex g_timing_mu;
 static bool g_timing = false;
 static cudaEvent_t g_ev[kTimingSlots][2];
 static bool g_ev_made = false;
@@ -198,15 +205,17 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
   KNN_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), stream));
   KNN_CUDA(cudaMemsetAsync(w.seg_flag, 0, w.seg_flag_bytes, stream));
-  const bool timed = g_timing && g_ev_n < kTimingSlots;
-  if (timed) KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][0], stream));
+  int ev_slot = -1;
+  {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    if (g_timing && g_ev_n < kTimingSlots) ev_slot = g_ev_n++;
+  }
+  const bool timed = ev_slot >= 0;
+  if (timed) KNN_CUDA(cudaEventRecord(g_ev[ev_slot][0], stream));
   int rc = launch_knn_filter(qh, n_query, ph, n_pool, dim_pad, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
                              w.seg_kth, w.seg_flag, mask_lo, mask_hi, q_err, p_err, w.counters + 12, stream);
   if (rc) return rc;
-  if (timed) {
-    KNN_CUDA(cudaEventRecord(g_ev[g_ev_n][1], stream));
-    ++g_ev_n;
-  }
+  if (timed) KNN_CUDA(cudaEventRecord(g_ev[ev_slot][1], stream));
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
                           index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, mask_lo, mask_hi,
                           q_err, p_err, stream);
@@ -228,45 +237,46 @@ int knnsvc_set_option(const char* name, int value) {
   KNN_CHECK_ARG(name != nullptr, -1, "set_option: null name");
   if (strcmp(name, "cta_group") == 0) {
     KNN_CHECK_ARG(value == 1 || value == 2, -1, "set_option: cta_group must be 1 or 2");
-    g_opt_cta_group = value;
+    g_opt_cta_group.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "spin_sleep_ns") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 60000, -1, "set_option: spin_sleep_ns out of range");
-    g_opt_spin_ns = value;
+    g_opt_spin_ns.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "epi_sleep_ns") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 60000, -1, "set_option: epi_sleep_ns out of range");
-    g_opt_epi_sleep_ns = value;
+    g_opt_epi_sleep_ns.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "concat_staged") == 0) {
-    g_opt_concat_staged = value != 0;
+    g_opt_concat_staged.store(value != 0, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "filter_flags") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 7, -1, "set_option: filter_flags out of range");
-    g_opt_filter_flags = value;
+    g_opt_filter_flags.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "weight_fit_cluster") == 0) {
-    g_opt_wf_cluster = value != 0;
+    g_opt_wf_cluster.store(value != 0, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "block_tiles") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: block_tiles out of range");
-    g_opt_block_tiles = value;
+    g_opt_block_tiles.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "bf16_operands") == 0) {
-    g_opt_bf16 = value != 0;
+    g_opt_bf16.store(value != 0, std::memory_order_relaxed);
     return 0;
   }
   KNN_CHECK_ARG(false, -1, "set_option: unknown option '%s'", name);
 }
 
 int knnsvc_filter_timing(int enable) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
   if (enable && !g_ev_made) {
     for (int i = 0; i < kTimingSlots; ++i)
       for (int j = 0; j < 2; ++j) KNN_CUDA(cudaEventCreate(&g_ev[i][j]));
@@ -278,6 +288,7 @@ int knnsvc_filter_timing(int enable) {
 }
 
 int knnsvc_filter_timing_collect(float* ms_host, int max_n) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
   int n = g_ev_n < max_n ? g_ev_n : max_n;
   for (int i = 0; i < n; ++i) {
     if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) return -1;

@@ -6,7 +6,31 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 namespace knnsvc {
+
+// Function attributes (cudaFuncSetAttribute), SM counts and occupancy answers belong to a DEVICE,
+// not to the process: every cache of one is an array indexed by the current device.  slot() is
+// nullptr when the device index is unknown or out of range — the caller then does the work every time.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  std::atomic<int> v[kMaxDevices];
+  std::atomic<int>* slot() {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return nullptr;
+    return &v[d];
+  }
+};
+// Opt a kernel in to `bytes` of dynamic shared memory on the current device (once per device and size).
+#define KNN_SMEM_ATTR(cache, func, bytes)                                                                   \
+  do {                                                                                                      \
+    std::atomic<int>* _s = (cache).slot();                                                                  \
+    if (!_s || _s->load(std::memory_order_acquire) < (int)(bytes)) {                                        \
+      KNN_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      if (_s) _s->store((int)(bytes), std::memory_order_release);                                           \
+    }                                                                                                       \
+  } while (0)
 
 void set_error(const char* fmt, ...);
 

@@ -408,11 +408,8 @@ int launch_concat_cost_staged(const int64_t* idx, const float* src, const float*
                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                               int64_t* out_idx, cudaStream_t stream) {
   const size_t smem = concat_staged_smem_bytes(dim);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    KNN_CUDA(cudaFuncSetAttribute(concat_cost_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  static PerDevice attr;
+  KNN_SMEM_ATTR(attr, concat_cost_staged_kernel, smem);
   concat_cost_staged_kernel<<<n_utt, CS_THREADS, smem, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0,
                                                                  concat_weight, utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();

@@ -742,16 +742,15 @@ int make_half_map(CUtensorMap* map, const void* base, int64_t rows, int dim_pad,
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      cached = v;
-    else
-      cached = 148;
-  }
-  return cached;
+  static PerDevice cached;   // SM count of each device (0 = not asked yet)
+  std::atomic<int>* slot = cached.slot();
+  if (slot && slot->load(std::memory_order_relaxed) > 0) return slot->load(std::memory_order_relaxed);
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+    v = 148;
+  if (slot) slot->store(v, std::memory_order_relaxed);
+  return v;
 }
 
 }  // namespace
@@ -810,12 +809,8 @@ static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, in
                           float* seg_top, float* seg_kth, int* seg_flag, const int64_t* mask_lo,
                           const int64_t* mask_hi, const float* q_err, const float* p_err, int* unit_counter,
                           cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(knn_filter_kernel<CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<CTAS>::SMEM_BYTES));
-    attr_done = true;
-  }
+  static PerDevice smem_attr;   // one per template instance
+  KNN_SMEM_ATTR(smem_attr, (knn_filter_kernel<CTAS, MASKED>), Cfg<CTAS>::SMEM_BYTES);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(NUM_THREADS);

@@ -421,11 +421,8 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
   if (gy < 1) gy = 1;
   size_t smem = (size_t)EX_Q * dim * sizeof(float) + (size_t)EX_WARPS * EX_Q * k * (sizeof(double) + sizeof(int64_t));
   KNN_CHECK_ARG(smem <= 200 * 1024, -2, "knn_exact: dim %d too large for shared memory", dim);
-  static bool attr_done = false;
-  if (!attr_done) {
-    KNN_CUDA(cudaFuncSetAttribute(knn_exact_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  static PerDevice attr;
+  KNN_SMEM_ATTR(attr, knn_exact_partial_kernel, 200 * 1024);
   dim3 grid(n_chunks, gy);
   knn_exact_partial_kernel<<<grid, EX_WARPS * 32, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, row_list,
                                                                    row_count_dev, row_count_host, slot_base,

@@ -625,18 +625,19 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
     max_len = len > max_len ? len : max_len;
   }
   const int64_t np_arg = n_pairs_total > 0 ? n_pairs_total : 1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  {
+    static PerDevice a0, a1, a2, a3;
     const int max_bytes = WF_STATE_FRAMES * 28 * (int)sizeof(float);   // 212.8 KB > 10240 * 16 B
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcMaxSmem));
-    KNN_CUDA(cudaFuncSetAttribute(weight_fit_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcMaxSmem));
-    attr_done = true;
+    KNN_SMEM_ATTR(a0, weight_fit_kernel<false>, max_bytes);
+    KNN_SMEM_ATTR(a1, weight_fit_kernel<true>, max_bytes);
+    KNN_SMEM_ATTR(a2, weight_fit_cluster_kernel<false>, kWcMaxSmem);
+    KNN_SMEM_ATTR(a3, weight_fit_cluster_kernel<true>, kWcMaxSmem);
   }
   // few, long utterances: a cluster per utterance (its state has to fit the cluster's shared memory,
   // and the device — or the SM partition this context runs in — has to be able to host a cluster)
-  static int cluster_ok = -1;
+  static PerDevice cluster_cache;   // per device: 0 = not asked yet, 1 = no, 2 = yes
+  std::atomic<int>* cl_slot = cluster_cache.slot();
+  int cluster_ok = cl_slot ? cl_slot->load(std::memory_order_relaxed) - 1 : -1;
   if (cluster_ok < 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(WC_C);
@@ -653,6 +654,7 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
     const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, weight_fit_cluster_kernel<false>, &cfg);
     if (e != cudaSuccess) (void)cudaGetLastError();
     cluster_ok = (e == cudaSuccess && n_clusters >= 1) ? 1 : 0;
+    if (cl_slot) cl_slot->store(cluster_ok + 1, std::memory_order_relaxed);
   }
   if (cluster_ok && opt_weight_fit_cluster() && n_utt * WC_C <= 144 && min_len >= WC_MIN_FRAMES &&
       wc_smem_bytes(max_len, false) <= (size_t)kWcMaxSmem) {

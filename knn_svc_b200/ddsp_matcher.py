@@ -74,7 +74,12 @@ class KNeighborsVC(nn.Module):
 
     @torch.inference_mode()
     def get_features(self, path, weights=None, vad_trigger_level=0, return_audio=False):
-        """WavLM features (seq_len, dim) of a wav path or tensor, optional VAD trim (reference :438-518)."""
+        """WavLM features (seq_len, dim) of a wav path or tensor, optional VAD trim (reference :438-518).
+        One deliberate deviation: the reference aligns the VAD cut to the 320-sample hop with
+        `x_front_trim[extra_cut:]` (:468, :479), which slices dim 0 — the CHANNEL axis of the [1, T]
+        waveform — and leaves an empty tensor whenever the cut is not a multiple of the hop (the next
+        call then crashes).  Here the SAMPLE axis is sliced, which is what the surrounding code
+        (`lstrip_len += extra_cut`) means."""
         import torchaudio
         import torchaudio.transforms as T
         if weights is None:
@@ -97,7 +102,7 @@ class KNeighborsVC(nn.Module):
                 trimmed = vad(w)
                 cut = w.shape[-1] - trimmed.shape[-1]
                 if cut % self.hop_length != 0:
-                    trimmed = trimmed[self.hop_length - cut % self.hop_length:]
+                    trimmed = trimmed[..., self.hop_length - cut % self.hop_length:]
                 return trimmed
             x = torch.flip(front_trim(torch.flip(front_trim(x), (-1,))), (-1,))
         wav = x.to(self.device)

@@ -27,9 +27,19 @@ def _dev(t: torch.Tensor, what: str):
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
-    """fp32 contiguous view/copy.  float64 inputs (the reference's real inference
-    path) hold fp32-representable values, so the cast is lossless there."""
-    if t.dtype != torch.float32:
+    """fp32 contiguous view/copy.  The kernels take fp32 rows.  float64 inputs are the reference's
+    real inference path (a float64 one-hot layer weighting promotes fp32 WavLM features
+    to float64 CONTAINERS of fp32-representable values), so the narrowing is lossless there — and
+    that is checked: a float64 tensor that does not survive the round trip through fp32 raises
+    instead of being silently rounded (the reference would have computed on the fp64 values).
+    fp16 / bf16 inputs widen losslessly."""
+    if t.dtype == torch.float64:
+        t32 = t.to(torch.float32)
+        if t.numel() and not torch.equal(t32.to(torch.float64), t):
+            raise ValueError("float64 input holds values that are not representable in float32; "
+                             "the CUDA path computes on fp32 rows (SURVEY D8) and will not round them silently")
+        t = t32
+    elif t.dtype != torch.float32:
         t = t.to(torch.float32)
     return t.contiguous()
 
@@ -108,14 +118,23 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (the search never allocates; the library's only internal
-    allocation is K5's small per-call scratch, from its own stream-ordered pool)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, CUDA stream, host thread): two searches on different
+    streams or from different threads never share candidate logs / counters, and a buffer is only
+    ever used on the stream it was allocated on.  (The search itself never allocates; the library's
+    only internal allocation is K5's small per-call scratch, from its own stream-ordered pool.)"""
+    import threading
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(index).cuda_stream, threading.get_ident())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def release_workspaces():
+    """Drop every cached search scratch buffer (they are grow-only otherwise)."""
+    _ws_cache.clear()
 
 
 def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0,

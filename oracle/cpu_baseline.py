@@ -14,19 +14,30 @@ import time
 import torch
 
 
-def _cosine_dist_chunk(src, pool, pool_norms):
-    src_norms = torch.linalg.vector_norm(src, dim=-1)
-    d = torch.cdist(src[None], pool[None], p=2)[0]
-    dot = (-(d * d) + src_norms[:, None] ** 2 + pool_norms[None] ** 2) / 2
-    return 1 - dot / (src_norms[:, None] * pool_norms[None])
+def _fast_cosine_dist(src, pool, increment=20):
+    """lib_ongaku_test.py:148-175, call for call: BOTH norm vectors are computed inside the function,
+    i.e. the pool norms are recomputed on every call — and the matcher calls it once per 20-row chunk
+    of the query (ddsp_prematch_dataset.py:1200), so the pool is re-read for its norms every chunk."""
+    src_norms_all = torch.norm(src, p=2, dim=-1)
+    pool_norms = torch.norm(pool, p=2, dim=-1)
+    out = []
+    for a in range(0, len(src), increment):
+        sn, sf = src_norms_all[a:a + increment], src[a:a + increment]
+        dot = -torch.cdist(sf[None], pool[None], p=2)[0] ** 2 + sn[:, None] ** 2 + pool_norms[None] ** 2
+        dot /= 2
+        d = 1 - (dot / (sn[:, None] * pool_norms[None]))
+        if torch.sum(torch.isnan(d)) > 0:
+            raise SystemExit("containing nan")
+        out.append(d)
+    return torch.cat(out, dim=0)
 
 
 def match_sample(query: torch.Tensor, pool: torch.Tensor, k_search: int = 32, k_mix: int = 4, increment: int = 20):
-    """One pass of the reference's matcher over `query` (CPU tensors)."""
-    pool_norms = torch.linalg.vector_norm(pool, dim=-1)
+    """One pass of the reference's matcher over `query` (CPU tensors): the chunk-20 loop of
+    ddsp_prematch_dataset.py:1196-1206 calling fast_cosine_dist on each chunk."""
     nbrs = []
     for a in range(0, len(query), increment):
-        dists = _cosine_dist_chunk(query[a:a + increment], pool, pool_norms)
+        dists = _fast_cosine_dist(query[a:a + increment], pool)
         nbrs.append(dists.topk(k=min(k_search, pool.shape[0]), dim=-1, largest=False).indices)
     nbrs = torch.cat(nbrs, dim=0)
     idx = nbrs[:, :k_mix]

@@ -61,3 +61,26 @@ def test_vocode_matches_the_reference(golden_pm):
     assert np.array_equal(knn.vocode(c).numpy(), golden_pm["a12_vocode_plain"])
     assert np.array_equal(knn.vocode(c, f0v).numpy(), golden_pm["a12_vocode_f0"])
     assert np.array_equal(knn.vocode(c, f0v, hv).numpy(), golden_pm["a12_vocode_mix"])
+
+
+def test_get_features_vad_trim_keeps_the_sample_axis():
+    """the reference slices dim 0 (channels) when it aligns the VAD cut to the hop
+    (ddsp_matcher.py:468,479), which empties the waveform whenever the cut is not a multiple of 320.
+    Ours slices the sample axis: features come back, and each side loses the VAD's own cut rounded UP
+    to a whole number of hops."""
+    import torchaudio.transforms as T
+    knn, wavlm = _knn()
+    g = torch.Generator().manual_seed(9)
+    t = torch.arange(32000) / 16000.0
+    voiced = 0.5 * torch.sin(2 * np.pi * 220 * t) * (1 + 0.5 * torch.sin(2 * np.pi * 3 * t)) \
+        + 0.2 * torch.randn(32000, generator=g)
+    wav = torch.cat([1e-4 * torch.randn(7777, generator=g), voiced, 1e-4 * torch.randn(3000, generator=g)])
+    vad = T.Vad(sample_rate=16000, trigger_level=7)
+    front = len(wav) - vad(wav[None]).shape[-1]
+    assert front > 0 and front % 320 != 0, "fixture: the raw VAD cut must not be hop-aligned"
+    feats, audio = knn.get_features(wav, None, vad_trigger_level=7, return_audio=True)
+    assert audio.dim() == 2 and audio.shape[0] == 1 and audio.shape[1] > 16000
+    cut = len(wav) - audio.shape[1]
+    assert cut >= front + (320 - front % 320)
+    assert torch.equal(audio[0, :100], wav[front + (320 - front % 320):][:100])     # front edge: hop-aligned cut
+    assert feats.shape[0] == (audio.shape[1] - 400) // 320 + 1
