@@ -1,16 +1,27 @@
-"""bench.py — headline benchmark of the B200-native kNN-SVC matcher.
+"""bench.py — benchmarks of the B200-native kNN-SVC matcher hot path.
 
-Metric (BASELINE.json): query frames/s matched against an N-frame pool, top-k = 4.
-Workload at every N: BASELINE config "100k-frame query batch vs 10M-frame pool,
-1024-dim synthetic WavLM-layer features" (cfg 4).  The pool is sharded by frame
-over the N GPUs (strong scaling: the total work is fixed), per-shard top-k lists
-are exchanged with one NCCL all-gather and merged, and the matched features are
-the k=4 gather-mean (partial sums per shard + one all-reduce at N > 1).
+Headline (default, what the driver runs): BASELINE cfg 4 — query frames/s matched against a
+10M-frame pool, top-k = 4, 100k-frame query batch, 1024-dim synthetic WavLM-layer features.  The pool
+is sharded by frame over the N GPUs (strong scaling: the total work is fixed); per-shard top-k lists
+are exchanged with ONE NCCL all-gather and merged; the matched features are produced by the rank
+that owns the query rows, its gather kernel reading the selected pool rows from the GPUs that hold
+them over NVLink (knn_svc_b200/sharded.py).
 
-One step = norms + fp16 operand preparation of the query batch AND the pool shard,
-the fused tcgen05 distance/top-k, the exact re-scoring, the merge and the gather-mean.
+One step = norms + fp16 operand preparation of the query batch AND of the pool shard, the fused
+tcgen05 distance/top-k, the exact re-scoring, the merge and the gather-mean.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--no-verify]
+
+Other workloads (same JSON contract, run by hand; outputs under profiles/):
+    cfg4g     cfg 4 on generator G (WavLM-like AR(1) rows with a shared mean)
+    cfg4k32   cfg 4 searched at k=32 and mixed from the first 4, as the live path does
+              (ddsp_prematch_dataset.py:1203,1246);  cfg4gk32: both
+    cfg3      3000 query frames vs a 30k-frame pool, k=4 (replicas at N>1: one batch per GPU)
+    cfg1/cfg2 one 3001-frame utterance vs a 3001-frame pool through match_utterance + harmonic bank,
+              no_post_opt / post_opt_0.2 + prioritize_f0 (replicas at N>1)
+    cfg5      dataset->dataset conversion, OpenSinger_test_to_nus-smc-corpus_48 split shape: 7038
+              (utterance, target speaker) pairs, 30k-frame target pools, post_opt_0.2, pairs dealt
+              over the ranks with no communication
 """
 from __future__ import annotations
 
@@ -28,31 +39,49 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 DIM = 1024
-TOPK = 4
-N_QUERY = 100_000
-N_POOL = 10_000_000
-METRIC = "query_frames_per_s_vs_10M_frame_pool_topk4"
 UNIT = "query frames/s"
+SEARCH_WORKLOADS = {
+    # name: (query frames, pool frames, search k, generator, sharded over ranks?)
+    "cfg4": (100_000, 10_000_000, 4, "randn", True),
+    "cfg4g": (100_000, 10_000_000, 4, "ar1", True),
+    "cfg4k32": (100_000, 10_000_000, 32, "randn", True),
+    "cfg4gk32": (100_000, 10_000_000, 32, "ar1", True),
+    "cfg3": (3_000, 30_000, 4, "randn", False),
+    "cfg3g": (3_000, 30_000, 4, "ar1", False),
+}
+MIX_K = 4
+# BASELINE cfg 5: data_splits/OpenSinger_test_to_nus-smc-corpus_48.txt — rows with label "0":
+# 2346 source utterances of 4 source speakers, each converted to 3 of the 4 target speakers.
+CFG5_SRC_UTTS = {"WomanRaw_47": 677, "ManRaw_26": 639, "WomanRaw_46": 532, "ManRaw_27": 498}
+CFG5_TARGETS = {"WomanRaw_47": ("MCUR", "JLEE", "MPUR"), "ManRaw_26": ("JLEE", "MCUR", "MPUR"),
+                "WomanRaw_46": ("MPUR", "JLEE", "SAMF"), "ManRaw_27": ("MPUR", "SAMF", "MCUR")}
+CFG5_POOL_FRAMES = 30_000
 
 
-def _filter_traffic(T, n_shard):
-    """DRAM bytes of ONE filter launch from the committed ncu capture of this workload
-    (profiles/filter_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum); None when the
-    capture is for another shape."""
+def _metric(name, k):
+    if name.startswith("cfg4"):
+        return f"query_frames_per_s_vs_10M_frame_pool_topk{MIX_K}"
+    return f"query_frames_per_s_{name}"
+
+
+def _traffic(name, T, n_shard):
+    """DRAM bytes of ONE filter launch from the committed ncu captures (profiles/filter_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per launch, one entry per captured shape); None when
+    this shape was not captured."""
     f = ROOT / "profiles" / "filter_traffic.json"
     if not f.exists():
         return None
     d = json.loads(f.read_text())
-    if d.get("query_frames") == T and d.get("pool_frames_per_gpu") == n_shard:
-        return d.get("dram_bytes_per_launch")
+    for e in d.get("captures", [d]):
+        if e.get("query_frames") == T and e.get("pool_frames_per_gpu") == n_shard and e.get("workload", "cfg4") == name:
+            return e.get("dram_bytes_per_launch")
     return None
 
 
 def _peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
-        d = json.loads(f.read_text())
-        return d, "measured"
+        return json.loads(f.read_text()), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -104,6 +133,31 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _workload_string(name, T, NP, k):
+    if name.startswith("cfg4") or name.startswith("cfg3"):
+        gen = SEARCH_WORKLOADS[name][3]
+        s = f"{name[:4]}: {T} query frames vs {NP}-frame pool, {DIM}-dim, topk={MIX_K}"
+        if k != MIX_K:
+            s += f" (searched at k={k}, mixed from the first {MIX_K})"
+        if gen != "randn":
+            s += ", generator G (AR(1) + shared mean, WavLM-like)"
+        return s
+    return name
+
+
+def _search_config(name, T, NP, k, world, exchange):
+    """the `config` object of a search workload — the SAME for our arm and the reference arm"""
+    shard = SEARCH_WORKLOADS[name][4]
+    n_shard = NP // world if shard else NP
+    return {"workload": _workload_string(name, T, NP, k), "pool_frames": NP, "query_frames": T, "dim": DIM,
+            "topk": MIX_K, "search_k": k,
+            "parallelism": (f"pool sharded by frame x{world}, NCCL all-gather top-k merge, peer-memory gather "
+                            f"({exchange})") if shard else f"{world} independent replicas",
+            "l2": "inputs (pool shard) exceed L2" if n_shard * DIM * 2 > 126e6 else
+                  "pool fits L2: every step rewrites the 2 x pool-size fp16 operand + norms first (prepare), no explicit flush",
+            "step": "prepare(query)+prepare(pool)+knn+merge+gather-mean"}
+
+
 # ----------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -111,19 +165,26 @@ def run_reference(args):
         return 0
     if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
         del os.environ["OMP_NUM_THREADS"]               # torchrun's default; the CPU arm may use every host core
-    import torch
+    import torch  # noqa: F401
     from oracle import cpu_baseline                     # the one place bench.py executes oracle/
-    nq, npool = args.cpu_queries, args.cpu_pool
+    name = args.workload
+    if name not in SEARCH_WORKLOADS:
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU arm times the search workloads; {name} is "
+                          "timed by tools/bench_torch_cpu.py"}))
+        return 0
+    T, NP, k, gen, _ = SEARCH_WORKLOADS[name]
+    T, NP = args.queries or T, args.pool or NP
+    nq, npool = min(args.cpu_queries, T), min(args.cpu_pool, NP)
     sec, threads = cpu_baseline.time_sample(nq, npool, DIM, steps=args.steps, warmup=args.warmup)
-    # the reference's cost is linear in T*Np: scale the sample's pool to the 10M-frame pool
-    value = nq / (sec * (N_POOL / npool))
-    sample = (f"{nq} query frames x {npool} pool frames x {DIM} dims per step, fp32, torch CPU; "
-              f"extrapolated linearly in pool size to {N_POOL} frames")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    # the reference's cost is linear in T*Np: scale the sample's pool to the full pool
+    value = nq / (sec * (NP / npool))
+    sample = (f"{nq} query frames x {npool} pool frames x {DIM} dims per step, fp32, torch CPU, the reference's "
+              f"chunk-20 loop incl. its per-chunk pool norms; extrapolated linearly in pool size to {NP} frames")
+    line = {"impl": "reference", "metric": _metric(name, k), "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg4: {N_QUERY} query frames vs {N_POOL}-frame pool, {DIM}-dim, topk={TOPK}",
-                       "pool_frames": N_POOL, "query_frames": N_QUERY, "dim": DIM, "topk": TOPK},
+            "scaling": "strong" if SEARCH_WORKLOADS[name][4] else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": _search_config(name, T, NP, k, args.gpus, args.exchange),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -131,182 +192,393 @@ def run_reference(args):
     return 0
 
 
-# ----------------------------------------------------------------------------- our arm
+# ----------------------------------------------------------------------------- helpers of our arm
+class Env:
+    """process-wide state of one bench run: rank, device, process group, library handle"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from knn_svc_b200 import _lib
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # (NCCL prints its "NCCL version ..." banner on stdout at communicator creation, whatever
+            # NCCL_DEBUG says; the JSON line below is the LAST line of rank 0's stdout)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def timed(self, fn, steps, warmup):
+        """W untimed steps, then exactly K steps between two barriers + synchronize; CUDA events;
+        max over ranks.  Returns (ms per step, clocks on rank 0, launches, filter ms per launch)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        self.lib.knnsvc_filter_timing(1)
+        launches0 = self.lib.knnsvc_launch_count()
+        sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        clocks = sampler.stop() if self.rank == 0 else None
+        launches = self.lib.knnsvc_launch_count() - launches0
+        import ctypes
+        buf = (ctypes.c_float * 256)()
+        n_t = self.lib.knnsvc_filter_timing_collect(ctypes.cast(buf, ctypes.c_void_p), 256)
+        self.lib.knnsvc_filter_timing(0)
+        filter_ms = sum(buf[i] for i in range(n_t)) / max(n_t, 1)
+        filter_total = sum(buf[i] for i in range(n_t)) / max(steps, 1)
+        ms, fms, ftot = self.max_over_ranks([e0.elapsed_time(e1) / steps, filter_ms, filter_total])
+        return ms, clocks, int(launches), fms, ftot
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_rows(env, n, gen, seed, seg_len):
+    """[n, 1024] fp32 rows on the device: i.i.d. N(0,1) or generator G"""
+    torch = env.torch
+    from knn_svc_b200 import synth
+    if gen == "ar1":
+        return synth.ar1_frames_device(n, DIM, seed=seed, device=env.dev, seg_len=seg_len)
+    g = torch.Generator(device=env.dev); g.manual_seed(seed)
+    x = torch.empty((n, DIM), device=env.dev)
+    for a in range(0, n, 1 << 20):
+        b = min(n, a + (1 << 20))
+        x[a:b] = torch.randn((b - a, DIM), device=env.dev, generator=g)
+    return x
+
+
+# ----------------------------------------------------------------------------- search workloads (cfg 3, cfg 4 family)
+def run_search(args, env):
+    torch, dist = env.torch, env.dist
+    from knn_svc_b200 import ops, sharded
+    from knn_svc_b200.ddsp_matcher import KNeighborsVC
+    name = args.workload
+    T, NP, k, gen, shard = SEARCH_WORKLOADS[name]
+    T, NP = args.queries or T, args.pool or NP
+    world, rank, dev = env.world, env.rank, env.dev
+    if shard:
+        lo, hi = sharded.shard_bounds(NP, world, rank)
+    else:
+        lo, hi = 0, NP                                   # replicas: every rank matches its own batch against its own pool
+    n_shard = hi - lo
+    # synthetic inputs, resident in HBM (query seed 0 replicated when sharded; pool shard seed 1000+rank)
+    query = make_rows(env, T, gen, 0 if shard else 7 + rank, 200)
+    pool_rows = make_rows(env, n_shard, gen, 1000 + rank, 500)
+    # replica workloads never communicate: their pool is built undistributed
+    pool = sharded.ShardedPool(pool_rows, lo, exchange=args.exchange, distributed=None if shard else False)
+    knn_vc = KNeighborsVC(None, None, None, device=dev)
+    query_host = torch.empty((T, DIM), dtype=torch.float32).pin_memory()
+    query_host.copy_(query)
+    q_lo, q_hi = sharded.query_slice(T, world, rank) if shard else (0, T)
+    feats_host = torch.empty((max(q_hi - q_lo, 1), DIM), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def match_step():
+        """the hot path on device tensors; the matched features of this rank's query rows"""
+        pool.reprepare()
+        return pool.match(query, k, gather="slice", check=False, mix_k=MIX_K)
+
+    ms_step, clocks, launches, filter_ms, filter_total = env.timed(match_step, args.steps, args.warmup)
+
+    # ---- end-to-end leg through the matcher API: pinned host query batch in, matched features out to
+    # pinned host memory; pool resident and prepared (built once, as get_matching_set does)
+    def e2e_step():
+        if k == MIX_K:
+            f = knn_vc.match(query_host, pool, topk=MIX_K, without_vocode=True, gather="slice")
+        else:
+            f = pool.match(query_host, k, gather="slice", mix_k=MIX_K).feats
+        feats_host[:q_hi - q_lo].copy_(f, non_blocking=True)
+
+    ms_e2e = env.timed(e2e_step, args.steps, max(1, args.warmup // 2))[0]
+
+    verify = None if args.no_verify else verify_search(env, pool, query, k, shard, lo, n_shard, NP)
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        flops = 2.0 * T * n_shard * DIM                     # algorithmic FLOPs of one filter launch (per GPU)
+        achieved = flops / (filter_ms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        long_step = ms_step > 200.0
+        if not long_step:
+            peak = float(peaks["bf16_tflops"])
+        roofline = {"bound": "tensor", "kernel": "knn_filter_kernel (tcgen05 fp16, fp32 accumulate)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": f"{peak_src} cuBLAS bf16, " + ("sustained (kernel timed inside a long step)" if long_step
+                                                                   else "burst (short step)"),
+                    "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
+                    "kernel_ms": filter_ms, "kernel_share_of_step": filter_total / ms_step,
+                    "algorithmic_flops_per_launch": flops, "traffic": _traffic(name, T, n_shard),
+                    "traffic_note": "DRAM bytes per launch from the committed ncu capture of this shape "
+                                    "(profiles/filter_traffic.json), null if this shape was not captured; the kernel is "
+                                    "tensor-bound, operands stream from L2"}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
+            from oracle import cpu_baseline              # checker/baseline only, never the measured path
+            nq, npool = min(args.cpu_queries, T), min(args.cpu_pool, NP)
+            sec, threads = cpu_baseline.time_sample(nq, npool, DIM, steps=1, warmup=0)
+            v = nq / (sec * (NP / npool))
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{nq} query frames x {npool} pool frames, fp32, torch CPU, the reference's chunk-20 loop "
+                             f"incl. its per-chunk pool norms (lib_ongaku_test.py:150-151), {sec:.1f} s; extrapolated "
+                             f"linearly in pool size to {NP} frames"}
+        total_q = T if shard else T * world
+        line = {"metric": _metric(name, k), "value": total_q / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if shard else "weak", "vs_baseline": None,
+                "dtype": "f16 tensor-core filter (f32 accumulate) + f32/f64 exact re-score", "data": "synthetic",
+                "config": _search_config(name, T, NP, k, world, args.exchange),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": total_q * DIM * 4, "d2h_bytes_per_step": total_q * DIM * 4,
+                        "api": "KNeighborsVC.match(query_host, ShardedPool, topk=4, without_vocode=True, gather='slice')"
+                               if k == MIX_K else "ShardedPool.match(query_host, k=32, mix_k=4)",
+                        "note": "pinned host query batch in, matched features out to pinned host memory, zero-norm "
+                                "validation included (bytes are totals over ranks: at N>1 each rank moves its 1/N "
+                                "slice over PCIe and the batch is replicated over NVLink); pool resident and prepared "
+                                "in HBM (built once, as get_matching_set does)"},
+                "gpu_launches": launches, "clocks": clocks, "verify": verify}
+        print(json.dumps(line))
+    pool.close()
+    return 0
+
+
+def verify_search(env, pool, query, k, shard, lo, n_shard, NP, n_rows=64):
+    """Outside the timed region, on every rank: the merged (distances, indices) of a sample of
+    query rows against the exact CUDA-core fp64 brute-force kernel run over every shard (an
+    independent decision procedure), and this rank's matched features against a torch
+    partial-sum + all-reduce of the same rows."""
+    torch, dist = env.torch, env.dist
+    from knn_svc_b200 import ops
+    sp = pool
+    T = query.shape[0]
+    rows = torch.linspace(0, T - 1, min(n_rows, T), device=env.dev).long().unique()
+    qs = ops.prepare_rows(query[rows].contiguous(), check=False)
+    m = sp.match(qs, k, gather="all", check=False, mix_k=MIX_K)
+    de, ie = ops.knn_exact(qs, sp.prepared, k, index_offset=lo)
+    if shard and env.world > 1:
+        from knn_svc_b200 import sharded
+        gd, gi = sharded.all_gather_topk(de, ie)
+        de, ie = ops.merge_topk(gd, gi)
+    gap = 1e-5
+    d = de.double()
+    untied = torch.ones_like(ie, dtype=torch.bool)
+    untied[:, 1:] &= (d[:, 1:] - d[:, :-1]) > gap
+    untied[:, :-1] &= (d[:, 1:] - d[:, :-1]) > gap
+    idx_ok = bool((m.idx[untied] == ie[untied]).all())
+    dist_err = float((m.dist - de).abs().max())
+    # features: sum over the rows this shard holds, all-reduced
+    i4 = m.idx[:, :MIX_K]
+    local = (i4 >= lo) & (i4 < lo + n_shard)
+    part = (sp.synth[(i4 - lo).clamp(0, n_shard - 1)] * (local.float() / MIX_K)[..., None]).sum(1)
+    if shard and env.world > 1:
+        dist.all_reduce(part)
+    scale = float(part.abs().max())
+    feat_err = float((m.feats - part).abs().max()) / max(scale, 1e-30)
+    ok = idx_ok and dist_err < 2e-6 and feat_err < 2e-6
+    flags = env.max_over_ranks([0.0 if ok else 1.0, dist_err, feat_err, 1.0 - float(untied.float().mean())])
+    res = {"rows": int(len(rows)), "ok_on_every_rank": flags[0] == 0.0, "untied_slot_indices_equal_exact_kernel": idx_ok,
+           "max_abs_dist_err": flags[1], "max_rel_feats_err_vs_allreduce": flags[2], "tied_slot_fraction": flags[3],
+           "against": "knn_exact (CUDA-core fp64 brute force) over every shard + fp32 merge; features vs torch partial "
+                      "sums + all-reduce"}
+    if flags[0] != 0.0:
+        raise RuntimeError(f"verification failed: {res}")
+    return res
+
+
+# ----------------------------------------------------------------------------- utterance pipelines (cfg 1, 2, 5)
+def _pipeline_pool(env, n_frames, seed):
+    torch = env.torch
+    from knn_svc_b200 import synth
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    rows = synth.ar1_frames_device(n_frames, DIM, seed=seed, device=env.dev, seg_len=500)
+    f0 = torch.from_numpy(synth.f0_track(n_frames, seed=seed + 1))
+    harm = torch.from_numpy(synth.harmonics_pool(2000, seed=seed + 2)).repeat(n_frames // 2000 + 1, 1)[:n_frames]
+    return pm.MatchingPool(rows, rows, f0, harm, env.dev)
+
+
+def run_single_utterance(args, env):
+    """cfg 1 / cfg 2: one 3001-frame utterance against a 3001-frame pool, whole matcher + harmonic
+    bank (what special_match hands the vocoder); N > 1 = N replicas."""
+    torch = env.torch
+    from knn_svc_b200 import synth
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    post_opt = "no_post_opt" if args.workload == "cfg1" else "post_opt_0.2"
+    T = NP = 3001
+    pool = _pipeline_pool(env, NP, 500 + env.rank)
+    q = synth.ar1_frames_device(T, DIM, seed=40 + env.rank, device=env.dev, seg_len=200)
+    f0q = torch.from_numpy(synth.f0_track(T, seed=41 + env.rank))
+    q_host = q.cpu().pin_memory()
+    sig_host = torch.empty((T * 320,), dtype=torch.float32).pin_memory()
+    feats_host = torch.empty((T, DIM), dtype=torch.float32).pin_memory()
+
+    def step(src=q):
+        r = pm.match_utterance(src, f0q, pool, post_opt=post_opt, ckpt_type="mix", prioritize_f0=True)
+        sig = pm.get_bulk_dsp_choral(r["shifted_f0"].to(env.dev)[None, :, None], r["harmonics"][None])
+        return r, sig
+
+    def e2e_step():
+        r, sig = step(q_host)
+        feats_host.copy_(r["out_feats"], non_blocking=True)
+        sig_host.copy_(sig.reshape(-1), non_blocking=True)
+
+    ms_step, clocks, launches, _, _ = env.timed(step, args.steps, args.warmup)
+    ms_e2e = env.timed(e2e_step, args.steps, max(1, args.warmup // 2))[0]
+    if env.rank == 0:
+        total = T * env.world
+        line = {"metric": f"query_frames_per_s_{args.workload}", "value": total / (ms_step * 1e-3), "unit": UNIT,
+                "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 filter + f32/f64",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: one {T}-frame utterance vs {NP}-frame pool, {post_opt}, prioritize_f0, "
+                                       "ckpt_type=mix, + harmonic bank (960 320 samples)",
+                           "l2": "whole working set is L2-resident by nature of the workload (25 MB); no flush",
+                           "parallelism": f"{env.world} independent replicas"},
+                "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": T * DIM * 4 * env.world, "d2h_bytes_per_step": (T * DIM * 4 + T * 320 * 4) * env.world,
+                        "api": "match_utterance(host query) + get_bulk_dsp_choral"},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    return 0
+
+
+def cfg5_jobs(world, rank, seed=0):
+    """(target speaker -> list of (source utterance id, length)) for THIS rank.  Utterance lengths
+    ~U(150, 1500) frames.  Per target pool the (utterance, target) pairs are sorted by
+    length and dealt round-robin over the ranks: every rank gets the same number of pairs (+-1) and
+    of frames (+-1 utterance) per pool, with no communication."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    lens = {}
+    for spk, n in CFG5_SRC_UTTS.items():
+        for u in range(n):
+            lens[(spk, u)] = int(rs.randint(150, 1501))
+    per_target = {}
+    for spk, tgts in CFG5_TARGETS.items():
+        for t in tgts:
+            per_target.setdefault(t, []).extend((spk, u) for u in range(CFG5_SRC_UTTS[spk]))
+    mine, total_pairs, total_frames = {}, 0, 0
+    for t in sorted(per_target):
+        pairs = sorted(per_target[t], key=lambda su: (-lens[su], su))
+        total_pairs += len(pairs)
+        total_frames += sum(lens[su] for su in pairs)
+        mine[t] = [(su, lens[su]) for su in pairs[rank::world]]
+    return mine, total_pairs, total_frames
+
+
+def run_cfg5(args, env):
+    """dataset -> dataset conversion (bulk_match's pair loop, ddsp_matcher.py:1073-1112) at the shape of
+    OpenSinger_test_to_nus-smc-corpus_48: one step = ALL 7038 (utterance, target) pairs, post_opt_0.2."""
+    torch = env.torch
+    from knn_svc_b200 import synth
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    mine, total_pairs, total_frames = cfg5_jobs(env.world, env.rank)
+    assert total_pairs == 7038
+    pools = {t: _pipeline_pool(env, CFG5_POOL_FRAMES, 900 + 10 * j) for j, t in enumerate(sorted(mine))}
+    # every distinct source utterance of this rank: features on the device (the WavLM output), f0 on the host
+    utts = {}
+    spk_no = {spk: j for j, spk in enumerate(sorted(CFG5_SRC_UTTS))}
+    for t, jobs in mine.items():
+        for su, n in jobs:
+            if su not in utts:
+                seed = 100_000 + 2 * (1000 * spk_no[su[0]] + su[1])
+                utts[su] = (synth.ar1_frames_device(n, DIM, seed=seed, device=env.dev, seg_len=200),
+                            torch.from_numpy(synth.f0_track(n, seed=seed + 1)))
+    batch = args.cfg5_batch
+    my_pairs = sum(len(j) for j in mine.values())
+    my_frames = sum(n for j in mine.values() for _, n in j)
+    host_out = torch.empty((max(n for j in mine.values() for _, n in j), DIM), dtype=torch.float32).pin_memory()
+
+    def step(download=False):
+        for t in sorted(mine):
+            jobs = mine[t]
+            for a in range(0, len(jobs), batch):
+                part = jobs[a:a + batch]
+                res = pm.match_utterances([utts[su][0] for su, _ in part], [utts[su][1] for su, _ in part], pools[t],
+                                          post_opt="post_opt_0.2", ckpt_type="mix", prioritize_f0=True)
+                if download:
+                    for r in res:
+                        host_out[:r["out_feats"].shape[0]].copy_(r["out_feats"], non_blocking=True)
+
+    ms_step, clocks, launches, _, _ = env.timed(step, args.steps, args.warmup)
+    ms_e2e = env.timed(lambda: step(True), args.steps, max(1, args.warmup // 2))[0]
+    counts = env.max_over_ranks([float(my_pairs), float(my_frames)])
+    if env.rank == 0:
+        line = {"metric": "utterance_target_pairs_per_s_cfg5", "value": total_pairs / (ms_step * 1e-3),
+                "unit": "(utterance, target) pairs/s", "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 filter + f32/f64", "data": "synthetic",
+                "query_frames_per_s": total_frames / (ms_step * 1e-3),
+                "config": {"workload": "cfg5: OpenSinger_test_to_nus-smc-corpus_48 split shape — 7038 (utterance, target) pairs "
+                                       f"({total_frames} query frames, utterances U(150,1500) frames), 4 target pools of "
+                                       f"{CFG5_POOL_FRAMES} frames, post_opt_0.2, prioritize_f0, ckpt_type=mix",
+                           "parallelism": f"pairs dealt over {env.world} ranks per target pool (sorted by length, round-robin), "
+                                          "no communication", "batch_utterances": batch,
+                           "max_pairs_per_rank": counts[0], "max_frames_per_rank": counts[1],
+                           "l2": "30k-frame pools (123 MB fp32 + 61 MB fp16) exceed L2 together with the batch"},
+                "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "(utterance, target) pairs/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": 0, "d2h_bytes_per_step": total_frames * DIM * 4,
+                        "api": "match_utterances (the body of match_at_inference_time) + download of the matched features; "
+                               "source features are the WavLM output and already on the device"},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--queries", type=int, default=N_QUERY)
-    ap.add_argument("--pool", type=int, default=N_POOL)
+    ap.add_argument("--workload", default="cfg4", choices=sorted(SEARCH_WORKLOADS) + ["cfg1", "cfg2", "cfg5"])
+    ap.add_argument("--queries", type=int, default=0, help="override the workload's query frames")
+    ap.add_argument("--pool", type=int, default=0, help="override the workload's pool frames")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "reduce_scatter"])
+    ap.add_argument("--cfg5-batch", type=int, default=1024, help="utterances per match_utterances call")
     ap.add_argument("--cpu-queries", type=int, default=200)
     ap.add_argument("--cpu-pool", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-
-    import torch
-    import torch.distributed as dist
-    from knn_svc_b200 import _lib, ops, sharded
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # (NCCL prints its "NCCL version ..." banner on stdout at communicator creation, whatever NCCL_DEBUG
-        # says; the JSON line below is the LAST line of rank 0's stdout)
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    T, NP = args.queries, args.pool
-    lo, hi = sharded.shard_bounds(NP, world, rank)
-    n_shard = hi - lo
-
-    # ---- synthetic inputs, resident in HBM (query seed 0 replicated, pool shard seed 1000+rank)
-    g = torch.Generator(device=dev); g.manual_seed(0)
-    query = torch.randn((T, DIM), device=dev, generator=g)
-    g.manual_seed(1000 + rank)
-    pool = torch.empty((n_shard, DIM), device=dev)
-    for a in range(0, n_shard, 1 << 20):
-        b = min(n_shard, a + (1 << 20))
-        pool[a:b] = torch.randn((b - a, DIM), device=dev, generator=g)
-    # pinned host buffers for the end-to-end leg
-    query_host = torch.empty((T, DIM), dtype=torch.float32).pin_memory()
-    query_host.copy_(query)
-    feats_host = torch.empty((T, DIM), dtype=torch.float32).pin_memory()
-    idx_host = torch.empty((T, TOPK), dtype=torch.int64).pin_memory()
-    dist_host = torch.empty((T, TOPK), dtype=torch.float32).pin_memory()
-    torch.cuda.synchronize()
-
-    def match_step(q_dev, pool_prepared=None):
-        """the hot path on device tensors: returns (dist, idx, matched features)"""
-        qp = ops.prepare_rows(q_dev, check=False)
-        pp = pool_prepared if pool_prepared is not None else ops.prepare_rows(pool, check=False)
-        d, i = ops.knn_search(qp, pp, TOPK, index_offset=lo)
-        if world > 1:
-            gd, gi = sharded.all_gather_topk(d, i)
-            d, i = ops.merge_topk(gd, gi)
-            local = (i >= lo) & (i < hi)
-            w = local.to(torch.float32) * (1.0 / TOPK)
-            feats = ops.gather_mix(pp.rows, (i - lo).clamp_(0, n_shard - 1), w)
-            dist.all_reduce(feats)
-        else:
-            feats = ops.gather_mix(pp.rows, i, None)
-        return d, i, feats
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident leg ("value")
-    for _ in range(args.warmup):
-        match_step(query)
-    barrier()
-    lib.knnsvc_filter_timing(1)
-    launches0 = lib.knnsvc_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = match_step(query)
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = lib.knnsvc_launch_count() - launches0
-    import ctypes
-    buf = (ctypes.c_float * 256)()
-    n_t = lib.knnsvc_filter_timing_collect(ctypes.cast(buf, ctypes.c_void_p), 256)
-    lib.knnsvc_filter_timing(0)
-    filter_ms = sum(buf[i] for i in range(n_t)) / max(n_t, 1)
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps, filter_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step, filter_ms = float(ms[0]), float(ms[1])
-
-    # ---- end-to-end leg: pinned host query batch in, matched features + indices out, pool resident
-    pool_prepared = ops.prepare_rows(pool, check=False)
-
-    # At N > 1 the host batch crosses PCIe ONCE in total: rank r uploads rows [r*chunk, (r+1)*chunk) and the
-    # ranks replicate the batch over NVLink (one all-gather); each rank downloads its own slice of the results.
-    chunk = (T + world - 1) // world
-    q_lo, q_hi = min(T, rank * chunk), min(T, (rank + 1) * chunk)
-    q_all = torch.zeros((world * chunk, DIM), device=dev) if world > 1 else None
-
-    def e2e_step():
-        if world > 1:
-            part = q_all[rank * chunk:(rank + 1) * chunk]
-            part[:q_hi - q_lo].copy_(query_host[q_lo:q_hi], non_blocking=True)
-            dist.all_gather_into_tensor(q_all, part.clone())
-            q_dev = q_all[:T]
-        else:
-            q_dev = query_host.to(dev, non_blocking=True)
-        d, i, f = match_step(q_dev, pool_prepared)
-        feats_host[q_lo:q_hi].copy_(f[q_lo:q_hi], non_blocking=True)
-        idx_host[q_lo:q_hi].copy_(i[q_lo:q_hi], non_blocking=True)
-        dist_host[q_lo:q_hi].copy_(d[q_lo:q_hi], non_blocking=True)
-
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2[0])
-
-    if rank == 0:
-        peaks, peak_src = _peaks()
-        flops = 2.0 * T * n_shard * DIM                     # algorithmic FLOPs of one filter launch (per GPU)
-        achieved = flops / (filter_ms * 1e-3) / 1e12
-        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        roofline = {"bound": "tensor", "kernel": "knn_filter_kernel (tcgen05 fp16, fp32 accumulate)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": f"{peak_src} sustained cuBLAS bf16 (kernel timed inside a long step)",
-                    "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
-                    "kernel_ms": filter_ms, "kernel_share_of_step": filter_ms / ms_step,
-                    "algorithmic_flops_per_launch": flops, "traffic": _filter_traffic(T, n_shard),
-                    "traffic_note": "DRAM bytes per launch from the committed ncu capture profiles/filter_traffic.json "
-                                    "(not measured in this run); the kernel is tensor-bound, operands stream from L2"}
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
-            from oracle import cpu_baseline              # checker/baseline only, never the measured path
-            sec, threads = cpu_baseline.time_sample(args.cpu_queries, args.cpu_pool, DIM, steps=1, warmup=0)
-            v = args.cpu_queries / (sec * (NP / args.cpu_pool))
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_queries} query frames x {args.cpu_pool} pool frames, fp32, torch CPU, "
-                             f"{sec:.1f} s; extrapolated linearly in pool size to {NP} frames"}
-        line = {"metric": METRIC, "value": T / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f16 tensor-core filter (f32 accumulate) + f32/f64 exact re-score",
-                "data": "synthetic",
-                "config": {"workload": f"cfg4: {T} query frames vs {NP}-frame pool, {DIM}-dim, topk={TOPK}",
-                           "pool_frames": NP, "query_frames": T, "dim": DIM, "topk": TOPK,
-                           "parallelism": f"pool sharded by frame x{world}, NCCL all-gather top-k merge",
-                           "l2": "inputs (pool shard) exceed L2", "step": "prepare(query)+prepare(pool)+knn+merge+gather-mean"},
-                "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": {"value": T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": T * DIM * 4, "d2h_bytes_per_step": T * DIM * 4 + T * TOPK * 12,
-                        "note": "pinned host query batch in, features+indices+distances out (bytes are totals over "
-                                "ranks: at N>1 each rank moves its 1/N slice over PCIe and the batch is replicated "
-                                "over NVLink); pool resident in HBM (built once, as get_matching_set does)"},
-                "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    env = Env()
+    try:
+        if args.workload in SEARCH_WORKLOADS:
+            return run_search(args, env)
+        if args.workload in ("cfg1", "cfg2"):
+            return run_single_utterance(args, env)
+        return run_cfg5(args, env)
+    finally:
+        env.finish()
 
 
 if __name__ == "__main__":

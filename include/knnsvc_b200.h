@@ -97,6 +97,25 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
                              float* out_dist, int64_t* out_idx,
                              void* workspace, size_t workspace_bytes, int* stats, void* stream);
 
+/* The general form of the search: the masked search plus `out_dist64` (optional, [n_query, k]):
+ * the fp64 cosine distances the re-score ranked by (out_dist is their fp32 rounding).  The
+ * sharded path (C1) exchanges and merges THESE, so a pool searched in N shards returns bit for bit
+ * what one search of the whole pool returns. */
+int knnsvc_knn_search_full(const float* q, const void* qh, const float* qn, int64_t n_query,
+                           const float* p, const void* ph, const float* pn, int64_t n_pool,
+                           int dim, int dim_pad, int k, int64_t index_offset,
+                           const float* q_err, const float* p_err,
+                           const int64_t* mask_lo, const int64_t* mask_hi,
+                           float* out_dist, double* out_dist64, int64_t* out_idx,
+                           void* workspace, size_t workspace_bytes, int* stats, void* stream);
+
+/* Where the search keeps its candidate log inside the caller's workspace (host-only, no GPU work;
+ * test / diagnostic aid — the parity tests read the tensor-core similarities s~ back from it):
+ * layout_host int64[8] <- {byte offset of log_val (float [n_query*n_seg][cap]), of log_idx
+ * (int32, same shape), of log_cnt (int32 [n_query*n_seg], cap+1 = overflowed), of seg_top
+ * (float [n_query*n_seg][k]), n_seg, cap, total bytes, 0}. */
+int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int k, int64_t* layout_host);
+
 /* Measurement hooks used by bench.py (no effect on results).
  *   knnsvc_launch_count            kernels this library has launched in this process
  *   knnsvc_filter_timing(1/0)      bracket the tcgen05 filter launch of every later
@@ -110,6 +129,8 @@ long long knnsvc_launch_count(void);
  * kernel where the row shape allows it, or the general kernel only),
  * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes),
  * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
+ * "log_cap" (candidate-log slots per row and pool segment, 0 = default 2048; the tests shrink it to
+ * drive rows into the overflow -> exact-kernel path with small fixtures),
  * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static
  * instead of dynamic unit scheduling), "weight_fit_cluster" = 1|0 (K6: a cluster of 8 CTAs per
  * utterance for launches of few long utterances, or always one CTA per utterance; same results). */
@@ -130,6 +151,32 @@ int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query,
  * so the result does not depend on the shard count. */
 int knnsvc_merge_topk(const float* gathered_dist, const int64_t* gathered_idx, int n_shards,
                       int64_t n_query, int k, float* out_dist, int64_t* out_idx, void* stream);
+
+/* fp64 variant: gathered_dist is double [n_shards, n_query, k] (knnsvc_knn_search_full's
+ * out_dist64); out_dist64 optional. */
+int knnsvc_merge_topk64(const double* gathered_dist, const int64_t* gathered_idx, int n_shards,
+                        int64_t n_query, int k, float* out_dist, double* out_dist64, int64_t* out_idx,
+                        void* stream);
+
+/* ---- C1: peer memory.  One process per GPU; a rank exports the allocation that holds its pool
+ * shard's fp32 rows and opens its peers' (CUDA IPC, peer access enabled lazily), so that the
+ * gather below can read matched rows straight from the GPU that owns them over NVLink.
+ *   knnsvc_ipc_export  handle_host: 64 bytes <- cudaIpcMemHandle_t of the allocation `ptr` lies in;
+ *                      offset_host <- byte offset of `ptr` inside that allocation
+ *   knnsvc_ipc_open    base_out <- device pointer of the peer's allocation in THIS process
+ *   knnsvc_ipc_close   unmaps it */
+int knnsvc_ipc_export(const void* ptr, void* handle_host, int64_t* offset_host);
+int knnsvc_ipc_open(const void* handle_host, void** base_out);
+int knnsvc_ipc_close(void* base);
+
+/* ---- K3 over a sharded pool: the gather + mix of knnsvc_gather_mix where pool rows
+ * [shard_lo_host[s], shard_lo_host[s+1]) live at shard_rows_host[s] (this GPU's memory or an
+ * IPC-mapped peer pointer).  idx holds GLOBAL row indices.  Same arithmetic, same order: the
+ * result is bit-identical to mixing from one contiguous pool.  shard_* are HOST arrays of
+ * n_shards (<= 16) pointers / n_shards + 1 bounds. */
+int knnsvc_gather_mix_sharded(const void* const* shard_rows_host, const int64_t* shard_lo_host, int n_shards,
+                              int dim, const int64_t* idx, const float* weights, int64_t n_query, int k,
+                              float* out, void* stream);
 
 /* ---- K3: gather + weighted mix -------------------------------------------
  * out[t,:] = sum_k w[t,k] * pool[idx[t,k],:]  (w == NULL -> mean) —

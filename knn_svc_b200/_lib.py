@@ -27,6 +27,9 @@ SIGNATURES = {
                                 vp]),
     "knnsvc_knn_search_masked": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp,
                                        vp, sz, vp, vp]),
+    "knnsvc_knn_search_full": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp,
+                                     vp, sz, vp, vp]),
+    "knnsvc_knn_workspace_layout": (i32, [i64, i64, i32, vp]),
     "knnsvc_launch_count": (C.c_longlong, []),
     "knnsvc_set_option": (i32, [C.c_char_p, i32]),
     "knnsvc_filter_timing": (i32, [i32]),
@@ -34,6 +37,11 @@ SIGNATURES = {
     "knnsvc_knn_exact_workspace_bytes": (sz, [i64, i64, i32]),
     "knnsvc_knn_exact": (i32, [vp, vp, i64, vp, vp, i64, i32, i32, i64, vp, vp, vp, sz, vp]),
     "knnsvc_merge_topk": (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),
+    "knnsvc_merge_topk64": (i32, [vp, vp, i32, i64, i32, vp, vp, vp, vp]),
+    "knnsvc_ipc_export": (i32, [vp, vp, vp]),
+    "knnsvc_ipc_open": (i32, [vp, vp]),
+    "knnsvc_ipc_close": (i32, [vp]),
+    "knnsvc_gather_mix_sharded": (i32, [vp, vp, i32, i32, vp, vp, i64, i32, vp, vp]),
     "knnsvc_gather_mix": (i32, [vp, i64, i32, vp, vp, i64, i32, vp, vp]),
     "knnsvc_f0_rerank": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "knnsvc_concat_cost_reselect": (i32, [vp, vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, vp]),

@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/knnsvc_b200.h.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -45,6 +46,9 @@ static std::atomic<int> g_opt_spin_ns{40};  // measured: ~3% faster than a pure 
 int opt_spin_ns() { return g_opt_spin_ns.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_epi_sleep_ns{0};
 int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns.load(std::memory_order_relaxed); }
+
+static std::atomic<int> g_opt_log_cap{0};
+int opt_log_cap() { return g_opt_log_cap.load(std::memory_order_relaxed); }
 
 static std::atomic<int> g_opt_concat_staged{1};
 int opt_concat_staged() { return g_opt_concat_staged.load(std::memory_order_relaxed); }
@@ -192,6 +196,16 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
                              int64_t index_offset, const float* q_err, const float* p_err,
                              const int64_t* mask_lo, const int64_t* mask_hi, float* out_dist, int64_t* out_idx,
                              void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
+  return knnsvc_knn_search_full(q, qh, qn, n_query, p, ph, pn, n_pool, dim, dim_pad, k, index_offset, q_err, p_err,
+                                mask_lo, mask_hi, out_dist, nullptr, out_idx, workspace, workspace_bytes, stats,
+                                stream_);
+}
+
+int knnsvc_knn_search_full(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
+                           const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+                           int64_t index_offset, const float* q_err, const float* p_err, const int64_t* mask_lo,
+                           const int64_t* mask_hi, float* out_dist, double* out_dist64, int64_t* out_idx,
+                           void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   KNN_CHECK_ARG((mask_lo == nullptr) == (mask_hi == nullptr), -1,
                 "knn_search: mask_lo and mask_hi must be given together");
@@ -200,6 +214,8 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   KNN_CHECK_ARG(k <= n_pool, -1, "knn_search: k=%d exceeds the pool size %lld", k, (long long)n_pool);
   if (n_query == 0) return 0;
   KNN_CHECK_ARG(q && qh && qn && p && ph && pn && out_dist && out_idx && workspace, -1, "knn_search: null pointer");
+  KNN_CHECK_ARG(!opt_bf16() || (q_err && p_err), -1,
+                "knn_search: bf16 operands need the measured row errors (the default window assumes fp16)");
   FilterPlan pl = plan_filter(n_query, n_pool, k);
   KnnWorkspace w = carve(workspace, n_query, n_pool, k, pl);
   KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
@@ -217,12 +233,13 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
   if (rc) return rc;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[ev_slot][1], stream));
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                          index_offset, out_dist, out_idx, w.flag_list, w.counters, w.counters + 1, mask_lo, mask_hi,
-                          q_err, p_err, stream);
+                          index_offset, out_dist, out_dist64, out_idx, w.flag_list, w.counters, w.counters + 1,
+                          mask_lo, mask_hi, q_err, p_err, stream);
   if (rc) return rc;
   // rows the error window could not decide: exact brute force, count known only on the device
   rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, w.flag_list, w.counters, 0, 0, kFlagCap,
-                             index_offset, out_dist, out_idx, w.exact_partial, mask_lo, mask_hi, stream);
+                             index_offset, out_dist, out_dist64, out_idx, w.exact_partial, mask_lo, mask_hi,
+                             stream);
   if (rc) return rc;
   if (stats) {
     write_plan_stats<<<1, 1, 0, stream>>>(stats, w.counters, pl.n_seg, pl.n_units, pl.grid, pl.cap);
@@ -266,6 +283,12 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "block_tiles") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: block_tiles out of range");
     g_opt_block_tiles.store(value, std::memory_order_relaxed);
+    return 0;
+  }
+  if (strcmp(name, "log_cap") == 0) {
+    KNN_CHECK_ARG(value == 0 || (value >= 64 && value <= 65536 && value % 8 == 0), -1,
+                  "set_option: log_cap must be 0 (default) or a multiple of 8 in [64, 65536]");
+    g_opt_log_cap.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "bf16_operands") == 0) {
@@ -315,7 +338,7 @@ int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query, const flo
   for (int64_t base = 0; base < n_query; base += cap) {
     const int64_t n = (n_query - base) < cap ? (n_query - base) : cap;
     int rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, nullptr, nullptr, n, base, cap,
-                                   index_offset, out_dist, out_idx, workspace, nullptr, nullptr,
+                                   index_offset, out_dist, nullptr, out_idx, workspace, nullptr, nullptr,
                                    (cudaStream_t)stream);
     if (rc) return rc;
   }
@@ -326,6 +349,84 @@ int knnsvc_merge_topk(const float* gathered_dist, const int64_t* gathered_idx, i
                       float* out_dist, int64_t* out_idx, void* stream) {
   KNN_CHECK_ARG(gathered_dist && gathered_idx && out_dist && out_idx, -1, "merge_topk: null pointer");
   return launch_merge_topk(gathered_dist, gathered_idx, n_shards, n_query, k, out_dist, out_idx, (cudaStream_t)stream);
+}
+
+int knnsvc_merge_topk64(const double* gathered_dist, const int64_t* gathered_idx, int n_shards, int64_t n_query,
+                        int k, float* out_dist, double* out_dist64, int64_t* out_idx, void* stream) {
+  KNN_CHECK_ARG(gathered_dist && gathered_idx && out_dist && out_idx, -1, "merge_topk64: null pointer");
+  return launch_merge_topk64(gathered_dist, gathered_idx, n_shards, n_query, k, out_dist, out_dist64, out_idx,
+                             (cudaStream_t)stream);
+}
+
+int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int k, int64_t* layout_host) {
+  KNN_CHECK_ARG(layout_host != nullptr, -1, "knn_workspace_layout: null output");
+  KNN_CHECK_ARG(n_query >= 1 && n_pool >= 1 && k >= 1 && k <= kMaxK, -1, "knn_workspace_layout: bad shape");
+  const FilterPlan pl = plan_filter(n_query, n_pool, k);
+  unsigned char* base = reinterpret_cast<unsigned char*>(uintptr_t(1) << 20);   // any non-null base: offsets only
+  const KnnWorkspace w = carve(base, n_query, n_pool, k, pl);
+  layout_host[0] = reinterpret_cast<unsigned char*>(w.log_val) - base;
+  layout_host[1] = reinterpret_cast<unsigned char*>(w.log_idx) - base;
+  layout_host[2] = reinterpret_cast<unsigned char*>(w.log_cnt) - base;
+  layout_host[3] = reinterpret_cast<unsigned char*>(w.seg_top) - base;
+  layout_host[4] = pl.n_seg;
+  layout_host[5] = pl.cap;
+  layout_host[6] = (int64_t)w.total;
+  layout_host[7] = 0;
+  return 0;
+}
+
+// ---- peer memory (one process per GPU): CUDA IPC handles of a shard's row storage
+int knnsvc_ipc_export(const void* ptr, void* handle_host, int64_t* offset_host) {
+  KNN_CHECK_ARG(ptr && handle_host && offset_host, -1, "ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* base = nullptr;
+  size_t size = 0;
+  // the handle names the whole ALLOCATION the pointer lies in; the caller's tensor may start inside it
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  KNN_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));   // no link-time libcuda
+  KNN_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, -10, "cuMemGetAddressRange entry point not available");
+  CUresult r = reinterpret_cast<RangeFn>(fn)(reinterpret_cast<CUdeviceptr*>(&base), &size,
+                                             reinterpret_cast<CUdeviceptr>(ptr));
+  KNN_CHECK_ARG(r == CUDA_SUCCESS, -12, "ipc_export: cuMemGetAddressRange failed with CUresult %d", (int)r);
+  cudaIpcMemHandle_t h;
+  KNN_CUDA(cudaIpcGetMemHandle(&h, base));
+  memcpy(handle_host, &h, sizeof(h));
+  *offset_host = (int64_t)(reinterpret_cast<const unsigned char*>(ptr) - reinterpret_cast<const unsigned char*>(base));
+  return 0;
+}
+
+int knnsvc_ipc_open(const void* handle_host, void** base_out) {
+  KNN_CHECK_ARG(handle_host && base_out, -1, "ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  KNN_CUDA(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int knnsvc_ipc_close(void* base) {
+  if (!base) return 0;
+  KNN_CUDA(cudaIpcCloseMemHandle(base));
+  return 0;
+}
+
+int knnsvc_gather_mix_sharded(const void* const* shard_rows_host, const int64_t* shard_lo_host, int n_shards, int dim,
+                              const int64_t* idx, const float* weights, int64_t n_query, int k, float* out,
+                              void* stream) {
+  KNN_CHECK_ARG(shard_rows_host && shard_lo_host && idx && out && k >= 1, -1, "gather_mix_sharded: bad arguments");
+  KNN_CHECK_ARG(n_shards >= 1 && n_shards <= kMaxShards, -1, "gather_mix_sharded: %d shards outside [1,%d]", n_shards,
+                kMaxShards);
+  RowTable tab;
+  tab.n = n_shards;
+  for (int s = 0; s < n_shards; ++s) {
+    KNN_CHECK_ARG(shard_rows_host[s] != nullptr && shard_lo_host[s + 1] >= shard_lo_host[s], -1,
+                  "gather_mix_sharded: bad shard %d", s);
+    tab.base[s] = reinterpret_cast<const float*>(shard_rows_host[s]);
+    tab.lo[s] = shard_lo_host[s];
+  }
+  tab.lo[n_shards] = shard_lo_host[n_shards];
+  return launch_gather_mix_sharded(tab, dim, idx, weights, n_query, k, out, (cudaStream_t)stream);
 }
 
 int knnsvc_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,

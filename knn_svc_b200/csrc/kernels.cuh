@@ -10,6 +10,7 @@ int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
 int opt_filter_flags();   // bit0: L2 prefetch of the next unit's query tile, bit2: static unit schedule (bit1 unused)
 int opt_weight_fit_cluster();   // 1 (default): few long utterances are fitted by a cluster of 8 CTAs each
+int opt_log_cap();       // candidate-log slots per (row, segment); 0 = default
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
@@ -25,8 +26,8 @@ size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k);
 int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
-                          float* out_dist, int64_t* out_idx, void* partial, const int64_t* mask_lo,
-                          const int64_t* mask_hi, cudaStream_t stream);
+                          float* out_dist, double* out_dist64, int64_t* out_idx, void* partial,
+                          const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream);
 
 // ---- knn_filter_sm100.cu
 struct FilterPlan {
@@ -44,13 +45,25 @@ constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb
 int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
-                       float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err, const float* p_err,
-                       cudaStream_t stream);
+                       float* out_dist, double* out_dist64, int64_t* out_idx, int64_t* flag_list, int* flag_count,
+                       int* stats, const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err,
+                       const float* p_err, cudaStream_t stream);
 int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
                       int64_t* out_idx, cudaStream_t stream);
+int launch_merge_topk64(const double* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
+                        double* out_dist64, int64_t* out_idx, cudaStream_t stream);
 
 // ---- post.cu
+// A pool stored as up to kMaxShards row blocks: rows [lo[s], lo[s+1]) live at base[s] (this GPU's
+// memory or a peer's, mapped through CUDA IPC — loads then travel over NVLink).
+constexpr int kMaxShards = 16;
+struct RowTable {
+  const float* base[kMaxShards];
+  int64_t lo[kMaxShards + 1];
+  int n;
+};
+int launch_gather_mix_sharded(const RowTable& tab, int dim, const int64_t* idx, const float* weights, int64_t n_query,
+                              int k, float* out, cudaStream_t stream);
 int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,
                       int64_t n_query, int k, float* out, cudaStream_t stream);
 int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx, int64_t n_query, int k,

@@ -552,7 +552,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;    // TMEM lane == query row inside this CTA's tile
     int* keys_row = reinterpret_cast<int*>(smem + L::topv) + row_in_tile;   // [kSlots][BM] packed keys
-    const float window_scaled = 2.0f * filter_eps(q_err, p_err) * kDotScale;
+    const float window_scaled = 2.0f * filter_eps(q_err, p_err, k_blocks * BK) * kDotScale;
     uint32_t tile_n = 0;
     int it = 0, sq = 0;
     uint32_t sq_phase = 0;
@@ -797,7 +797,11 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   pl.n_blk = best_nb;
   pl.n_units = pl.n_qtiles * pl.n_seg * pl.n_blk;
   pl.grid = (pl.n_units < workers ? pl.n_units : workers) * pl.ctas;
-  pl.cap = 64 * k < 256 ? 256 : 64 * k;
+  // Candidate-log slots per (row, segment).  Sparse data (i.i.d. rows) logs ~70 entries per row at k = 4;
+  // WavLM-like rows (a large shared mean: every pool row within ~0.03 cosine of every other) hold
+  // ~800-1200 candidates inside the 2*eps window of the k-th best at 1M-10M pool rows, and a row that
+  // overflows its log costs a brute-force pass, so the log is sized for the dense case at every k.
+  pl.cap = opt_log_cap() > 0 ? opt_log_cap() : 2048;
   return pl;
 }
 

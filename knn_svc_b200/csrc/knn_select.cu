@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
     const float* __restrict__ log_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
     const float* __restrict__ seg_top, int64_t index_offset, float* __restrict__ out_dist,
-    int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list, int* __restrict__ flag_count,
+    double* __restrict__ out_dist64, int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list,
+    int* __restrict__ flag_count,
     int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi,
     const float* __restrict__ q_err, const float* __restrict__ p_err) {
   extern __shared__ __align__(16) double s_q[];  // [dim] the query row, converted once
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
         const float o = s_top[j];
         rank += (o > v) || (o == v && j < e);
       }
-      if (rank == k - 1) s_thr = v - 2.0f * filter_eps(q_err, p_err);
+      if (rank == k - 1) s_thr = v - 2.0f * filter_eps(q_err, p_err, (dim + 63) / 64 * 64);
     }
     for (int s = tid; s < n_seg; s += RS_THREADS) {
       const int c = log_cnt[row * n_seg + s];
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
         if (rank < k) {
           if (final) {
             out_dist[row * k + rank] = (float)d;
+            if (out_dist64) out_dist64[row * k + rank] = d;
             out_idx[row * k + rank] = (int64_t)i + index_offset;
           } else {
             s_best_d[rank] = d;
@@ -224,9 +226,9 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
 int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
-                       float* out_dist, int64_t* out_idx, int64_t* flag_list, int* flag_count, int* stats,
-                       const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err, const float* p_err,
-                       cudaStream_t stream) {
+                       float* out_dist, double* out_dist64, int64_t* out_idx, int64_t* flag_list, int* flag_count,
+                       int* stats, const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err,
+                       const float* p_err, cudaStream_t stream) {
   if (n_query == 0) return 0;
   KNN_CHECK_ARG(pl.n_seg * k <= RS_MAXTOP, -3, "n_seg*k too large");
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
@@ -234,8 +236,9 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
   KNN_CHECK_ARG(smem <= 32 * 1024, -3, "dim %d too large for the rescoring kernel", dim);
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, log_val, log_idx, log_cnt, seg_top,
-                                                                   index_offset, out_dist, out_idx, flag_list,
-                                                                   flag_count, stats, mask_lo, mask_hi, q_err, p_err);
+                                                                   index_offset, out_dist, out_dist64, out_idx,
+                                                                   flag_list, flag_count, stats, mask_lo, mask_hi,
+                                                                   q_err, p_err);
   KNN_LAUNCH_CHECK();
   return 0;
 }
@@ -247,11 +250,13 @@ int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const f
 constexpr int MG_WARPS = 4;
 constexpr int MG_MAX = 512;
 
-__global__ void __launch_bounds__(MG_WARPS * 32) merge_topk_kernel(const float* __restrict__ gd,
+template <typename DT>
+__global__ void __launch_bounds__(MG_WARPS * 32) merge_topk_kernel(const DT* __restrict__ gd,
                                                                    const int64_t* __restrict__ gi, int n_shards,
                                                                    int64_t n_query, int k, float* __restrict__ out_dist,
+                                                                   DT* __restrict__ out_dist_full,
                                                                    int64_t* __restrict__ out_idx) {
-  __shared__ float sd[MG_WARPS][MG_MAX];
+  __shared__ DT sd[MG_WARPS][MG_MAX];
   __shared__ int64_t si[MG_WARPS][MG_MAX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = n_shards * k;
@@ -264,17 +269,18 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_topk_kernel(const float* 
     }
     __syncwarp();
     for (int e = lane; e < n; e += 32) {
-      const float d = sd[warp][e];
+      const DT d = sd[warp][e];
       const int64_t i = si[warp][e];
       if (i < 0) continue;  // padding of a shard smaller than k
       int rank = 0;
       for (int j = 0; j < n; ++j) {
-        const float dj = sd[warp][j];
+        const DT dj = sd[warp][j];
         const int64_t ij = si[warp][j];
         rank += (ij >= 0) && ((dj < d) || (dj == d && ij < i));
       }
       if (rank < k) {
-        out_dist[row * k + rank] = d;
+        out_dist[row * k + rank] = (float)d;
+        if (out_dist_full) out_dist_full[row * k + rank] = d;
         out_idx[row * k + rank] = i;
       }
     }
@@ -288,7 +294,25 @@ int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t 
                 MG_MAX);
   int64_t grid = ceil_div64(n_query, MG_WARPS);
   if (grid > 148 * 16) grid = 148 * 16;
-  merge_topk_kernel<<<(unsigned)grid, MG_WARPS * 32, 0, stream>>>(gd, gi, n_shards, n_query, k, out_dist, out_idx);
+  merge_topk_kernel<float><<<(unsigned)grid, MG_WARPS * 32, 0, stream>>>(gd, gi, n_shards, n_query, k, out_dist,
+                                                                          nullptr, out_idx);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// The same merge on the fp64 distances the re-score ranked by: a pool searched in N shards then
+// returns bit for bit what one search of the whole pool returns (the fp32 roundings of two
+// different fp64 distances can tie; ranking the shards' lists on the rounded values could then
+// order, or cut, differently from the single search).
+int launch_merge_topk64(const double* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
+                        double* out_dist64, int64_t* out_idx, cudaStream_t stream) {
+  if (n_query == 0) return 0;
+  KNN_CHECK_ARG(n_shards >= 1 && n_shards * k <= MG_MAX, -3, "merge_topk: n_shards*k=%d exceeds %d", n_shards * k,
+                MG_MAX);
+  int64_t grid = ceil_div64(n_query, MG_WARPS);
+  if (grid > 148 * 16) grid = 148 * 16;
+  merge_topk_kernel<double><<<(unsigned)grid, MG_WARPS * 32, 0, stream>>>(gd, gi, n_shards, n_query, k, out_dist,
+                                                                           out_dist64, out_idx);
   KNN_LAUNCH_CHECK();
   return 0;
 }

@@ -63,6 +63,69 @@ int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t*
   return 0;
 }
 
+// K3 over a pool that lives in several row blocks (sharded.py): the same arithmetic in the same
+// order as gather_mix_kernel, so the result is bit-identical to mixing from one contiguous pool;
+// rows of another GPU's shard are read through its IPC-mapped pointer (NVLink P2P loads, 16 B per
+// lane, K of them in flight per thread).  Launched by the rank that OWNS the query rows.
+__device__ __forceinline__ const float* table_row(const RowTable& tab, int64_t r, int dim) {
+  r = r < 0 ? 0 : (r >= tab.lo[tab.n] ? tab.lo[tab.n] - 1 : r);
+  int s = 0;
+#pragma unroll 1
+  while (s + 1 < tab.n && r >= tab.lo[s + 1]) ++s;
+  return tab.base[s] + (r - tab.lo[s]) * dim;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_mix_sharded_kernel(const __grid_constant__ RowTable tab, int dim,
+                                                                 const int64_t* __restrict__ idx,
+                                                                 const float* __restrict__ weights, int64_t n_query,
+                                                                 int k, float* __restrict__ out) {
+  const int per_row = VEC ? dim / 4 : dim;
+  const int64_t total = n_query * per_row;
+  const float uniform = 1.0f / (float)k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = e / per_row;
+    const int c = (int)(e % per_row);
+    if (VEC) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < k; ++j) {
+        const float* row = table_row(tab, __ldg(idx + t * k + j), dim);
+        const float w = weights ? __ldg(weights + t * k + j) : uniform;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + c);
+        acc.x = fmaf(w, v.x, acc.x);
+        acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z);
+        acc.w = fmaf(w, v.w, acc.w);
+      }
+      reinterpret_cast<float4*>(out + t * dim)[c] = acc;
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) {
+        const float* row = table_row(tab, __ldg(idx + t * k + j), dim);
+        const float w = weights ? __ldg(weights + t * k + j) : uniform;
+        acc = fmaf(w, __ldg(row + c), acc);
+      }
+      out[t * dim + c] = acc;
+    }
+  }
+}
+
+int launch_gather_mix_sharded(const RowTable& tab, int dim, const int64_t* idx, const float* weights, int64_t n_query,
+                              int k, float* out, cudaStream_t stream) {
+  if (n_query == 0 || dim == 0) return 0;
+  bool vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int s = 0; s < tab.n; ++s) vec = vec && ((reinterpret_cast<uintptr_t>(tab.base[s]) & 15) == 0);
+  const int64_t total = n_query * (vec ? dim / 4 : dim);
+  int64_t grid = ceil_div64(total, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  if (vec)
+    gather_mix_sharded_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(tab, dim, idx, weights, n_query, k, out);
+  else
+    gather_mix_sharded_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(tab, dim, idx, weights, n_query, k, out);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------ K4 f0 re-rank
 // sort_by_f0_compatibility (ddsp_prematch_dataset.py:954-997): key =
 // |log2(f0[idx]+1e-5) - log2(expected+1e-5)| in fp32, stable ascending sort of the

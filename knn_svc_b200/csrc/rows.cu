@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
     const float* __restrict__ pn, int64_t n_pool, int dim, int k, const int64_t* __restrict__ row_list,
     const int* __restrict__ row_count_dev, int64_t row_count_host, int64_t slot_base, int64_t slot_cap,
     double* __restrict__ part_d, int64_t* __restrict__ part_i, int direct, int64_t index_offset,
-    float* __restrict__ out_dist, int64_t* __restrict__ out_idx, const int64_t* __restrict__ mask_lo,
-    const int64_t* __restrict__ mask_hi) {
+    float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
+    const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);                       // [EX_Q][dim]
   double* ld = reinterpret_cast<double*>(sq + (size_t)EX_Q * dim);      // [EX_WARPS][EX_Q][k]
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
           if (lane == 0) {
             if (direct) {
               out_dist[orow * k + o] = (float)bd;
+              if (out_dist64) out_dist64[orow * k + o] = bd;
               out_idx[orow * k + o] = (bi == INT64_MAX) ? -1 : bi + index_offset;
             } else {
               od[o] = bd;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) knn_exact_merge_kernel(
     const double* __restrict__ part_d, const int64_t* __restrict__ part_i, int n_chunks, int k,
     const int64_t* __restrict__ row_list, const int* __restrict__ row_count_dev, int64_t row_count_host,
     int64_t slot_base, int64_t slot_cap, int64_t index_offset, float* __restrict__ out_dist,
-    int64_t* __restrict__ out_idx) {
+    double* __restrict__ out_dist64, int64_t* __restrict__ out_idx) {
   int64_t total = row_count_host;
   if (row_count_dev) {
     total = (int64_t)*row_count_dev;
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(256) knn_exact_merge_kernel(
       last_i = si[0];
       if (threadIdx.x == 0) {
         out_dist[row * k + o] = (float)last_d;
+        if (out_dist64) out_dist64[row * k + o] = last_d;
         out_idx[row * k + o] = (last_i == INT64_MAX) ? -1 : last_i + index_offset;
       }
       __syncthreads();
@@ -409,8 +411,8 @@ size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k) {
 int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
-                          float* out_dist, int64_t* out_idx, void* partial, const int64_t* mask_lo,
-                          const int64_t* mask_hi, cudaStream_t stream) {
+                          float* out_dist, double* out_dist64, int64_t* out_idx, void* partial,
+                          const int64_t* mask_lo, const int64_t* mask_hi, cudaStream_t stream) {
   const int n_chunks = exact_chunks(n_pool);
   double* part_d = reinterpret_cast<double*>(partial);
   int64_t* part_i = reinterpret_cast<int64_t*>(part_d + (size_t)slot_cap * n_chunks * k);
@@ -427,13 +429,13 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
   knn_exact_partial_kernel<<<grid, EX_WARPS * 32, smem, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, row_list,
                                                                    row_count_dev, row_count_host, slot_base,
                                                                    slot_cap, part_d, part_i, 0, index_offset, out_dist,
-                                                                   out_idx, mask_lo, mask_hi);
+                                                                   out_dist64, out_idx, mask_lo, mask_hi);
   KNN_LAUNCH_CHECK();
   if (row_count_dev) {
     // many-rows regime (exits immediately unless the device-side count exceeds slot_cap)
     knn_exact_partial_kernel<<<dim3(1, 148 * 2), EX_WARPS * 32, smem, stream>>>(
         q, qn, n_query, p, pn, n_pool, dim, k, row_list, row_count_dev, row_count_host, slot_base, slot_cap, part_d,
-        part_i, 1, index_offset, out_dist, out_idx, mask_lo, mask_hi);
+        part_i, 1, index_offset, out_dist, out_dist64, out_idx, mask_lo, mask_hi);
     KNN_LAUNCH_CHECK();
   }
   int64_t mg = row_count_dev ? slot_cap : row_count_host;
@@ -441,7 +443,7 @@ int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, cons
   if (mg < 1) mg = 1;
   knn_exact_merge_kernel<<<(unsigned)mg, 256, 0, stream>>>(part_d, part_i, n_chunks, k, row_list, row_count_dev,
                                                            row_count_host, slot_base, slot_cap, index_offset,
-                                                           out_dist, out_idx);
+                                                           out_dist, out_dist64, out_idx);
   KNN_LAUNCH_CHECK();
   return 0;
 }

@@ -120,19 +120,42 @@ class KNeighborsVC(nn.Module):
     @torch.inference_mode()
     def match(self, query_seq: Tensor, matching_set: Tensor, query_f0: Tensor = None, synth_set: Tensor = None,
               topk: int = 4, tgt_loudness_db=-16, target_duration=None, device=None, without_vocode=False,
-              post_opt: str = "no_post_opt", matching_f0: Tensor = None) -> Tensor:
+              post_opt: str = "no_post_opt", matching_f0: Tensor = None, gather: str = "all") -> Tensor:
         """kNN regression of `query_seq` onto `matching_set` (reference :522-586; its dead
         debug block :559-576 removed).  `post_opt` other than "no_post_opt" routes the
         top-k through the concatenation-smoothness stage exactly as
-        match_at_inference_time does (greedy re-selection + fitted mixing weights)."""
+        match_at_inference_time does (greedy re-selection + fitted mixing weights).
+        `matching_set` may be a `sharded.ShardedPool` (a pool sharded by frame over the GPUs of the
+        box, one process per GPU): every rank makes the same call; with `gather="all"` (default) each
+        gets all T matched rows, with `gather="slice"` only the rows it produced."""
         device = torch.device(device) if device is not None else self.device
-        synth_set = matching_set.to(device) if synth_set is None else synth_set.to(device)
-        matching_set = matching_set.to(device)
-        query_seq = query_seq.to(device)
+        from .sharded import ShardedPool
+        sharded_pool = matching_set if isinstance(matching_set, ShardedPool) else None
+        if sharded_pool is None:
+            synth_set = matching_set.to(device) if synth_set is None else synth_set.to(device)
+            matching_set = matching_set.to(device)
+        else:
+            device = sharded_pool.device
         if target_duration is not None:
             target_samples = int(target_duration * self.sr)
             scale_factor = (target_samples / self.hop_length) / query_seq.shape[0]
             query_seq = F.interpolate(query_seq.T[None], scale_factor=scale_factor, mode="linear")[0].T
+        if sharded_pool is not None:
+            # a pool sharded by frame over the GPUs of the box (one process per GPU, sharded.py): every
+            # rank calls match() with the same query and gets all T matched rows back, bit-identical to
+            # the single-GPU result.  synth_set, if any, was given to the ShardedPool (`synth_rows`).
+            if synth_set is not None:
+                raise ValueError("pass the synth rows to ShardedPool(synth_rows=...), not to match()")
+            if "no_post_opt" not in post_opt:
+                raise NotImplementedError("post_opt on a frame-sharded pool: the greedy re-selection follows "
+                                          "`previous selection + 1` across shard boundaries; replicate the pool "
+                                          "for the post-opt stage (SURVEY 8e)")
+            out_feats = sharded_pool.match(query_seq, topk, gather=gather).feats   # host queries: upload_query
+            assert gather != "all" or out_feats.shape == query_seq.shape
+            if without_vocode:
+                return out_feats
+            f0 = None if query_f0 is None else query_f0[None, :, None].to(device)
+            return self.vocode(out_feats[None], f0).squeeze()
         q = ops.prepare_rows(query_seq)
         p = ops.prepare_rows(matching_set)
         _, idx = ops.knn_search(q, p, topk)                                   # :550-554

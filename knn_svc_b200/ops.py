@@ -139,14 +139,17 @@ def release_workspaces():
 
 def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0,
                return_stats: bool = False, mask_lo: torch.Tensor | None = None,
-               mask_hi: torch.Tensor | None = None):
+               mask_hi: torch.Tensor | None = None, return_dist64: bool = False):
     """k smallest cosine distances per query row, ascending, with int64 pool
     indices — the fused replacement of fast_cosine_dist + topk
     (ddsp_prematch_dataset.py:1196-1206, ddsp_matcher.py:550-554).
 
     `mask_lo` / `mask_hi` ([T] int64, together): the pool columns [mask_lo[t], mask_hi[t]) of
     query row t get distance exactly 1 — the offline prematch's self-utterance rule
-    `dists[:, start_index:end_index] = 1` (ddsp_prematch_dataset.py:1623-1624)."""
+    `dists[:, start_index:end_index] = 1` (ddsp_prematch_dataset.py:1623-1624).
+    `return_dist64`: also return the fp64 distances the re-score ranked by (the sharded path
+    exchanges and merges those; `dist` is their fp32 rounding).  Return order:
+    dist, idx[, dist64][, stats]."""
     if (mask_lo is None) != (mask_hi is None):
         raise ValueError("mask_lo and mask_hi must be given together")
     if not (1 <= k <= MAX_K):
@@ -159,6 +162,7 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
     T = query.n
     dist = torch.empty((T, k), dtype=torch.float32, device=dev)
     idx = torch.empty((T, k), dtype=torch.int64, device=dev)
+    dist64 = torch.empty((T, k), dtype=torch.float64, device=dev) if return_dist64 else None
     stats = torch.zeros((8,), dtype=torch.int32, device=dev)
     lib = _lib.load()
     if mask_lo is not None:
@@ -176,20 +180,45 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
             part_stats = torch.zeros((8,), dtype=torch.int32, device=dev) if chunk < T else stats
             for a in range(0, T, chunk):
                 n = min(chunk, T - a)
-                _lib.check(lib.knnsvc_knn_search_masked(
+                _lib.check(lib.knnsvc_knn_search_full(
                     query.rows[a:].data_ptr(), query.half[a:].data_ptr(), query.norms[a:].data_ptr(), n,
                     pool.rows.data_ptr(), pool.half.data_ptr(), pool.norms.data_ptr(), pool.n, query.dim,
                     query.dim_pad, k, index_offset, _ptr(query.err), _ptr(pool.err),
                     None if mask_lo is None else mask_lo[a:].data_ptr(),
                     None if mask_hi is None else mask_hi[a:].data_ptr(),
-                    dist[a:].data_ptr(), idx[a:].data_ptr(), ws.data_ptr(), ws.numel(), part_stats.data_ptr(),
-                    _stream()), "knn_search")
+                    dist[a:].data_ptr(), None if dist64 is None else dist64[a:].data_ptr(), idx[a:].data_ptr(),
+                    ws.data_ptr(), ws.numel(), part_stats.data_ptr(), _stream()), "knn_search")
                 if chunk < T:
                     stats[:3] += part_stats[:3]          # flagged rows, logged candidates, survivors
                     stats[3:] = part_stats[3:]
-    if return_stats:
-        return dist, idx, stats
-    return dist, idx
+    out = (dist, idx) + ((dist64,) if return_dist64 else ()) + ((stats,) if return_stats else ())
+    return out
+
+
+def knn_workspace_layout(n_query: int, n_pool: int, k: int) -> dict:
+    """Where knn_search keeps its candidate log inside the scratch buffer (diagnostics / tests)."""
+    import ctypes
+    arr = (ctypes.c_int64 * 8)()
+    _lib.check(_lib.load().knnsvc_knn_workspace_layout(n_query, n_pool, k, ctypes.cast(arr, ctypes.c_void_p)),
+               "knn_workspace_layout")
+    names = ("log_val", "log_idx", "log_cnt", "seg_top", "n_seg", "cap", "total")
+    return {n: int(arr[i]) for i, n in enumerate(names)}
+
+
+def knn_candidate_log(query: PreparedRows, pool: PreparedRows, k: int):
+    """Run the search and hand back what the tensor-core filter logged: (values [T*n_seg, cap] fp32 —
+    the accumulator's cosine similarities s~ —, columns [T*n_seg, cap] int32, counts [T*n_seg],
+    layout dict), plus the search result.  Test / diagnostic aid: the error-window bound
+    |s~ - s| <= eps is checked against THESE values, i.e. against what tcgen05.mma left in TMEM."""
+    T = query.n
+    res = knn_search(query, pool, k, return_stats=True)
+    lay = knn_workspace_layout(T, pool.n, k)
+    ws = _workspace(lay["total"], query.rows.device)
+    slots, cap = T * lay["n_seg"], lay["cap"]
+    val = ws[lay["log_val"]:lay["log_val"] + slots * cap * 4].view(torch.float32).view(slots, cap).clone()
+    col = ws[lay["log_idx"]:lay["log_idx"] + slots * cap * 4].view(torch.int32).view(slots, cap).clone()
+    cnt = ws[lay["log_cnt"]:lay["log_cnt"] + slots * 4].view(torch.int32).clone()
+    return val, col, cnt, lay, res
 
 
 def knn_exact(query: PreparedRows, pool: PreparedRows, k: int, index_offset: int = 0):
@@ -225,6 +254,58 @@ def merge_topk(gathered_dist: torch.Tensor, gathered_idx: torch.Tensor):
         _lib.check(lib.knnsvc_merge_topk(gd.data_ptr(), gi.data_ptr(), R, T, k, dist.data_ptr(), idx.data_ptr(),
                                          _stream()), "merge_topk")
     return dist, idx
+
+
+def merge_topk64(gathered_dist64: torch.Tensor, gathered_idx: torch.Tensor):
+    """[R, T, k] per-shard fp64 distances + global indices -> ([T,k] fp32, [T,k] fp64, [T,k] int64)
+    merged by (fp64 dist, idx): bit for bit what one search of the whole pool returns."""
+    _dev(gathered_dist64, "gathered_dist64")
+    R, T, k = gathered_dist64.shape
+    gd, gi = gathered_dist64.to(torch.float64).contiguous(), _i64c(gathered_idx)
+    dist = torch.empty((T, k), dtype=torch.float32, device=gd.device)
+    dist64 = torch.empty((T, k), dtype=torch.float64, device=gd.device)
+    idx = torch.empty((T, k), dtype=torch.int64, device=gd.device)
+    if T == 0:
+        return dist, dist64, idx
+    lib = _lib.load()
+    with torch.cuda.device(gd.device):
+        _lib.check(lib.knnsvc_merge_topk64(gd.data_ptr(), gi.data_ptr(), R, T, k, dist.data_ptr(), dist64.data_ptr(),
+                                           idx.data_ptr(), _stream()), "merge_topk64")
+    return dist, dist64, idx
+
+
+class ShardedRows:
+    """Row table of a pool that lives in several blocks — this GPU's shard plus its peers'
+    IPC-mapped shards: `ptrs[s]` is a device pointer valid in THIS process for global rows
+    [bounds[s], bounds[s+1])."""
+
+    def __init__(self, ptrs, bounds, dim: int, device):
+        import ctypes
+        assert len(bounds) == len(ptrs) + 1
+        self.n, self.dim, self.device = len(ptrs), int(dim), torch.device(device)
+        self.ptrs, self.bounds = [int(p) for p in ptrs], [int(b) for b in bounds]
+        self._ptr_arr = (ctypes.c_void_p * self.n)(*self.ptrs)
+        self._lo_arr = (ctypes.c_int64 * (self.n + 1))(*self.bounds)
+
+
+def gather_mix_sharded(table: ShardedRows, idx: torch.Tensor, weights: torch.Tensor | None = None) -> torch.Tensor:
+    """gather_mix over a sharded pool (GLOBAL indices); bit-identical to gather_mix on the
+    concatenated pool.  Rows of other GPUs are read over NVLink through their mapped pointers."""
+    import ctypes
+    _dev(idx, "indices")
+    idx = _i64c(idx)
+    T, k = idx.shape
+    w = None if weights is None else _f32c(weights.to(idx.device))
+    out = torch.empty((T, table.dim), dtype=torch.float32, device=idx.device)
+    if T == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.knnsvc_gather_mix_sharded(ctypes.cast(table._ptr_arr, ctypes.c_void_p),
+                                                 ctypes.cast(table._lo_arr, ctypes.c_void_p), table.n, table.dim,
+                                                 idx.data_ptr(), _ptr(w), T, k, out.data_ptr(), _stream()),
+                   "gather_mix_sharded")
+    return out
 
 
 def gather_mix(pool: torch.Tensor, idx: torch.Tensor, weights: torch.Tensor | None = None) -> torch.Tensor:

@@ -81,3 +81,39 @@ def harmonics_pool(n: int, h: int = N_HARM, seed: int = 0) -> np.ndarray:
         a[t] = 0.9 * a[t - 1] + 0.1 * a[t]
     a = 0.0108 * a / np.arange(1, h + 1)[None, :]
     return a.astype(np.float32)
+
+
+def ar1_frames_device(n: int, d: int = D_WAVLM, seed: int = 0, device="cuda", seg_len: int = 500, rho: float = 0.98,
+                      mean_scale: float = 3.0, mean_seed: int = 12345, out=None):
+    """Generator G of SURVEY.md §8d at dataset scale, on the GPU (torch's device generator; the
+    numbers differ from `ar1_frames`, the process is the same): independent AR(1) runs of
+    `seg_len` frames per dimension — utterances of a pool (500 frames) or the ~200-frame stretches
+    between hard resets of a query — plus the shared mean vector 3*N(0,1)^d that query and pool
+    have in common (same `mean_seed`).  Fills and returns a [n, d] fp32 tensor."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(mean_seed)
+    mean = mean_scale * torch.randn((d,), device=dev, generator=g)
+    g.manual_seed(seed)
+    x = torch.empty((n, d), dtype=torch.float32, device=dev) if out is None else out
+    assert x.shape == (n, d)
+    s = float(np.sqrt(1.0 - rho * rho))
+    n_full = n // seg_len
+    # segments are advanced in lock step, a few thousand at a time (82 MB of state per 20k segments)
+    for a in range(0, n_full, 8192):
+        b = min(n_full, a + 8192)
+        view = x[a * seg_len:b * seg_len].view(b - a, seg_len, d)
+        state = torch.randn((b - a, d), device=dev, generator=g)
+        for t in range(seg_len):
+            if t:
+                state = rho * state + s * torch.randn((b - a, d), device=dev, generator=g)
+            view[:, t] = state + mean
+    tail = n - n_full * seg_len
+    if tail:
+        state = torch.randn((d,), device=dev, generator=g)
+        for t in range(tail):
+            if t:
+                state = rho * state + s * torch.randn((d,), device=dev, generator=g)
+            x[n_full * seg_len + t] = state + mean
+    return x

@@ -32,3 +32,14 @@ def has_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+@pytest.fixture
+def small_log():
+    """candidate log of 256 slots per (row, segment) for one test: small fixtures then overflow it
+    and exercise the exact-kernel fallback; the default (2048) is restored afterwards"""
+    from knn_svc_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.knnsvc_set_option(b"log_cap", 256), "set_option")
+    yield
+    _lib.check(lib.knnsvc_set_option(b"log_cap", 0), "set_option")

@@ -45,7 +45,7 @@ def test_filter_traversal_plan_invariants():
         assert ctas == 1 and n_qt == -(-T // 128) and n_pt == -(-NP // 256)
         assert 1 <= n_seg <= min(16, n_pt) and n_blk >= 1 and units == n_qt * n_seg * n_blk
         assert 1 <= grid <= 148 and grid == min(units, 148)
-        assert cap == max(256, 64 * k)
+        assert cap == 2048
         seg_tiles = -(-n_pt // n_seg)
         assert -(-seg_tiles // n_blk) <= 96, "a block holds at most 96 pool tiles (48 MB of fp16 operand)"
         if n_qt >= 148:
@@ -103,6 +103,18 @@ def test_merge_rule_host_is_shard_invariant():
         assert torch.equal(md, torch.gather(full, 1, order))
 
 
+def test_query_slices_tile_the_batch():
+    """the rows each rank produces matched features for: contiguous, equal-sized chunks that tile [0, T)"""
+    from knn_svc_b200.sharded import query_slice
+    for T in (0, 1, 7, 100, 100_000, 100_003):
+        for world in (1, 2, 3, 8):
+            edges = [query_slice(T, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == T
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            chunk = (T + world - 1) // world
+            assert all(b - a <= chunk for a, b in edges)
+
+
 WORKER = r"""
 import os, sys, torch, numpy as np
 import torch.distributed as dist
@@ -121,6 +133,12 @@ md, mi = merge_topk_host(gd, gi)
 want = torch.argsort(full, dim=1, stable=True)[:, :k]
 assert torch.equal(mi, want), (rank, mi[0], want[0])
 assert torch.equal(md, torch.gather(full, 1, want))
+# the sharded search exchanges fp64 distances: same payload packing, dtype preserved bit for bit
+gd64, gi64 = all_gather_topk(ld.double() * (1 + 2.0 ** -40), li)
+assert gd64.dtype == torch.float64 and torch.equal(gi64, gi)
+assert torch.equal(gd64[rank], ld.double() * (1 + 2.0 ** -40))
+md64, mi64 = merge_topk_host(gd64, gi64)
+assert torch.equal(mi64, want)
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write(f"rank{rank}-ok\n"); sys.stdout.flush()

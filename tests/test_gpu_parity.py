@@ -120,7 +120,7 @@ def test_knn_search_ragged_shapes(ops, T, Np, D, k):
     check_knn_against_oracle(idx.cpu().numpy(), dist.cpu().numpy(), o_idx, o_val, k)
 
 
-def test_knn_search_ties_and_duplicates(ops):
+def test_knn_search_ties_and_duplicates(ops, small_log):
     """duplicated pool rows (exact ties), a query equal to a pool row, near ties"""
     p = synth.ar1_frames(600, seed=31)
     p[100:140] = p[50]                      # 41 identical rows
@@ -147,7 +147,7 @@ def test_knn_search_ties_and_duplicates(ops):
     assert np.array_equal(np.sort(idx2.cpu().numpy()[rows], 1), np.sort(o2_idx[rows, :4], 1))
 
 
-def test_knn_search_many_undecidable_rows(ops):
+def test_knn_search_many_undecidable_rows(ops, small_log):
     """> 1024 rows whose error window holds more candidates than the log: the device-side row list
     exceeds the chunked fallback's capacity and the direct regime of the exact kernel takes over."""
     base = synth.ar1_frames(3000, seed=35)
@@ -353,7 +353,15 @@ def test_weight_fit_matches_reference(ops, golden, name, scale):
     rows = orc._neighbour_rows(idx, np.asarray(pool, np.float64))
     l_ref = orc.smoothness_loss(ref_w.astype(np.float64), rows, scale)
     l_got = orc.smoothness_loss(w.astype(np.float64), rows, scale)
-    assert abs(l_ref - l_got) <= 1e-5 * abs(l_ref) + 1e-7, (l_ref, l_got)   # SURVEY D13 gate
+    rel_loss = abs(l_ref - l_got) / abs(l_ref)
+    import json
+    from pathlib import Path
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    with open(out / "r2_k6_deviation.jsonl", "a") as f:
+        f.write(json.dumps({"fit": name, "stop_iteration": int(info[0]), "loss_ref": l_ref, "loss_ours": l_got,
+                            "loss_rel_dev": rel_loss, "max_abs_weight_dev": float(np.abs(w - ref_w).max())}) + "\n")
+    assert rel_loss <= 1e-6, (l_ref, l_got)                                 # SURVEY D13 / §8d gate: 1e-6 relative
     assert abs(info[1] - l_got) <= 1e-6 * abs(l_got) + 1e-9                  # kernel's own loss is the true loss
     assert np.all(w >= 0) and np.all(w <= 1) and np.allclose(w.sum(1), 1, atol=1e-6)
     print(f"K6 {name}: max |w - w_ref| = {np.abs(w - ref_w).max():.3e} (reported, not gated at 1e-4: D13)")
@@ -547,7 +555,7 @@ def filter_options():
 
 
 @pytest.mark.parametrize("block_tiles,flags,cta_group", [(1, 1, 1), (2, 1, 1), (3, 0, 1), (1, 5, 1), (2, 5, 2), (1, 1, 2)])
-def test_knn_search_block_traversal_changes_nothing(ops, filter_options, block_tiles, flags, cta_group):
+def test_knn_search_block_traversal_changes_nothing(ops, filter_options, small_log, block_tiles, flags, cta_group):
     """The filter walks the pool in L2-sized blocks, handing each row's state (top-k list, candidate
     log) from block to block through global memory, with units claimed dynamically or split statically,
     by one CTA or a CTA pair.  Tiny blocks (256-768 pool rows) force several hand-overs per chain on sets

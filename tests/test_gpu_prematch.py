@@ -76,7 +76,7 @@ def test_masked_search_distance_one_semantics(ops):
     assert np.all(o_val[:, :10] == 1.0) and np.all(o_val[:, 10] > 1.0)
 
 
-def test_masked_search_through_exact_fallback(ops):
+def test_masked_search_through_exact_fallback(ops, small_log):
     """hundreds of duplicated pool rows overflow the candidate log -> the exact brute-force
     kernel decides, and it must honour the mask too"""
     base = synth.ar1_frames(3000, seed=94)

@@ -1,0 +1,266 @@
+"""Round-2 parity additions (VERDICT r1 "next round" 1b-1d, weak 5), through the C ABI:
+
+  * the tensor-core accumulator values themselves (read back from the filter's candidate log) are
+    inside the error window the search relies on, on adversarial rows, dim 1024 and 4096, fp16 and
+    bf16 operands;
+  * BASELINE cfg 1 / cfg 2 at their real shape (T = Np = 3001, real f0 tracks) against the
+    reference's own outputs (tests/golden/make_golden_cfg12.py);
+  * KNeighborsVC.match(post_opt=...) checked for VALUES against the oracle's composition;
+  * gather_mix over a sharded row table == gather_mix over the contiguous pool (bit for bit).
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from knn_svc_b200 import synth
+from oracle import matcher_oracle as orc
+from tests.util import GAP, check_knn_against_oracle, positions_untied, set_rows
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from knn_svc_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def _set_opt(name, value):
+    from knn_svc_b200 import _lib
+    _lib.check(_lib.load().knnsvc_set_option(name.encode(), int(value)), "set_option")
+
+
+def _adversarial_rows(n, d, seed):
+    """rows that stress the accumulator: all-positive mean-shifted (WavLM-like: every product has
+    the same sign, partial sums grow monotonically to ~1), heavy-tailed, near-duplicates of each
+    other (s ~ 1), sign-flipped copies (s ~ -1), a few huge components, tiny components"""
+    rs = np.random.RandomState(seed)
+    x = np.abs(rs.standard_normal((n, d))) + 3.0                       # all positive, common mean
+    x[n // 4: n // 2] = rs.standard_t(2.0, size=(n // 2 - n // 4, d))  # heavy tails
+    x[n // 2: n // 2 + 8] = x[:8] * (1 + 1e-3 * rs.standard_normal((8, d)))       # near duplicates
+    x[n // 2 + 8: n // 2 + 16] = -x[:8]                                # anti-parallel
+    x[n // 2 + 16: n // 2 + 24, :4] *= 300.0                           # energy in a few components
+    x[n // 2 + 24: n // 2 + 32] = 1e-3 * rs.standard_normal((8, d)) + 1.0          # nearly constant rows
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+@pytest.mark.parametrize("dim", [1024, 4096])
+def test_filter_accumulator_error_is_inside_the_window(ops, dim, fmt):
+    """|s~ - s| <= eps with s~ the value tcgen05.mma left in TMEM (as logged by the filter's
+    epilogue), s the exact fp64 cosine similarity and eps the window the search uses — and the
+    accumulator's own share |s~ - (u_q . u_p)| <= acc_eps(dim), u the fp16/bf16 operands.  A pool of
+    k = 32 rows makes the filter log EVERY column (its threshold only exists once k values were seen),
+    so the whole accumulator tile is read back, chunk by chunk."""
+    _set_opt("bf16_operands", fmt == "bf16")
+    try:
+        q = _adversarial_rows(256, dim, seed=1)
+        p = np.concatenate([_adversarial_rows(192, dim, seed=2), q[:64] * 0.5])      # incl. exact parallels
+        qp, pp_all = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p))
+        scale = 1024.0
+        uq = (qp.half.view(torch.bfloat16) if fmt == "bf16" else qp.half).double().cpu().numpy()[:, :dim] / scale
+        unit_q = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64), axis=1, keepdims=True)
+        acc_eps = 1.4e-4 * max(1.0, dim / 1024.0)
+        worst_total, worst_acc, n_vals = 0.0, 0.0, 0
+        for a in range(0, len(p), 32):
+            chunk = p[a:a + 32]
+            pp = ops.prepare_rows(dev(chunk))
+            val, col, cnt, lay, _ = ops.knn_candidate_log(qp, pp, 32)
+            assert lay["n_seg"] == 1 and int(cnt.min()) == 32 and int(cnt.max()) == 32, "every column must be logged"
+            val, col = val[:, :32].double().cpu().numpy(), col[:, :32].cpu().numpy().astype(np.int64)
+            up = (pp.half.view(torch.bfloat16) if fmt == "bf16" else pp.half).double().cpu().numpy()[:, :dim] / scale
+            unit_p = chunk.astype(np.float64) / np.linalg.norm(chunk.astype(np.float64), axis=1, keepdims=True)
+            s_exact = np.take_along_axis(unit_q @ unit_p.T, col, axis=1)
+            s_oper = np.take_along_axis(uq @ up.T, col, axis=1)
+            eps = float(qp.err.item()) + float(pp.err.item()) + float(qp.err.item()) * float(pp.err.item()) + acc_eps
+            worst_total = max(worst_total, float(np.abs(val - s_exact).max() / eps))
+            worst_acc = max(worst_acc, float(np.abs(val - s_oper).max()))
+            n_vals += val.size
+        print(f"accumulator check dim={dim} {fmt}: {n_vals} values, max |s~-s|/eps = {worst_total:.3f}, "
+              f"max |s~ - u_q.u_p| = {worst_acc:.2e} (bound {acc_eps:.1e})")
+        out = ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        with open(out / "r2_accumulator_check.jsonl", "a") as f:
+            f.write(json.dumps({"dim": dim, "operands": fmt, "values": n_vals, "max_err_over_eps": worst_total,
+                                "max_accumulator_err": worst_acc, "acc_eps_bound": acc_eps}) + "\n")
+        assert worst_total <= 1.0
+        assert worst_acc <= acc_eps
+    finally:
+        _set_opt("bf16_operands", 0)
+
+
+def test_filter_log_holds_every_true_neighbour_with_its_accumulator_value(ops):
+    """on a WavLM-like set at a realistic size: every true top-32 member is in the log, and each
+    logged s~ is within the measured eps of the exact similarity"""
+    q, p = synth.ar1_frames(300, seed=41, reset_every=100), synth.ar1_frames(30000, seed=42)
+    qp, pp = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(p))
+    val, col, cnt, lay, res = ops.knn_candidate_log(qp, pp, 32)
+    assert int(res[2][0]) == 0                          # no row needed the exact fallback
+    n_seg, cap = lay["n_seg"], lay["cap"]
+    val, col, cnt = val.cpu().numpy(), col.cpu().numpy(), cnt.cpu().numpy()
+    o_idx, o_val = orc.knn(q, p, 33)
+    unit_q = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64), axis=1, keepdims=True)
+    unit_p = p.astype(np.float64) / np.linalg.norm(p.astype(np.float64), axis=1, keepdims=True)
+    eps = float(qp.err.item()) + float(pp.err.item()) + float(qp.err.item()) * float(pp.err.item()) + 1.4e-4
+    worst = 0.0
+    for t in range(len(q)):
+        logged = {}
+        for s in range(n_seg):
+            n = min(int(cnt[t * n_seg + s]), cap)
+            logged.update(zip(col[t * n_seg + s, :n].tolist(), val[t * n_seg + s, :n].tolist()))
+        assert set(o_idx[t, :32].tolist()) <= set(logged), f"row {t}: a true neighbour is missing from the log"
+        cols = np.fromiter(logged.keys(), dtype=np.int64)
+        s_exact = unit_p[cols] @ unit_q[t]
+        worst = max(worst, float(np.abs(np.fromiter(logged.values(), dtype=np.float64) - s_exact).max()))
+    print(f"logged s~ vs exact on 300x30000 AR(1): max |s~ - s| = {worst:.2e}, eps = {eps:.2e}")
+    assert worst <= eps
+
+
+# ----------------------------------------------------------------------------- cfg 1 / cfg 2, real shape
+@pytest.fixture(scope="module")
+def golden12():
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_outputs_cfg12.npz"))
+
+
+def _cfg12_inputs(g):
+    T = len(g["f0_src"])
+    qf = synth.ar1_frames(T, seed=301, reset_every=200)
+    pf = synth.ar1_frames(T, seed=302)
+    hp = synth.harmonics_pool(T, seed=303)
+    return qf, pf, g["f0_src"], g["f0_tgt"], hp
+
+
+def test_cfg12_search_and_reselection_match_the_reference(ops, golden12):
+    """T = Np = 3001: top-32 indices, f0 re-rank and BOTH greedy re-selections over all 3001 frames
+    (the recurrence is compared up to the first legitimately tied row, of which there is none here)"""
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    qf, pf, f0q, f0p, hp = _cfg12_inputs(golden12)
+    qp, pp = ops.prepare_rows(dev(qf)), ops.prepare_rows(dev(pf))
+    dist, idx = ops.knn_search(qp, pp, 32)
+    o_idx, o_val = golden12["nbrs33"].astype(np.int64), golden12["vals33"]
+    check_knn_against_oracle(idx.cpu().numpy(), dist.cpu().numpy(), o_idx, o_val, 32)
+    # downstream stages are fed the REFERENCE's indices so that each stage is pinned on its own
+    ref32 = dev(o_idx[:, :32])
+    shifted = pm.shift_query_f0(torch.from_numpy(f0q), torch.from_numpy(f0p))
+    prio = pm.sort_by_f0_compatibility(shifted, dev(f0p), ref32).cpu().numpy()
+    assert np.array_equal(prio, golden12["prio32"])
+    sel = pm.knn_with_concat_cost(ref32[:, :4].contiguous(), qp.rows, pp.rows, concat_weight=0.2).cpu().numpy()
+    assert np.array_equal(sel, golden12["k5_nof0"]), int((sel != golden12["k5_nof0"]).any(1).argmax())
+    sel_f0 = pm.knn_with_concat_cost(dev(golden12["prio32"][:, :4].astype(np.int64)), qp.rows, pp.rows, shifted.to(DEV),
+                                     dev(f0p), concat_weight=0.2).cpu().numpy()
+    assert np.array_equal(sel_f0, golden12["k5_f0"]), int((sel_f0 != golden12["k5_f0"]).any(1).argmax())
+
+
+@pytest.mark.parametrize("post_opt", ["no_post_opt", "post_opt_0.2"])
+def test_cfg12_pipeline_matches_the_reference(ops, golden12, post_opt):
+    """match_at_inference_time at cfg 1 / cfg 2 shape against the reference's run of the same call"""
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    qf, pf, f0q, f0p, hp = _cfg12_inputs(golden12)
+
+    def fake_pool(wav, *a, **k):
+        if "src" in str(wav):
+            feats, f0, n, harm = torch.from_numpy(qf).double(), torch.from_numpy(f0q), len(qf), torch.zeros(len(qf), 49)
+        else:
+            feats, f0, n, harm = torch.from_numpy(pf).double(), torch.from_numpy(f0p), len(pf), torch.from_numpy(hp)
+        key = str(wav)
+        return ({key: feats}, {key: feats}, {key: torch.zeros(n, 320)}, {key: torch.ones(n, 201)}, {key: f0}, {key: harm})
+
+    old = pm.get_complete_spk_pool
+    pm.get_complete_spk_pool = fake_pool
+    try:
+        feats, harm, audio, sf0 = pm.match_at_inference_time(
+            Path("/x/src.wav"), Path("/x/ref.wav"), None, None, None, device=DEV, prioritize_f0=True,
+            ckpt_type="mix", src_dataset_path="/x", tgt_dataset_path="/x", post_opt=post_opt)
+    finally:
+        pm.get_complete_spk_pool = old
+    tag = post_opt.replace(".", "p")
+    fe = feats["/x/src.wav"].cpu().numpy()
+    ref = golden12[f"{tag}_feats_sub"]
+    ha, ref_h = harm["/x/src.wav"].cpu().numpy(), golden12[f"{tag}_harm"]
+    rel = np.abs(fe[:, ::16] - ref).max() / np.abs(ref).max()
+    rel_sum = np.abs(fe.astype(np.float64).sum(1) - golden12[f"{tag}_feats_rowsum"]).max() / np.abs(golden12[f"{tag}_feats_rowsum"]).max()
+    relh = np.abs(ha - ref_h).max() / np.abs(ref_h).max()
+    relf = np.abs(sf0["/x/src.wav"].numpy() - golden12[f"{tag}_f0"]).max() / golden12[f"{tag}_f0"].max()
+    print(f"cfg1/2 pipeline {post_opt} (3001 x 3001): feats rel {rel:.2e}, row sums rel {rel_sum:.2e}, "
+          f"harmonics rel {relh:.2e}, f0 rel {relf:.2e}")
+    with open(ROOT / "gpurun_out" / "r2_cfg12_deviation.jsonl", "a") as f:
+        f.write(json.dumps({"post_opt": post_opt, "feats_rel": float(rel), "rowsum_rel": float(rel_sum),
+                            "harmonics_rel": float(relh), "f0_rel": float(relf)}) + "\n")
+    assert relf <= 1e-6
+    if post_opt == "no_post_opt":
+        assert rel <= 1e-4 and relh <= 1e-4 and rel_sum <= 1e-4      # north-star tolerance
+    else:
+        assert rel < 5e-3 and relh < 5e-2                            # passes through the Adam fit
+
+
+# ----------------------------------------------------------------------------- match(post_opt) values
+def test_matcher_match_post_opt_values(ops):
+    """KNeighborsVC.match(post_opt="post_opt_0.2") == oracle composition: kNN -> greedy re-selection
+    -> fitted mixing weights -> mix.  Indices exact; the features inherit the Adam fit's conditioning
+    (SURVEY D13), so they are gated through the achieved smoothness loss and a loose bound."""
+    from knn_svc_b200.ddsp_matcher import KNeighborsVC
+    m = KNeighborsVC(None, None, None, device=DEV)
+    q, p = synth.ar1_frames(160, seed=171, reset_every=60), synth.ar1_frames(900, seed=172)
+    out = m.match(torch.from_numpy(q), torch.from_numpy(p), topk=4, without_vocode=True, post_opt="post_opt_0.2")
+    o_idx, o_val = orc.knn(q, p, 5)
+    assert set_rows(o_val, 4).all(), "fixture: the top-4 sets must be determined"
+    sel = orc.knn_with_concat_cost(o_idx[:, :4], q, p, concat_weight=0.2)
+    w = orc.compute_wavlm_weight(sel, p)
+    want = orc.gather_mix(p, sel, w)
+    got = out.cpu().numpy()
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    rows = orc._neighbour_rows(sel, np.asarray(p, np.float64))
+    # recover our weights' loss from the features is not possible; compare the loss of the oracle's fit with
+    # the loss of OUR fit on the same indices
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    w_ours = pm.compute_wavlm_weight(dev(sel), dev(p)).cpu().numpy().astype(np.float64)
+    l_ref, l_got = orc.smoothness_loss(w.astype(np.float64), rows, 0.1), orc.smoothness_loss(w_ours, rows, 0.1)
+    print(f"match(post_opt_0.2): feats rel {rel:.2e}; loss ref {l_ref:.9e} ours {l_got:.9e}")
+    assert abs(l_ref - l_got) <= 1e-6 * abs(l_ref) + 1e-9
+    assert rel < 5e-3
+    # and the no-fit / no-reselect corner: post_opt string that parses to -1 but is not "no_post_opt"
+    out3 = m.match(torch.from_numpy(q), torch.from_numpy(p), topk=4, without_vocode=True, post_opt="no_post_opt")
+    assert np.abs(out3.cpu().numpy() - orc.gather_mix(p, o_idx[:, :4], None)).max() <= 1e-4 * np.abs(want).max()
+
+
+# ----------------------------------------------------------------------------- sharded row table (one GPU)
+@pytest.mark.parametrize("dim", [1024, 49])
+def test_gather_mix_sharded_equals_contiguous(ops, dim):
+    rs = np.random.RandomState(3)
+    pool = synth.randn_frames(5000, d=dim, seed=5)
+    bounds = [0, 1, 1700, 1700, 3333, 5000]                    # a 1-row shard and an empty shard
+    pool_t = dev(pool)
+    parts = [pool_t[a:b].clone() if b > a else pool_t[:1].clone() for a, b in zip(bounds[:-1], bounds[1:])]
+    table = ops.ShardedRows([t.data_ptr() for t in parts], bounds, dim, torch.device(DEV))
+    idx = rs.randint(0, 5000, size=(777, 4)).astype(np.int64)
+    idx[0] = [0, 1, 1699, 1700]; idx[1] = [3332, 3333, 4999, 0]
+    w = rs.rand(777, 4).astype(np.float32)
+    for weights in (None, dev(w)):
+        a = ops.gather_mix(pool_t, dev(idx), weights)
+        b = ops.gather_mix_sharded(table, dev(idx), weights)
+        assert torch.equal(a, b)
+    assert ops.gather_mix_sharded(table, dev(idx[:0]), None).shape == (0, dim)
+
+
+def test_merge_topk64_ranks_on_fp64(ops):
+    """two fp64 distances that round to the SAME fp32 value: the fp64 merge keeps their order, and
+    shards that hold exact duplicates resolve to the lower global index"""
+    a, b = 0.25, 0.25 + 2.0 ** -40
+    gd = torch.tensor([[[b, 0.9]], [[a, 0.8]]], dtype=torch.float64, device=DEV)      # [R=2, T=1, k=2]
+    gi = torch.tensor([[[5, 6]], [[70, 80]]], dtype=torch.int64, device=DEV)
+    d, d64, i = ops.merge_topk64(gd, gi)
+    assert i.tolist() == [[70, 5]] and d64.tolist() == [[a, b]] and d[0, 0] == d[0, 1]
+    gd = torch.tensor([[[a, 0.9]], [[a, 0.8]]], dtype=torch.float64, device=DEV)
+    d, d64, i = ops.merge_topk64(gd, gi)
+    assert i.tolist() == [[5, 70]]
