@@ -319,6 +319,10 @@ def run_search(args, env):
     ms_e2e = env.timed(e2e_step, args.steps, max(1, args.warmup // 2))[0]
 
     verify = None if args.no_verify else verify_search(env, pool, query, k, shard, lo, n_shard, NP)
+    # candidate statistics of one search of this rank's shard (outside the timed region)
+    st = ops.knn_search(ops.prepare_rows(query, check=False), pool.prepared, k, index_offset=lo, return_stats=True)[2].tolist()
+    search_stats = {"rows_through_exact_fallback": st[0], "logged_candidates_per_row": st[1] / T,
+                    "rescored_survivors_per_row": st[2] / T, "pool_segments": st[3], "work_units": st[4], "log_cap": st[6]}
     if rank == 0:
         peaks, peak_src = _peaks()
         flops = 2.0 * T * n_shard * DIM                     # algorithmic FLOPs of one filter launch (per GPU)
@@ -362,7 +366,7 @@ def run_search(args, env):
                                 "validation included (bytes are totals over ranks: at N>1 each rank moves its 1/N "
                                 "slice over PCIe and the batch is replicated over NVLink); pool resident and prepared "
                                 "in HBM (built once, as get_matching_set does)"},
-                "gpu_launches": launches, "clocks": clocks, "verify": verify}
+                "gpu_launches": launches, "clocks": clocks, "verify": verify, "search_stats": search_stats}
         print(json.dumps(line))
     pool.close()
     return 0

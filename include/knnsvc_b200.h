@@ -39,7 +39,8 @@ int knnsvc_version(void);
  * ddsp_matcher.py:215-216, and prepares the tensor-core operand.
  *   x        [rows, ld] fp32, first `dim` columns used
  *   half_out [rows, dim_pad] fp16 = fp16(x * 1024/|x|), zero in the pad columns
- *   norms    [rows] fp32 = |x|
+ *   norms    [rows] fp64 = |x| (fp64-accumulated; the re-score divides by these, so that its
+ *            distances carry no fp32 rounding of the norms: ~1e-16, not 6e-8)
  *   bad_rows int counter, incremented per zero-norm / non-finite row (the
  *            reference NaNs and exits there, lib_ongaku_test.py:166-169)
  *   max_err  optional float, ZEROED BY THE CALLER: receives max over rows of
@@ -48,7 +49,7 @@ int knnsvc_version(void);
  *            then assumes the fp16 worst case)
  */
 int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld,
-                        void* half_out, int dim_pad, float* norms,
+                        void* half_out, int dim_pad, double* norms,
                         int* bad_rows, float* max_err, void* stream);
 
 /* ---- K1 full matrix (API parity only; never on the fused path) -----------
@@ -77,8 +78,8 @@ size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, 
 /* The traversal the search would use for this shape (host-only, no GPU work): plan_host int[8] <-
  * {CTAs per MMA, query tiles, pool tiles, pool segments, blocks per chain, work units, grid, log cap}. */
 int knnsvc_knn_plan(int64_t n_query, int64_t n_pool, int k, int* plan_host);
-int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query,
-                      const float* p, const void* ph, const float* pn, int64_t n_pool,
+int knnsvc_knn_search(const float* q, const void* qh, const double* qn, int64_t n_query,
+                      const float* p, const void* ph, const double* pn, int64_t n_pool,
                       int dim, int dim_pad, int k, int64_t index_offset,
                       const float* q_err, const float* p_err,
                       float* out_dist, int64_t* out_idx,
@@ -89,8 +90,8 @@ int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n
  * DEFINED as 1, exactly what the offline prematch does to an utterance's own frames —
  * `dists[:, start_index:end_index] = 1` before `.topk(k=32)`, ddsp_prematch_dataset.py:1608-1632
  * (per_spk_extract).  mask_lo/mask_hi: device int64 [n_query]; both NULL = knnsvc_knn_search. */
-int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query,
-                             const float* p, const void* ph, const float* pn, int64_t n_pool,
+int knnsvc_knn_search_masked(const float* q, const void* qh, const double* qn, int64_t n_query,
+                             const float* p, const void* ph, const double* pn, int64_t n_pool,
                              int dim, int dim_pad, int k, int64_t index_offset,
                              const float* q_err, const float* p_err,
                              const int64_t* mask_lo, const int64_t* mask_hi,
@@ -101,8 +102,8 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
  * the fp64 cosine distances the re-score ranked by (out_dist is their fp32 rounding).  The
  * sharded path (C1) exchanges and merges THESE, so a pool searched in N shards returns bit for bit
  * what one search of the whole pool returns. */
-int knnsvc_knn_search_full(const float* q, const void* qh, const float* qn, int64_t n_query,
-                           const float* p, const void* ph, const float* pn, int64_t n_pool,
+int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int64_t n_query,
+                           const float* p, const void* ph, const double* pn, int64_t n_pool,
                            int dim, int dim_pad, int k, int64_t index_offset,
                            const float* q_err, const float* p_err,
                            const int64_t* mask_lo, const int64_t* mask_hi,
@@ -141,8 +142,8 @@ int knnsvc_filter_timing_collect(float* ms_host, int max_n);
 /* Exact brute-force kNN on CUDA cores (same outputs as knnsvc_knn_search).
  * Used for rows the filter flags, and by tests as an independent GPU check. */
 size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k);
-int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query,
-                     const float* p, const float* pn, int64_t n_pool, int dim, int k,
+int knnsvc_knn_exact(const float* q, const double* qn, int64_t n_query,
+                     const float* p, const double* pn, int64_t n_pool, int dim, int k,
                      int64_t index_offset, float* out_dist, int64_t* out_idx,
                      void* workspace, size_t workspace_bytes, void* stream);
 

@@ -153,7 +153,7 @@ extern "C" {
 const char* knnsvc_last_error(void) { return g_err; }
 int knnsvc_version(void) { return 100; }
 
-int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad, float* norms,
+int knnsvc_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad, double* norms,
                         int* bad_rows, float* max_err, void* stream) {
   KNN_CHECK_ARG(rows >= 0 && dim >= 1 && ld >= dim && dim_pad >= dim, -1, "prepare_rows: bad shape");
   if (rows == 0) return 0;   // an empty row set has no storage to point at
@@ -183,16 +183,16 @@ int knnsvc_knn_plan(int64_t n_query, int64_t n_pool, int k, int* plan_host) {
   return 0;
 }
 
-int knnsvc_knn_search(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
-                      const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+int knnsvc_knn_search(const float* q, const void* qh, const double* qn, int64_t n_query, const float* p,
+                      const void* ph, const double* pn, int64_t n_pool, int dim, int dim_pad, int k,
                       int64_t index_offset, const float* q_err, const float* p_err, float* out_dist,
                       int64_t* out_idx, void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
   return knnsvc_knn_search_masked(q, qh, qn, n_query, p, ph, pn, n_pool, dim, dim_pad, k, index_offset, q_err, p_err,
                                   nullptr, nullptr, out_dist, out_idx, workspace, workspace_bytes, stats, stream_);
 }
 
-int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
-                             const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+int knnsvc_knn_search_masked(const float* q, const void* qh, const double* qn, int64_t n_query, const float* p,
+                             const void* ph, const double* pn, int64_t n_pool, int dim, int dim_pad, int k,
                              int64_t index_offset, const float* q_err, const float* p_err,
                              const int64_t* mask_lo, const int64_t* mask_hi, float* out_dist, int64_t* out_idx,
                              void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
@@ -201,8 +201,8 @@ int knnsvc_knn_search_masked(const float* q, const void* qh, const float* qn, in
                                 stream_);
 }
 
-int knnsvc_knn_search_full(const float* q, const void* qh, const float* qn, int64_t n_query, const float* p,
-                           const void* ph, const float* pn, int64_t n_pool, int dim, int dim_pad, int k,
+int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int64_t n_query, const float* p,
+                           const void* ph, const double* pn, int64_t n_pool, int dim, int dim_pad, int k,
                            int64_t index_offset, const float* q_err, const float* p_err, const int64_t* mask_lo,
                            const int64_t* mask_hi, float* out_dist, double* out_dist64, int64_t* out_idx,
                            void* workspace, size_t workspace_bytes, int* stats, void* stream_) {
@@ -327,7 +327,7 @@ size_t knnsvc_knn_exact_workspace_bytes(int64_t n_query, int64_t n_pool, int k) 
   return exact_partial_bytes(slots, n_pool, k) + 256;
 }
 
-int knnsvc_knn_exact(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+int knnsvc_knn_exact(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                      int64_t n_pool, int dim, int k, int64_t index_offset, float* out_dist, int64_t* out_idx,
                      void* workspace, size_t workspace_bytes, void* stream) {
   KNN_CHECK_ARG(n_query >= 0 && n_pool >= 1 && dim >= 1, -1, "knn_exact: bad shape");

@@ -18,12 +18,12 @@ int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA 
 
 // ---- rows.cu
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
-                        float* norms, int* bad_rows, float* max_err, cudaStream_t stream);
+                        double* norms, int* bad_rows, float* max_err, cudaStream_t stream);
 int launch_cosine_dist(const float* q, int64_t nq, const float* p, int64_t np_, int dim, float* out,
                        cudaStream_t stream);
 int exact_chunks(int64_t n_pool);
 size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k);
-int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+int launch_knn_exact_rows(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
                           float* out_dist, double* out_dist64, int64_t* out_idx, void* partial,
@@ -42,7 +42,7 @@ size_t filter_flag_count(const FilterPlan& pl);
 
 // ---- knn_select.cu
 constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb
-int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, double* out_dist64, int64_t* out_idx, int64_t* flag_list, int* flag_count,

@@ -75,8 +75,8 @@ __device__ __forceinline__ void rs_dot2(const float* __restrict__ pa, const floa
 }
 
 __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
-    const float* __restrict__ q, const float* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
-    const float* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
+    const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
+    const double* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
     const float* __restrict__ log_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
     const float* __restrict__ seg_top, int64_t index_offset, float* __restrict__ out_dist,
     double* __restrict__ out_dist64, int64_t* __restrict__ out_idx, int64_t* __restrict__ flag_list,
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
       continue;
     }
     const float thr = s_thr;
-    const double qnorm = (double)qn[row];
+    const double qnorm = qn[row];
     // masked column range: distance defined as 1 (ddsp_prematch_dataset.py:1623-1624)
     const int64_t m_lo = mask_lo ? mask_lo[row] : 0, m_hi = mask_lo ? mask_hi[row] : 0;
     int n_scored = 0;   // entries [0, n_scored) of the list already carry their exact distance
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
         if (vec) rs_dot2<true>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, s_q, dim, lane, da, db);
         else rs_dot2<false>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, s_q, dim, lane, da, db);
         if (lane == 0) {
-          s_dist[e] = (ia >= m_lo && ia < m_hi) ? 1.0 : 1.0 - da / (qnorm * (double)pn[ia]);
-          if (has_b) s_dist[e + 1] = (ib >= m_lo && ib < m_hi) ? 1.0 : 1.0 - db / (qnorm * (double)pn[ib]);
+          s_dist[e] = (ia >= m_lo && ia < m_hi) ? 1.0 : 1.0 - da / (qnorm * pn[ia]);
+          if (has_b) s_dist[e + 1] = (ib >= m_lo && ib < m_hi) ? 1.0 : 1.0 - db / (qnorm * pn[ib]);
         }
       }
       n_scored = n;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
   }
 }
 
-int launch_knn_rescore(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
                        float* out_dist, double* out_dist64, int64_t* out_idx, int64_t* flag_list, int* flag_count,

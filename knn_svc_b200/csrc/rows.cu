@@ -19,7 +19,7 @@ namespace knnsvc {
 // One warp per row; HBM-bound: reads dim*4 B, writes dim_pad*2 + 4 B per row.
 __global__ void __launch_bounds__(256) prepare_rows_kernel(
     const float* __restrict__ x, int64_t rows, int dim, int64_t ld,
-    __half* __restrict__ hout, int dim_pad, float* __restrict__ norms, int* __restrict__ bad_rows, int bf16,
+    __half* __restrict__ hout, int dim_pad, double* __restrict__ norms, int* __restrict__ bad_rows, int bf16,
     float* __restrict__ max_err) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) prepare_rows_kernel(
     const double nrm = sqrt(ss);
     const bool bad = !(nrm > 0.0) || !isfinite(nrm);
     if (lane == 0) {
-      norms[r] = (float)nrm;
+      norms[r] = nrm;
       if (bad) atomicAdd(bad_rows, 1);
     }
     const float sc = bad ? 0.0f : (float)((double)kHalfScale / nrm);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) prepare_rows_kernel(
 }
 
 int launch_prepare_rows(const float* x, int64_t rows, int dim, int64_t ld, void* half_out, int dim_pad,
-                        float* norms, int* bad_rows, float* max_err, cudaStream_t stream) {
+                        double* norms, int* bad_rows, float* max_err, cudaStream_t stream) {
   if (rows == 0) return 0;
   int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -211,8 +211,8 @@ __device__ __forceinline__ bool ex_less(double da, int64_t ia, double db, int64_
 }
 
 __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
-    const float* __restrict__ q, const float* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
-    const float* __restrict__ pn, int64_t n_pool, int dim, int k, const int64_t* __restrict__ row_list,
+    const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
+    const double* __restrict__ pn, int64_t n_pool, int dim, int k, const int64_t* __restrict__ row_list,
     const int* __restrict__ row_count_dev, int64_t row_count_host, int64_t slot_base, int64_t slot_cap,
     double* __restrict__ part_d, int64_t* __restrict__ part_i, int direct, int64_t index_offset,
     float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
       int64_t r = -1;
       if (s < total) r = row_list ? row_list[s] : (slot_base + s);
       rows_s[threadIdx.x] = r;
-      qn_s[threadIdx.x] = (r >= 0) ? (double)qn[r] : 1.0;
+      qn_s[threadIdx.x] = (r >= 0) ? qn[r] : 1.0;
       mlo_s[threadIdx.x] = (r >= 0 && mask_lo) ? mask_lo[r] : 0;
       mhi_s[threadIdx.x] = (r >= 0 && mask_lo) ? mask_hi[r] : 0;
     }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
 #pragma unroll
         for (int qi = 0; qi < EX_Q; ++qi)
           if (qi == lane) dot = acc[qi];
-        double d = 1.0 - dot / (qn_s[lane] * (double)pn[pr]);
+        double d = 1.0 - dot / (qn_s[lane] * pn[pr]);
         if (pr >= mlo_s[lane] && pr < mhi_s[lane]) d = 1.0;
         double* ldq = ld + (warp * EX_Q + lane) * k;
         int64_t* liq = li + (warp * EX_Q + lane) * k;
@@ -408,7 +408,7 @@ size_t exact_partial_bytes(int64_t slots, int64_t n_pool, int k) {
 
 // Runs the exact kNN for `slots` rows: either the device-side list (row_list,
 // row_count_dev; at most slot_cap rows) or the contiguous rows [slot_base, slot_base+row_count_host).
-int launch_knn_exact_rows(const float* q, const float* qn, int64_t n_query, const float* p, const float* pn,
+int launch_knn_exact_rows(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                           int64_t n_pool, int dim, int k, const int64_t* row_list, const int* row_count_dev,
                           int64_t row_count_host, int64_t slot_base, int64_t slot_cap, int64_t index_offset,
                           float* out_dist, double* out_dist64, int64_t* out_idx, void* partial,

@@ -134,6 +134,7 @@ class KNeighborsVC(nn.Module):
         if sharded_pool is None:
             synth_set = matching_set.to(device) if synth_set is None else synth_set.to(device)
             matching_set = matching_set.to(device)
+            query_seq = query_seq.to(device)
         else:
             device = sharded_pool.device
         if target_duration is not None:

@@ -59,7 +59,7 @@ class PreparedRows:
     """A [n, dim] fp32 row set with its norms and the fp16 tensor-core operand."""
     rows: torch.Tensor      # [n, dim] fp32
     half: torch.Tensor      # [n, dim_pad] fp16 = fp16(rows * 1024/|row|)
-    norms: torch.Tensor     # [n] fp32
+    norms: torch.Tensor     # [n] fp64 (fp64-accumulated |row|)
     err: torch.Tensor = None  # [1] fp32: max over rows of |half/1024 - row/|row||_2 (measured rounding error)
 
     @property
@@ -86,7 +86,7 @@ def prepare_rows(x: torch.Tensor, check: bool = True) -> PreparedRows:
     n, dim = x.shape
     dim_pad = (dim + _HALF_ALIGN - 1) // _HALF_ALIGN * _HALF_ALIGN
     half = torch.empty((n, dim_pad), dtype=torch.float16, device=x.device)
-    norms = torch.empty((n,), dtype=torch.float32, device=x.device)
+    norms = torch.empty((n,), dtype=torch.float64, device=x.device)
     scal = torch.zeros((2,), dtype=torch.int32, device=x.device)     # [0] bad-row counter, [1] max error (float bits)
     bad, err = scal[0:1], scal[1:2].view(torch.float32)
     lib = _lib.load()
