@@ -71,8 +71,9 @@ int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t 
  *   q_err/p_err   the max_err scalars knnsvc_prepare_rows produced for the two row
  *             sets (device pointers; NULL = fp16 worst case, a wider window, same results)
  *   out_dist  [n_query, k] fp32 ascending;  out_idx [n_query, k] int64
- *   stats     optional int[8]: {flagged rows, logged candidates (sat.), survivors,
- *             segments, units, grid, log cap, reserved}
+ *   stats     optional int[8]: {rows through the exact fallback, logged candidates, candidates above
+ *             the first (fp16-window) threshold = refined in fp32, segments, units, grid, log cap,
+ *             candidates inside the refined window = scored in fp64}
  */
 size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, int k);
 /* The traversal the search would use for this shape (host-only, no GPU work): plan_host int[8] <-
@@ -114,8 +115,10 @@ int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int
  * test / diagnostic aid — the parity tests read the tensor-core similarities s~ back from it):
  * layout_host int64[8] <- {byte offset of log_val (float [n_query*n_seg][cap]), of log_idx
  * (int32, same shape), of log_cnt (int32 [n_query*n_seg], cap+1 = overflowed), of seg_top
- * (float [n_query*n_seg][k]), n_seg, cap, total bytes, 0}. */
-int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int k, int64_t* layout_host);
+ * (float [n_query*n_seg][k]), n_seg, cap, total bytes, byte offset of ref_val (float, shape of
+ * log_val: the fp32-refined similarity of each entry, -inf where s~ fell below the row's first
+ * threshold)}. */
+int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int dim_pad, int k, int64_t* layout_host);
 
 /* Measurement hooks used by bench.py (no effect on results).
  *   knnsvc_launch_count            kernels this library has launched in this process

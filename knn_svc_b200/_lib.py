@@ -29,7 +29,7 @@ SIGNATURES = {
                                        vp, sz, vp, vp]),
     "knnsvc_knn_search_full": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp,
                                      vp, sz, vp, vp]),
-    "knnsvc_knn_workspace_layout": (i32, [i64, i64, i32, vp]),
+    "knnsvc_knn_workspace_layout": (i32, [i64, i64, i32, i32, vp]),
     "knnsvc_launch_count": (C.c_longlong, []),
     "knnsvc_set_option": (i32, [C.c_char_p, i32]),
     "knnsvc_filter_timing": (i32, [i32]),

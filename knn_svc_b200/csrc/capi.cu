@@ -76,6 +76,9 @@ struct KnnWorkspace {
   int* log_cnt;
   float* seg_top;
   float* seg_kth;
+  float* ref_val;   // refined (fp32) similarity of every log entry, -inf below the first threshold
+  float* row_thr;   // first threshold of every row (+inf: the row overflowed its log)
+  int* blk_off;     // [slots][rf_nblk + 1] start of every refine block inside the (sorted) log
   int* seg_flag;
   size_t seg_flag_bytes;
   int64_t* flag_list;
@@ -85,6 +88,7 @@ struct KnnWorkspace {
 };
 
 KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const FilterPlan& pl) {
+  // (log_val .. seg_top come first and do not depend on the feature dimension: knnsvc_knn_workspace_layout)
   KnnWorkspace w;
   size_t off = 0;
   unsigned char* b = reinterpret_cast<unsigned char*>(base);
@@ -99,6 +103,9 @@ KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const Fil
   w.log_cnt = reinterpret_cast<int*>(take(slots * sizeof(int)));
   w.seg_top = reinterpret_cast<float*>(take(slots * k * sizeof(float)));
   w.seg_kth = reinterpret_cast<float*>(take(slots * sizeof(float)));
+  w.ref_val = reinterpret_cast<float*>(take(slots * pl.cap * sizeof(float)));
+  w.row_thr = reinterpret_cast<float*>(take((size_t)n_query * sizeof(float)));
+  w.blk_off = reinterpret_cast<int*>(take(slots * (size_t)(pl.rf_nblk + 1) * sizeof(int)));
   w.seg_flag_bytes = filter_flag_count(pl) * sizeof(int);
   w.seg_flag = reinterpret_cast<int*>(take(w.seg_flag_bytes));
   w.flag_list = reinterpret_cast<int64_t*>(take((size_t)n_query * sizeof(int64_t)));
@@ -106,6 +113,12 @@ KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const Fil
   w.exact_partial = take(exact_partial_bytes(kFlagCap, n_pool, k));
   w.total = off;
   return w;
+}
+
+FilterPlan full_plan(int64_t n_query, int64_t n_pool, int dim_pad, int k) {
+  FilterPlan pl = plan_filter(n_query, n_pool, k);
+  plan_refine(n_query, n_pool, dim_pad, &pl.rf_rows, &pl.rf_nblk);
+  return pl;
 }
 
 __global__ void write_plan_stats(int* stats, const int* counters, int n_seg, int n_units, int grid, int cap) {
@@ -116,7 +129,7 @@ __global__ void write_plan_stats(int* stats, const int* counters, int n_seg, int
   stats[4] = n_units;
   stats[5] = grid;
   stats[6] = cap;
-  stats[7] = counters[0];
+  stats[7] = counters[7];   // candidates inside the refined window (scored in fp64)
 }
 
 }  // namespace
@@ -168,9 +181,8 @@ int knnsvc_cosine_dist(const float* q, int64_t n_query, const float* p, int64_t 
 }
 
 size_t knnsvc_knn_workspace_bytes(int64_t n_query, int64_t n_pool, int dim_pad, int k) {
-  (void)dim_pad;
-  if (n_query <= 0 || n_pool <= 0 || k < 1 || k > kMaxK) return 0;
-  FilterPlan pl = plan_filter(n_query, n_pool, k);
+  if (n_query <= 0 || n_pool <= 0 || k < 1 || k > kMaxK || dim_pad < 1) return 0;
+  FilterPlan pl = full_plan(n_query, n_pool, dim_pad, k);
   return carve(nullptr, n_query, n_pool, k, pl).total;
 }
 
@@ -216,7 +228,7 @@ int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int
   KNN_CHECK_ARG(q && qh && qn && p && ph && pn && out_dist && out_idx && workspace, -1, "knn_search: null pointer");
   KNN_CHECK_ARG(!opt_bf16() || (q_err && p_err), -1,
                 "knn_search: bf16 operands need the measured row errors (the default window assumes fp16)");
-  FilterPlan pl = plan_filter(n_query, n_pool, k);
+  FilterPlan pl = full_plan(n_query, n_pool, dim_pad, k);
   KnnWorkspace w = carve(workspace, n_query, n_pool, k, pl);
   KNN_CHECK_ARG(workspace_bytes >= w.total, -2, "knn_search: workspace %zu < required %zu", workspace_bytes, w.total);
   KNN_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), stream));
@@ -233,8 +245,8 @@ int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int
   if (rc) return rc;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[ev_slot][1], stream));
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                          index_offset, out_dist, out_dist64, out_idx, w.flag_list, w.counters, w.counters + 1,
-                          mask_lo, mask_hi, q_err, p_err, stream);
+                          w.ref_val, w.row_thr, w.blk_off, index_offset, out_dist, out_dist64, out_idx, w.flag_list,
+                          w.counters, w.counters + 1, mask_lo, mask_hi, q_err, p_err, stream);
   if (rc) return rc;
   // rows the error window could not decide: exact brute force, count known only on the device
   rc = launch_knn_exact_rows(q, qn, n_query, p, pn, n_pool, dim, k, w.flag_list, w.counters, 0, 0, kFlagCap,
@@ -358,10 +370,11 @@ int knnsvc_merge_topk64(const double* gathered_dist, const int64_t* gathered_idx
                              (cudaStream_t)stream);
 }
 
-int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int k, int64_t* layout_host) {
+int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int dim_pad, int k, int64_t* layout_host) {
   KNN_CHECK_ARG(layout_host != nullptr, -1, "knn_workspace_layout: null output");
-  KNN_CHECK_ARG(n_query >= 1 && n_pool >= 1 && k >= 1 && k <= kMaxK, -1, "knn_workspace_layout: bad shape");
-  const FilterPlan pl = plan_filter(n_query, n_pool, k);
+  KNN_CHECK_ARG(n_query >= 1 && n_pool >= 1 && k >= 1 && k <= kMaxK && dim_pad >= 1, -1,
+                "knn_workspace_layout: bad shape");
+  const FilterPlan pl = full_plan(n_query, n_pool, dim_pad, k);
   unsigned char* base = reinterpret_cast<unsigned char*>(uintptr_t(1) << 20);   // any non-null base: offsets only
   const KnnWorkspace w = carve(base, n_query, n_pool, k, pl);
   layout_host[0] = reinterpret_cast<unsigned char*>(w.log_val) - base;
@@ -371,7 +384,7 @@ int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int k, int64_t*
   layout_host[4] = pl.n_seg;
   layout_host[5] = pl.cap;
   layout_host[6] = (int64_t)w.total;
-  layout_host[7] = 0;
+  layout_host[7] = reinterpret_cast<unsigned char*>(w.ref_val) - base;
   return 0;
 }
 

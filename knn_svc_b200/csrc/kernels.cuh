@@ -32,8 +32,10 @@ int launch_knn_exact_rows(const float* q, const double* qn, int64_t n_query, con
 // ---- knn_filter_sm100.cu
 struct FilterPlan {
   int ctas, n_qtiles, n_ptiles, n_seg, n_blk, n_units, grid, cap;
+  int rf_rows, rf_nblk;   // refine blocks (knn_select.cu): pool rows per block, number of blocks
 };
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
+void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk);
 int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n_pool, int dim_pad, int k,
                       const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt, float* seg_top,
                       float* seg_kth, int* seg_flag, const int64_t* mask_lo, const int64_t* mask_hi,
@@ -44,10 +46,10 @@ size_t filter_flag_count(const FilterPlan& pl);
 constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb
 int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
-                       const int* log_idx, const int* log_cnt, const float* seg_top, int64_t index_offset,
-                       float* out_dist, double* out_dist64, int64_t* out_idx, int64_t* flag_list, int* flag_count,
-                       int* stats, const int64_t* mask_lo, const int64_t* mask_hi, const float* q_err,
-                       const float* p_err, cudaStream_t stream);
+                       const int* log_idx, const int* log_cnt, const float* seg_top, float* ref_val, float* row_thr,
+                       int* blk_off, int64_t index_offset, float* out_dist, double* out_dist64, int64_t* out_idx,
+                       int64_t* flag_list, int* flag_count, int* stats, const int64_t* mask_lo, const int64_t* mask_hi,
+                       const float* q_err, const float* p_err, cudaStream_t stream);
 int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
                       int64_t* out_idx, cudaStream_t stream);
 int launch_merge_topk64(const double* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,

@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_chunks = gridDim.x;
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(q) & 15) == 0);                      // the re-score kernel's own rule
   // Device-side row lists run in one of two regimes, chosen by the count the host cannot see:
   //   chunked (direct == 0): <= slot_cap rows, the pool is split over gridDim.x CTAs per row group
   //                          and per-chunk partial lists are merged by knn_exact_merge_kernel;
@@ -266,13 +268,40 @@ __global__ void __launch_bounds__(EX_WARPS * 32) knn_exact_partial_kernel(
 
     for (int64_t pr = c0 + warp; pr < c1; pr += EX_WARPS) {
       const float* prow = p + pr * dim;
+      // The dot product follows knn_select.cu's rs_dot2 operation for operation (same element-to-lane
+      // assignment, two fma chains per lane, same reduction tree): a (query, pool row) pair gets the
+      // SAME fp64 bits whichever kernel scores it, so rows decided here and rows decided by the
+      // re-score order exact duplicates identically (by index), also across pool shards.
       double acc[EX_Q];
+      if (vec) {
+        double a1[EX_Q];
 #pragma unroll
-      for (int qi = 0; qi < EX_Q; ++qi) acc[qi] = 0.0;
-      for (int c = lane; c < dim; c += 32) {
-        float pv = __ldg(prow + c);
+        for (int qi = 0; qi < EX_Q; ++qi) {
+          acc[qi] = 0.0;
+          a1[qi] = 0.0;
+        }
+        const float4* p4 = reinterpret_cast<const float4*>(prow);
+        for (int c = lane; c < dim / 4; c += 32) {
+          const float4 v = __ldg(p4 + c);
 #pragma unroll
-        for (int qi = 0; qi < EX_Q; ++qi) acc[qi] += (double)pv * (double)sq[qi * dim + c];
+          for (int qi = 0; qi < EX_Q; ++qi) {
+            const float4 qv = *reinterpret_cast<const float4*>(sq + qi * dim + 4 * c);
+            acc[qi] = fma((double)v.x, (double)qv.x, acc[qi]);
+            a1[qi] = fma((double)v.y, (double)qv.y, a1[qi]);
+            acc[qi] = fma((double)v.z, (double)qv.z, acc[qi]);
+            a1[qi] = fma((double)v.w, (double)qv.w, a1[qi]);
+          }
+        }
+#pragma unroll
+        for (int qi = 0; qi < EX_Q; ++qi) acc[qi] += a1[qi];
+      } else {
+#pragma unroll
+        for (int qi = 0; qi < EX_Q; ++qi) acc[qi] = 0.0;
+        for (int c = lane; c < dim; c += 32) {
+          const float pv = __ldg(prow + c);
+#pragma unroll
+          for (int qi = 0; qi < EX_Q; ++qi) acc[qi] = fma((double)pv, (double)sq[qi * dim + c], acc[qi]);
+        }
       }
 #pragma unroll
       for (int qi = 0; qi < EX_Q; ++qi) acc[qi] = warp_sum(acc[qi]);

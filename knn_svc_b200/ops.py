@@ -195,13 +195,13 @@ def knn_search(query: PreparedRows, pool: PreparedRows, k: int, index_offset: in
     return out
 
 
-def knn_workspace_layout(n_query: int, n_pool: int, k: int) -> dict:
+def knn_workspace_layout(n_query: int, n_pool: int, dim_pad: int, k: int) -> dict:
     """Where knn_search keeps its candidate log inside the scratch buffer (diagnostics / tests)."""
     import ctypes
     arr = (ctypes.c_int64 * 8)()
-    _lib.check(_lib.load().knnsvc_knn_workspace_layout(n_query, n_pool, k, ctypes.cast(arr, ctypes.c_void_p)),
+    _lib.check(_lib.load().knnsvc_knn_workspace_layout(n_query, n_pool, dim_pad, k, ctypes.cast(arr, ctypes.c_void_p)),
                "knn_workspace_layout")
-    names = ("log_val", "log_idx", "log_cnt", "seg_top", "n_seg", "cap", "total")
+    names = ("log_val", "log_idx", "log_cnt", "seg_top", "n_seg", "cap", "total", "ref_val")
     return {n: int(arr[i]) for i, n in enumerate(names)}
 
 
@@ -212,7 +212,7 @@ def knn_candidate_log(query: PreparedRows, pool: PreparedRows, k: int):
     |s~ - s| <= eps is checked against THESE values, i.e. against what tcgen05.mma left in TMEM."""
     T = query.n
     res = knn_search(query, pool, k, return_stats=True)
-    lay = knn_workspace_layout(T, pool.n, k)
+    lay = knn_workspace_layout(T, pool.n, query.dim_pad, k)
     ws = _workspace(lay["total"], query.rows.device)
     slots, cap = T * lay["n_seg"], lay["cap"]
     val = ws[lay["log_val"]:lay["log_val"] + slots * cap * 4].view(torch.float32).view(slots, cap).clone()

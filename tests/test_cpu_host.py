@@ -53,7 +53,9 @@ def test_filter_traversal_plan_invariants():
         if n_qt * n_seg < 148:
             assert n_blk == 1 or n_qt * 16 < 148, "few chains: blocks of a chain would serialise"
         ws = lib.knnsvc_knn_workspace_bytes(T, NP, 1024, k)
-        assert ws >= T * n_seg * cap * 8 and ws < T * n_seg * cap * 8 + T * n_seg * (k + 3) * 4 + (1 << 26)
+        # candidate log (value, column) + refined value per slot, per-slot block offsets (<= 1025 ints), small terms
+        assert ws >= T * n_seg * cap * 12
+        assert ws < T * n_seg * cap * 12 + T * n_seg * (k + 3 + 1026) * 4 + (1 << 26)
     # the headline shape: one segment, 407 blocks of 96 tiles per chain
     out = (ctypes.c_int * 8)()
     lib.knnsvc_knn_plan(100_000, 10_000_000, 4, ctypes.cast(out, ctypes.c_void_p))
