@@ -182,6 +182,23 @@ int knnsvc_gather_mix_sharded(const void* const* shard_rows_host, const int64_t*
                               int dim, const int64_t* idx, const float* weights, int64_t n_query, int k,
                               float* out, void* stream);
 
+/* ---- K5 / K6 over a sharded pool: the post-opt stage on a pool that lives in several row blocks
+ * (same table as knnsvc_gather_mix_sharded; idx holds GLOBAL row indices).  The greedy re-selection
+ * follows `previous selection + 1` (lib_ongaku_test.py:294-295) and the weight fit gathers rows
+ * idx-1, idx, idx+1 (ddsp_prematch_dataset.py:585-590) ACROSS shard boundaries; rows of other GPUs are
+ * fetched through their mapped pointers (TMA bulk copies / loads over NVLink).  pool_f0 is the
+ * f0 of the WHOLE pool (replicated, n floats).  Results are bit-identical to the single-pool calls. */
+int knnsvc_concat_cost_reselect_sharded(const int64_t* idx, const float* src,
+                                        const void* const* shard_rows_host, const int64_t* shard_lo_host,
+                                        int n_shards, int dim, const float* shifted_src_f0, const float* pool_f0,
+                                        float concat_weight, const int64_t* utt_offsets_host, int n_utt,
+                                        int64_t* out_idx, void* stream);
+int knnsvc_weight_fit_sharded(const int64_t* idx, const void* const* shard_rows_host,
+                              const int64_t* shard_lo_host, int n_shards, int dim,
+                              const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
+                              float* out_weights, double* info, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* ---- K3: gather + weighted mix -------------------------------------------
  * out[t,:] = sum_k w[t,k] * pool[idx[t,k],:]  (w == NULL -> mean) —
  * ddsp_prematch_dataset.py:1348,1358,1364,1435,1444,1446; ddsp_matcher.py:578. */

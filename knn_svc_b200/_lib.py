@@ -42,6 +42,8 @@ SIGNATURES = {
     "knnsvc_ipc_open": (i32, [vp, vp]),
     "knnsvc_ipc_close": (i32, [vp]),
     "knnsvc_gather_mix_sharded": (i32, [vp, vp, i32, i32, vp, vp, i64, i32, vp, vp]),
+    "knnsvc_concat_cost_reselect_sharded": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, f32, vp, i32, vp, vp]),
+    "knnsvc_weight_fit_sharded": (i32, [vp, vp, vp, i32, i32, vp, i32, i32, f64, i32, vp, vp, vp, sz, vp]),
     "knnsvc_gather_mix": (i32, [vp, i64, i32, vp, vp, i64, i32, vp, vp]),
     "knnsvc_f0_rerank": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "knnsvc_concat_cost_reselect": (i32, [vp, vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, vp]),

@@ -424,21 +424,29 @@ int knnsvc_ipc_close(void* base) {
   return 0;
 }
 
+static int make_table(const void* const* shard_rows_host, const int64_t* shard_lo_host, int n_shards, RowTable* tab,
+                      const char* what) {
+  KNN_CHECK_ARG(shard_rows_host && shard_lo_host, -1, "%s: null shard table", what);
+  KNN_CHECK_ARG(n_shards >= 1 && n_shards <= kMaxShards, -1, "%s: %d shards outside [1,%d]", what, n_shards, kMaxShards);
+  tab->n = n_shards;
+  for (int s = 0; s < n_shards; ++s) {
+    KNN_CHECK_ARG(shard_rows_host[s] != nullptr && shard_lo_host[s + 1] >= shard_lo_host[s], -1, "%s: bad shard %d", what,
+                  s);
+    tab->base[s] = reinterpret_cast<const float*>(shard_rows_host[s]);
+    tab->lo[s] = shard_lo_host[s];
+  }
+  tab->lo[n_shards] = shard_lo_host[n_shards];
+  KNN_CHECK_ARG(shard_lo_host[0] == 0 && tab->lo[n_shards] >= 1, -1, "%s: the shards must cover rows [0, n) with n >= 1", what);
+  return 0;
+}
+
 int knnsvc_gather_mix_sharded(const void* const* shard_rows_host, const int64_t* shard_lo_host, int n_shards, int dim,
                               const int64_t* idx, const float* weights, int64_t n_query, int k, float* out,
                               void* stream) {
-  KNN_CHECK_ARG(shard_rows_host && shard_lo_host && idx && out && k >= 1, -1, "gather_mix_sharded: bad arguments");
-  KNN_CHECK_ARG(n_shards >= 1 && n_shards <= kMaxShards, -1, "gather_mix_sharded: %d shards outside [1,%d]", n_shards,
-                kMaxShards);
+  KNN_CHECK_ARG(idx && out && k >= 1, -1, "gather_mix_sharded: bad arguments");
   RowTable tab;
-  tab.n = n_shards;
-  for (int s = 0; s < n_shards; ++s) {
-    KNN_CHECK_ARG(shard_rows_host[s] != nullptr && shard_lo_host[s + 1] >= shard_lo_host[s], -1,
-                  "gather_mix_sharded: bad shard %d", s);
-    tab.base[s] = reinterpret_cast<const float*>(shard_rows_host[s]);
-    tab.lo[s] = shard_lo_host[s];
-  }
-  tab.lo[n_shards] = shard_lo_host[n_shards];
+  int rc = make_table(shard_rows_host, shard_lo_host, n_shards, &tab, "gather_mix_sharded");
+  if (rc) return rc;
   return launch_gather_mix_sharded(tab, dim, idx, weights, n_query, k, out, (cudaStream_t)stream);
 }
 
@@ -454,11 +462,34 @@ int knnsvc_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
   return launch_f0_rerank(expected_f0, pool_f0, idx, n_query, k, out_idx, (cudaStream_t)stream);
 }
 
+static int concat_cost_on_table(const int64_t* idx, const float* src, const RowTable& pool, int dim,
+                                const float* shifted_src_f0, const float* pool_f0, float concat_weight,
+                                const int64_t* utt_offsets_host, int n_utt, int64_t* out_idx, void* stream_);
+
 int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
                                 const float* shifted_src_f0, const float* pool_f0, float concat_weight,
                                 const int64_t* utt_offsets_host, int n_utt, int64_t* out_idx, void* stream_) {
+  KNN_CHECK_ARG(pool && n_pool >= 1, -1, "concat_cost: bad arguments");
+  return concat_cost_on_table(idx, src, single_table(pool, n_pool), dim, shifted_src_f0, pool_f0, concat_weight,
+                              utt_offsets_host, n_utt, out_idx, stream_);
+}
+
+int knnsvc_concat_cost_reselect_sharded(const int64_t* idx, const float* src, const void* const* shard_rows_host,
+                                        const int64_t* shard_lo_host, int n_shards, int dim,
+                                        const float* shifted_src_f0, const float* pool_f0, float concat_weight,
+                                        const int64_t* utt_offsets_host, int n_utt, int64_t* out_idx, void* stream_) {
+  RowTable tab;
+  int rc = make_table(shard_rows_host, shard_lo_host, n_shards, &tab, "concat_cost_sharded");
+  if (rc) return rc;
+  return concat_cost_on_table(idx, src, tab, dim, shifted_src_f0, pool_f0, concat_weight, utt_offsets_host, n_utt,
+                              out_idx, stream_);
+}
+
+static int concat_cost_on_table(const int64_t* idx, const float* src, const RowTable& pool, int dim,
+                                const float* shifted_src_f0, const float* pool_f0, float concat_weight,
+                                const int64_t* utt_offsets_host, int n_utt, int64_t* out_idx, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  KNN_CHECK_ARG(idx && src && pool && out_idx && utt_offsets_host && n_utt >= 0, -1, "concat_cost: bad arguments");
+  KNN_CHECK_ARG(idx && src && out_idx && utt_offsets_host && n_utt >= 0, -1, "concat_cost: bad arguments");
   KNN_CHECK_ARG((shifted_src_f0 == nullptr) == (pool_f0 == nullptr), -1,
                 "concat_cost: shifted_src_f0 and pool_f0 must be given together");
   if (n_utt == 0) return 0;
@@ -478,7 +509,7 @@ int knnsvc_concat_cost_reselect(const int64_t* idx, const float* src, const floa
   int64_t* d_off = reinterpret_cast<int64_t*>(d_ws);
   KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            stream));
-  int rc = launch_concat_cost(idx, src, pool, n_pool, dim, shifted_src_f0, pool_f0, concat_weight, d_off, n_utt,
+  int rc = launch_concat_cost(idx, src, pool, dim, shifted_src_f0, pool_f0, concat_weight, d_off, n_utt,
                               n_frames, reinterpret_cast<double*>(d_ws + off_bytes), out_idx, stream);
   cudaFreeAsync(d_ws, stream);
   return rc;
@@ -492,8 +523,8 @@ int knnsvc_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   KNN_CHECK_ARG(idx && synth && out_weights && workspace && n_query >= 0, -1, "weight_fit: bad arguments");
   KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(n_query, k, 1), -2, "weight_fit: workspace too small");
   const int64_t offs[2] = {0, n_query};
-  return launch_weight_fit(idx, synth, n_pool, dim, offs, 1, k, loss_scale, max_iters, nullptr, out_weights, info,
-                           workspace, (cudaStream_t)stream);
+  return launch_weight_fit(idx, single_table(synth, n_pool), dim, offs, 1, k, loss_scale, max_iters, nullptr, out_weights,
+                           info, workspace, (cudaStream_t)stream);
 }
 
 size_t knnsvc_weight_fit_batched_workspace_bytes(int64_t n_frames, int k, int n_utt) {
@@ -517,8 +548,23 @@ int knnsvc_weight_fit_amp(const int64_t* idx, const float* synth, int64_t n_pool
   if (n_utt == 0) return 0;
   KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(utt_offsets_host[n_utt], k, n_utt), -2,
                 "weight_fit: workspace too small");
-  return launch_weight_fit(idx, synth, n_pool, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, amp_ratio,
-                           out_weights, info, workspace, (cudaStream_t)stream);
+  return launch_weight_fit(idx, single_table(synth, n_pool), dim, utt_offsets_host, n_utt, k, loss_scale, max_iters,
+                           amp_ratio, out_weights, info, workspace, (cudaStream_t)stream);
+}
+
+int knnsvc_weight_fit_sharded(const int64_t* idx, const void* const* shard_rows_host, const int64_t* shard_lo_host,
+                              int n_shards, int dim, const int64_t* utt_offsets_host, int n_utt, int k,
+                              double loss_scale, int max_iters, float* out_weights, double* info, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  KNN_CHECK_ARG(idx && out_weights && workspace && utt_offsets_host && n_utt >= 0, -1, "weight_fit: bad arguments");
+  if (n_utt == 0) return 0;
+  KNN_CHECK_ARG(workspace_bytes >= weight_fit_workspace_bytes(utt_offsets_host[n_utt], k, n_utt), -2,
+                "weight_fit: workspace too small");
+  RowTable tab;
+  int rc = make_table(shard_rows_host, shard_lo_host, n_shards, &tab, "weight_fit_sharded");
+  if (rc) return rc;
+  return launch_weight_fit(idx, tab, dim, utt_offsets_host, n_utt, k, loss_scale, max_iters, nullptr, out_weights, info,
+                           workspace, (cudaStream_t)stream);
 }
 
 int knnsvc_harmonic_bank(const float* f0, const float* amp, int batch, int64_t frames, int n_harm, int sample_rate,

@@ -120,7 +120,7 @@ __device__ long long g_k5_prof[8];
 }  // namespace
 
 __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
-    const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
+    const int64_t* __restrict__ idx, const float* __restrict__ src, const __grid_constant__ RowTable pool,
     int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
     const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
     int64_t* __restrict__ out_idx) {
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
   const int64_t n = f_end - f_begin;
   if (n <= 0) return;
   const bool use_f0 = src_f0 != nullptr;
+  const int64_t n_pool = pool.lo[pool.n];
   const uint32_t row_bytes = (uint32_t)dim * 4u;
   auto row_ptr = [&](int gen, int r) { return rows + ((size_t)gen * CS_ROWS + r) * dim; };
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
     if (lane < CS_K) {
       const int64_t id = idx[f_begin * CS_K + lane];
       sh.meta[0].idx_g[lane] = id;
-      cs_bulk_row(cs_smem_u32(row_ptr(0, lane)), pool + id * dim, row_bytes, cs_smem_u32(&sh.full_bar[0]));
+      cs_bulk_row(cs_smem_u32(row_ptr(0, lane)), table_row(pool, id, dim), row_bytes, cs_smem_u32(&sh.full_bar[0]));
     }
     __syncwarp();
     if (lane == 0) cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[0]), CS_K * row_bytes);
@@ -190,11 +191,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
         else c = sh.meta[gp].spec_g[sh.sp[(s - 2) & 1][lane - CS_K]];
         id = c + 1 >= n_pool ? n_pool - 1 : c + 1;   // lib_ongaku_test.py:294-295
         sh.meta[g].spec_g[lane] = id;
-        cs_bulk_row(cs_smem_u32(row_ptr(g, CS_K + lane)), pool + id * dim, row_bytes, bar);
+        cs_bulk_row(cs_smem_u32(row_ptr(g, CS_K + lane)), table_row(pool, id, dim), row_bytes, bar);
       } else if (lane < CS_C + CS_K) {         // rows of idx[s]
         id = next_idx;
         sh.meta[g].idx_g[lane - CS_C] = id;
-        cs_bulk_row(cs_smem_u32(row_ptr(g, lane - CS_C)), pool + id * dim, row_bytes, bar);
+        cs_bulk_row(cs_smem_u32(row_ptr(g, lane - CS_C)), table_row(pool, id, dim), row_bytes, bar);
         if (s + 1 < n) next_idx = idx[(f_begin + s + 1) * CS_K + (lane - CS_C)];
       } else if (lane == CS_C + CS_K) {        // query row s and its per-frame scalars
         cs_bulk_row(cs_smem_u32(row_ptr(g, CS_ROWS - 1)), src + (f_begin + s) * dim, row_bytes, bar);
@@ -398,19 +399,20 @@ size_t concat_staged_smem_bytes(int dim) {
   return (size_t)CS_GENS * CS_ROWS * dim * sizeof(float) + sizeof(CsShared);
 }
 
-bool concat_staged_eligible(const float* src, const float* pool, int dim) {
-  return dim >= 4 && dim % 4 == 0 && dim <= CS_MAX_DIM && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
-         (reinterpret_cast<uintptr_t>(pool) & 15) == 0;
+bool concat_staged_eligible(const float* src, const RowTable& pool, int dim) {
+  bool ok = dim >= 4 && dim % 4 == 0 && dim <= CS_MAX_DIM && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (int s = 0; s < pool.n; ++s) ok = ok && (reinterpret_cast<uintptr_t>(pool.base[s]) & 15) == 0;
+  return ok;
 }
 
-int launch_concat_cost_staged(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+int launch_concat_cost_staged(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                               const float* src_f0, const float* pool_f0, float concat_weight,
                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                               int64_t* out_idx, cudaStream_t stream) {
   const size_t smem = concat_staged_smem_bytes(dim);
   static PerDevice attr;
   KNN_SMEM_ATTR(attr, concat_cost_staged_kernel, smem);
-  concat_cost_staged_kernel<<<n_utt, CS_THREADS, smem, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0,
+  concat_cost_staged_kernel<<<n_utt, CS_THREADS, smem, stream>>>(idx, src, pool, dim, src_f0, pool_f0,
                                                                  concat_weight, utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
 #ifdef KNNSVC_K5_PROFILE

@@ -64,26 +64,50 @@ struct RowTable {
   int64_t lo[kMaxShards + 1];
   int n;
 };
+inline RowTable single_table(const float* rows, int64_t n_rows) {
+  RowTable t;
+  t.n = 1;
+  t.base[0] = rows;
+  t.lo[0] = 0;
+  t.lo[1] = n_rows;
+  return t;
+}
+#ifdef __CUDACC__
+// pointer to global row r (clamped into the table's range, as the reference clamps `prev + 1` and
+// `idx +- 1` at the ends of the pool: lib_ongaku_test.py:294-295, ddsp_prematch_dataset.py:585-590)
+__device__ __forceinline__ const float* table_row(const RowTable& tab, int64_t r, int dim) {
+  r = r < 0 ? 0 : (r >= tab.lo[tab.n] ? tab.lo[tab.n] - 1 : r);
+  int s = 0;
+#pragma unroll 1
+  while (s + 1 < tab.n && r >= tab.lo[s + 1]) ++s;
+  return tab.base[s] + (r - tab.lo[s]) * dim;
+}
+__device__ __forceinline__ bool table_aligned16(const RowTable& tab) {
+  bool ok = true;
+  for (int s = 0; s < tab.n; ++s) ok = ok && ((reinterpret_cast<uintptr_t>(tab.base[s]) & 15) == 0);
+  return ok;
+}
+#endif
 int launch_gather_mix_sharded(const RowTable& tab, int dim, const int64_t* idx, const float* weights, int64_t n_query,
                               int k, float* out, cudaStream_t stream);
 int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t* idx, const float* weights,
                       int64_t n_query, int k, float* out, cudaStream_t stream);
 int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64_t* idx, int64_t n_query, int k,
                      int64_t* out_idx, cudaStream_t stream);
-int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
                        int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream);
 
 // ---- concat_cost_sm100.cu
-bool concat_staged_eligible(const float* src, const float* pool, int dim);
-int launch_concat_cost_staged(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+bool concat_staged_eligible(const float* src, const RowTable& pool, int dim);
+int launch_concat_cost_staged(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                               const float* src_f0, const float* pool_f0, float concat_weight,
                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                               int64_t* out_idx, cudaStream_t stream);
 
 // ---- weight_fit.cu
 size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt);
-int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+int launch_weight_fit(const int64_t* idx, const RowTable& synth, int dim,
                       const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
                       const float* amp, float* out_weights, double* info, void* workspace, cudaStream_t stream);
 

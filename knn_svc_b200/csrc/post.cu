@@ -67,14 +67,6 @@ int launch_gather_mix(const float* pool, int64_t n_pool, int dim, const int64_t*
 // order as gather_mix_kernel, so the result is bit-identical to mixing from one contiguous pool;
 // rows of another GPU's shard are read through its IPC-mapped pointer (NVLink P2P loads, 16 B per
 // lane, K of them in flight per thread).  Launched by the rank that OWNS the query rows.
-__device__ __forceinline__ const float* table_row(const RowTable& tab, int64_t r, int dim) {
-  r = r < 0 ? 0 : (r >= tab.lo[tab.n] ? tab.lo[tab.n] - 1 : r);
-  int s = 0;
-#pragma unroll 1
-  while (s + 1 < tab.n && r >= tab.lo[s + 1]) ++s;
-  return tab.base[s] + (r - tab.lo[s]) * dim;
-}
-
 template <bool VEC>
 __global__ void __launch_bounds__(256) gather_mix_sharded_kernel(const __grid_constant__ RowTable tab, int dim,
                                                                  const int64_t* __restrict__ idx,
@@ -222,7 +214,7 @@ constexpr int CC_WARPS = 2 * CC_C;
 constexpr int CC_ACC = 6;  // |c|^2, d2(src,c), d2(prev_j,c) j=0..3
 
 __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
-    const int64_t* __restrict__ idx, const float* __restrict__ src, const float* __restrict__ pool, int64_t n_pool,
+    const int64_t* __restrict__ idx, const float* __restrict__ src, const __grid_constant__ RowTable pool,
     int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
     const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
     int64_t* __restrict__ out_idx) {
@@ -230,8 +222,8 @@ __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
   const int64_t f_begin = utt_offsets[blockIdx.x], f_end = utt_offsets[blockIdx.x + 1];
   if (f_end <= f_begin) return;
   const bool use_f0 = src_f0 != nullptr;
-  const bool vec4 = (dim % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(pool) & 15) == 0);
+  const bool vec4 = (dim % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && table_aligned16(pool);
+  const int64_t n_pool = pool.lo[pool.n];
 
   __shared__ int64_t s_prev[CC_K];
   __shared__ double s_prev_n2[CC_K];
@@ -247,7 +239,7 @@ __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
   if (threadIdx.x == 0) s_w = (double)concat_weight;
   __syncthreads();
   if (warp < CC_K) {  // |row|^2 of the four initial selections
-    const float* r = pool + s_prev[warp] * dim;
+    const float* r = table_row(pool, s_prev[warp], dim);
     double n = 0;
     for (int c = lane; c < dim; c += 32) {
       const float v = __ldg(r + c);
@@ -294,12 +286,12 @@ __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
     double lcand = 0.0;
     if (use_f0 && threadIdx.x < CC_C) lcand = log2((double)__ldg(pool_f0 + s_cand[threadIdx.x]) + 1e-5);
     {
-      const float* crow = pool + s_cand[cand_id] * dim;
+      const float* crow = table_row(pool, s_cand[cand_id], dim);
       const float* srow = src + i * dim;
-      const float* p0 = pool + s_prev[0] * dim;
-      const float* p1 = pool + s_prev[1] * dim;
-      const float* p2 = pool + s_prev[2] * dim;
-      const float* p3 = pool + s_prev[3] * dim;
+      const float* p0 = table_row(pool, s_prev[0], dim);
+      const float* p1 = table_row(pool, s_prev[1], dim);
+      const float* p2 = table_row(pool, s_prev[2], dim);
+      const float* p3 = table_row(pool, s_prev[3], dim);
       double nc = 0, dm = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
       if (vec4) {
         const int n4h = dim / 8;                 // float4s in this warp's half of the row
@@ -417,7 +409,7 @@ __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
   }
 }
 
-int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, int64_t n_pool, int dim,
+int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
                        int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream) {
   if (n_utt == 0 || n_frames == 0) return 0;
@@ -428,9 +420,9 @@ int launch_concat_cost(const int64_t* idx, const float* src, const float* pool, 
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
   if (opt_concat_staged() && concat_staged_eligible(src, pool, dim))   // shared-memory staged recurrence (concat_cost_sm100.cu)
-    return launch_concat_cost_staged(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
+    return launch_concat_cost_staged(idx, src, pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
                                      base, n2, out_idx, stream);
-  concat_cost_kernel<<<n_utt, CC_WARPS * 32, 0, stream>>>(idx, src, pool, n_pool, dim, src_f0, pool_f0, concat_weight,
+  concat_cost_kernel<<<n_utt, CC_WARPS * 32, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0, concat_weight,
                                                       utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
   return 0;

@@ -59,7 +59,7 @@ __device__ __forceinline__ void wg_accumulate(const double (&v)[WF_V], double (&
 }
 
 __global__ void __launch_bounds__(WG_WARPS * 32) weight_gram_kernel(const int64_t* __restrict__ idx,
-                                                                    const float* __restrict__ synth, int64_t n_pool,
+                                                                    const __grid_constant__ RowTable synth,
                                                                     int dim, int64_t n_query, double* __restrict__ gram) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_pairs = n_query - 1;
@@ -72,15 +72,13 @@ __global__ void __launch_bounds__(WG_WARPS * 32) weight_gram_kernel(const int64_
     const int64_t base = (j < WF_K) ? __ldg(idx + (t + 1) * WF_K + j) : __ldg(idx + t * WF_K + (j - WF_K));
     int64_t r0 = base + ((j < WF_K) ? -1 : 0);
     int64_t r1 = base + ((j < WF_K) ? 0 : 1);
-    r0 = r0 < 0 ? 0 : (r0 >= n_pool ? n_pool - 1 : r0);
-    r1 = r1 < 0 ? 0 : (r1 >= n_pool ? n_pool - 1 : r1);
-    rows[0][j] = synth + r0 * dim;
-    rows[1][j] = synth + r1 * dim;
+    rows[0][j] = table_row(synth, r0, dim);      // clamped to the pool's ends like the reference's gather
+    rows[1][j] = table_row(synth, r1, dim);
   }
   double acc[WF_E];
 #pragma unroll
   for (int e = 0; e < WF_E; ++e) acc[e] = 0.0;
-  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(synth) & 15) == 0);
+  const bool vec = (dim & 3) == 0 && table_aligned16(synth);
 #pragma unroll
   for (int b = 0; b < 2; ++b) {
     if (vec) {
@@ -583,7 +581,7 @@ size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt) {
 // concatenated idx / out_weights; one CTA runs one utterance's whole optimisation, so a batch of
 // utterances (BASELINE cfg 5) fills the SMs; a launch of few, long utterances gives each of them a
 // cluster of 8 CTAs instead.  info: double[n_utt][4].
-int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, int dim,
+int launch_weight_fit(const int64_t* idx, const RowTable& synth, int dim,
                       const int64_t* utt_offsets_host, int n_utt, int k, double loss_scale, int max_iters,
                       const float* amp, float* out_weights, double* info, void* workspace, cudaStream_t stream) {
   KNN_CHECK_ARG(k == WF_K, -3, "weight_fit: k=%d, only k=%d is on the reference path", k, WF_K);
@@ -614,8 +612,8 @@ int launch_weight_fit(const int64_t* idx, const float* synth, int64_t n_pool, in
   const int64_t n_pairs_total = n_query - 1;
   if (n_pairs_total > 0) {
     // pairs that straddle two utterances are computed too (same pool, in-range rows) and never read
-    weight_gram_kernel<<<(unsigned)ceil_div64(n_pairs_total, WG_WARPS), WG_WARPS * 32, 0, stream>>>(idx, synth, n_pool,
-                                                                                                 dim, n_query, gram);
+    weight_gram_kernel<<<(unsigned)ceil_div64(n_pairs_total, WG_WARPS), WG_WARPS * 32, 0, stream>>>(idx, synth, dim,
+                                                                                                 n_query, gram);
     KNN_LAUNCH_CHECK();
   }
   int64_t min_len = INT64_MAX, max_len = 0;

@@ -148,10 +148,11 @@ class KNeighborsVC(nn.Module):
             if synth_set is not None:
                 raise ValueError("pass the synth rows to ShardedPool(synth_rows=...), not to match()")
             if "no_post_opt" not in post_opt:
-                raise NotImplementedError("post_opt on a frame-sharded pool: the greedy re-selection follows "
-                                          "`previous selection + 1` across shard boundaries; replicate the pool "
-                                          "for the post-opt stage (SURVEY 8e)")
-            out_feats = sharded_pool.match(query_seq, topk, gather=gather).feats   # host queries: upload_query
+                if topk != 4:
+                    raise ValueError("post_opt needs topk=4 (the reference keeps 4 candidates, ddsp_prematch_dataset.py:1246)")
+                out_feats = sharded_pool.match_post_opt(query_seq, _pm.parse_post_opt(post_opt), gather=gather).feats
+            else:
+                out_feats = sharded_pool.match(query_seq, topk, gather=gather).feats   # host queries: upload_query
             assert gather != "all" or out_feats.shape == query_seq.shape
             if without_vocode:
                 return out_feats

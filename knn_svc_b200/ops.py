@@ -341,12 +341,18 @@ def f0_rerank(expected_f0: torch.Tensor, pool_f0: torch.Tensor, idx: torch.Tenso
     return out
 
 
-def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tensor,
-                         shifted_src_f0: torch.Tensor | None = None, pool_f0: torch.Tensor | None = None,
-                         concat_weight: float = 0.2, utt_offsets=None) -> torch.Tensor:
-    _dev(src, "src_elements"); _dev(pool, "tgt_elements")
+def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool, shifted_src_f0: torch.Tensor | None = None,
+                         pool_f0: torch.Tensor | None = None, concat_weight: float = 0.2, utt_offsets=None) -> torch.Tensor:
+    """Greedy concatenation-cost re-selection (K5).  `pool` is the [Np, D] pool tensor or a
+    `ShardedRows` table (a pool sharded over GPUs: `idx` then holds GLOBAL rows and `pool_f0` the f0 of
+    the whole pool); results are identical."""
+    _dev(src, "src_elements")
     dev = src.device
-    idx, src, pool = _i64c(idx.to(dev)), _f32c(src), _f32c(pool)
+    table = pool if isinstance(pool, ShardedRows) else None
+    if table is None:
+        _dev(pool, "tgt_elements")
+        pool = _f32c(pool)
+    idx, src = _i64c(idx.to(dev)), _f32c(src)
     T, k = idx.shape
     if k != 4:
         raise ValueError("knn_with_concat_cost: the reference path keeps 4 candidates per frame")
@@ -362,27 +368,43 @@ def concat_cost_reselect(idx: torch.Tensor, src: torch.Tensor, pool: torch.Tenso
     if T == 0:
         return out
     with torch.cuda.device(dev):
-        _lib.check(lib.knnsvc_concat_cost_reselect(idx.data_ptr(), src.data_ptr(), pool.data_ptr(), pool.shape[0],
-                                                   pool.shape[1], _ptr(sf), _ptr(pf), float(concat_weight),
-                                                   ctypes.cast(arr, ctypes.c_void_p), len(offs) - 1, out.data_ptr(),
-                                                   _stream()), "concat_cost_reselect")
+        if table is None:
+            _lib.check(lib.knnsvc_concat_cost_reselect(idx.data_ptr(), src.data_ptr(), pool.data_ptr(), pool.shape[0],
+                                                       pool.shape[1], _ptr(sf), _ptr(pf), float(concat_weight),
+                                                       ctypes.cast(arr, ctypes.c_void_p), len(offs) - 1, out.data_ptr(),
+                                                       _stream()), "concat_cost_reselect")
+        else:
+            if src.shape[1] != table.dim:
+                raise ValueError("feature dimensions differ")
+            _lib.check(lib.knnsvc_concat_cost_reselect_sharded(
+                idx.data_ptr(), src.data_ptr(), ctypes.cast(table._ptr_arr, ctypes.c_void_p),
+                ctypes.cast(table._lo_arr, ctypes.c_void_p), table.n, table.dim, _ptr(sf), _ptr(pf), float(concat_weight),
+                ctypes.cast(arr, ctypes.c_void_p), len(offs) - 1, out.data_ptr(), _stream()), "concat_cost_reselect_sharded")
     return out
 
 
-def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_iters: int = 100000,
+def weight_fit(idx: torch.Tensor, synth, loss_scale: float, max_iters: int = 100000,
                return_info: bool = False, utt_offsets=None, amp_ratio: torch.Tensor | None = None):
     """Adam(amsgrad) fit of the softmax mixing weights (K6).  With `utt_offsets` the rows of
     `idx` are a concatenation of utterances, each fitted independently (one CTA each, one
     launch); info is then [n_utt, 4].  `amp_ratio` [T,k] scales every candidate row before
-    mixing (compute_weight_with_amp, ddsp_prematch_dataset.py:684-803)."""
-    _dev(synth, "synth_set")
-    dev = synth.device
-    idx, synth = _i64c(idx.to(dev)), _f32c(synth)
+    mixing (compute_weight_with_amp, ddsp_prematch_dataset.py:684-803).  `synth` is the [Np, D]
+    tensor or a `ShardedRows` table (GLOBAL indices; no amp_ratio)."""
+    table = synth if isinstance(synth, ShardedRows) else None
+    if table is None:
+        _dev(synth, "synth_set")
+        synth = _f32c(synth)
+        dev = synth.device
+    else:
+        dev = table.device
+    idx = _i64c(idx.to(dev))
     T, k = idx.shape
     amp = None
     if amp_ratio is not None:
         if tuple(amp_ratio.shape) != (T, k):
             raise AssertionError("amp_ratio must have the shape of target_feature_indices")   # reference :687
+        if table is not None:
+            raise ValueError("amp_ratio is not supported on a sharded pool")
         amp = _f32c(amp_ratio.to(dev))
     offs = [0, T] if utt_offsets is None else [int(v) for v in utt_offsets]
     if offs[0] != 0 or offs[-1] != T:
@@ -397,10 +419,17 @@ def weight_fit(idx: torch.Tensor, synth: torch.Tensor, loss_scale: float, max_it
         with torch.cuda.device(dev):
             nbytes = lib.knnsvc_weight_fit_batched_workspace_bytes(T, k, n_utt)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            _lib.check(lib.knnsvc_weight_fit_amp(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1],
-                                                 ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
-                                                 int(max_iters), _ptr(amp), out.data_ptr(), info.data_ptr(),
-                                                 ws.data_ptr(), ws.numel(), _stream()), "weight_fit")
+            if table is None:
+                _lib.check(lib.knnsvc_weight_fit_amp(idx.data_ptr(), synth.data_ptr(), synth.shape[0], synth.shape[1],
+                                                     ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
+                                                     int(max_iters), _ptr(amp), out.data_ptr(), info.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _stream()), "weight_fit")
+            else:
+                _lib.check(lib.knnsvc_weight_fit_sharded(idx.data_ptr(), ctypes.cast(table._ptr_arr, ctypes.c_void_p),
+                                                         ctypes.cast(table._lo_arr, ctypes.c_void_p), table.n, table.dim,
+                                                         ctypes.cast(arr, ctypes.c_void_p), n_utt, k, float(loss_scale),
+                                                         int(max_iters), out.data_ptr(), info.data_ptr(), ws.data_ptr(),
+                                                         ws.numel(), _stream()), "weight_fit_sharded")
     if utt_offsets is None:
         info = info[0]
     if return_info:

@@ -221,6 +221,50 @@ class ShardedPool:
         return (d, i, d64) if return_dist64 else (d, i)
 
     # ------------------------------------------------------------------ the matcher: search + gather-mean
+    def row_table(self):
+        """The pool as a row table valid on this GPU (peers' shards through their mapped pointers)."""
+        from . import ops
+        if self.table is not None:
+            return self.table
+        if self.distributed:
+            raise RuntimeError("the peer-memory row table needs exchange='p2p'")
+        # one local block; its rows are addressed 0 .. n-1 (match_post_opt removes a non-zero global offset)
+        return ops.ShardedRows([self.synth.data_ptr()], [0, self.prepared.n], self.synth.shape[1], self.device)
+
+    def match_post_opt(self, query, concat_weight: float, gather: str = "all", check: bool = True) -> ShardedMatch:
+        """`match` followed by the concatenation-smoothness stage on the plain cosine top-4
+        (ddsp_prematch_dataset.py:1246,1295,1357-1358): greedy re-selection (skipped when
+        `concat_weight` is -1), fitted mixing weights, weighted mix.  `previous selection + 1` and the
+        fit's `idx +- 1` rows cross shard boundaries freely: both kernels address the pool through
+        the peer row table.  The recurrence is one serial chain per utterance, so every rank runs
+        it (deterministic: same bits everywhere); the final gather is split by query slice as in `match`.
+        The matching rows and the mixed rows must be the same set (synth_rows=None)."""
+        from . import ops
+        if self.synth.data_ptr() != self.prepared.rows.data_ptr():
+            raise ValueError("post_opt on a sharded pool needs synth_rows to be the matching rows")
+        qp = query if isinstance(query, ops.PreparedRows) else \
+            ops.prepare_rows(query.to(self.device) if query.is_cuda else self.upload_query(query), check=check)
+        d, i, d64 = self.knn(qp, 4, return_dist64=True)
+        table = self.row_table()
+        local_base = 0 if self.distributed or self.offset == 0 else self.offset
+        idx = i - local_base
+        if concat_weight != -1:
+            idx = ops.concat_cost_reselect(idx, qp.rows, table, concat_weight=concat_weight)
+        w = ops.weight_fit(idx, table, 0.1)
+        T = qp.n
+        lo, hi = query_slice(T, self.world, self.rank) if self.distributed else (0, T)
+        part = ops.gather_mix_sharded(table, idx[lo:hi], w[lo:hi])
+        idx = idx + local_base
+        if gather == "slice" or not self.distributed:
+            return ShardedMatch(d, idx, part, (lo, hi), d64)
+        chunk = (T + self.world - 1) // self.world
+        dim = self.synth.shape[1]
+        padded = torch.zeros((chunk, dim), dtype=torch.float32, device=self.device)
+        padded[:hi - lo] = part
+        allf = torch.empty((self.world * chunk, dim), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(allf, padded, group=self.group)
+        return ShardedMatch(d, idx, allf[:T], (0, T), d64)
+
     def match(self, query, k: int = 4, gather: str = "slice", weights: torch.Tensor | None = None,
               check: bool = True, mix_k: int | None = None) -> ShardedMatch:
         """kNN regression of the query rows onto the sharded pool: the merged top-k and the mean

@@ -77,6 +77,13 @@ def main():
     got = knn.match(query_t, sp, topk=4, without_vocode=True)
     want = knn.match(query_t, pool_t, topk=4, without_vocode=True)
     assert torch.equal(got, want)
+    # post_opt on the sharded pool: greedy re-selection and weight fit read the pool through the peer row
+    # table (`previous selection + 1` and idx +- 1 cross shard boundaries); bit-identical to one GPU
+    for post_opt in ("post_opt_0.2", "post_opt_plain"):          # the second parses to -1: fit only, no re-selection
+        got = knn.match(query_t, sp, topk=4, without_vocode=True, post_opt=post_opt)
+        want = knn.match(query_t, pool_t, topk=4, without_vocode=True, post_opt=post_opt)
+        assert torch.equal(got, want), post_opt
+        checks += 1
     sp.close()
     torch.cuda.synchronize()
     dist.barrier()

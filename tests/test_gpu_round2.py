@@ -266,6 +266,39 @@ def test_gather_mix_sharded_equals_contiguous(ops, dim):
     assert ops.gather_mix_sharded(table, dev(idx[:0]), None).shape == (0, dim)
 
 
+def test_post_opt_stage_on_a_row_table_equals_contiguous(ops):
+    """K5 (both kernels, with and without f0) and K6 addressed through a 3-block row table return the
+    bits they return on the contiguous pool; the blocks are cut so that `previous selection + 1` and
+    the fit's idx +- 1 rows cross block boundaries all the time"""
+    from knn_svc_b200 import ddsp_prematch_dataset as pm
+    rs = np.random.RandomState(11)
+    pool = synth.ar1_frames(1200, seed=61)
+    q = synth.ar1_frames(300, seed=62, reset_every=90)
+    f0q, f0p = synth.f0_track(300, seed=63), synth.f0_track(1200, seed=64)
+    bounds = [0, 401, 402, 1200]
+    pool_t = dev(pool)
+    parts = [pool_t[a:b].clone() for a, b in zip(bounds[:-1], bounds[1:])]
+    table = ops.ShardedRows([t.data_ptr() for t in parts], bounds, 1024, torch.device(DEV))
+    base = rs.randint(395, 408, size=(300, 1))                       # candidates hug the block boundaries
+    idx = np.clip(base + rs.randint(-3, 4, size=(300, 4)), 0, 1199).astype(np.int64)
+    idx[250:] = rs.randint(0, 1200, size=(50, 4))
+    idx[-1] = 1199                                                   # clamp at the end of the pool
+    offs = [0, 120, 121, 300]
+    for staged in (1, 0):
+        _set_opt("concat_staged", staged)
+        try:
+            for f0 in (None, (dev(f0q), dev(f0p))):
+                args = () if f0 is None else f0
+                a = ops.concat_cost_reselect(dev(idx), dev(q), pool_t, *args, concat_weight=0.2, utt_offsets=offs)
+                b = ops.concat_cost_reselect(dev(idx), dev(q), table, *args, concat_weight=0.2, utt_offsets=offs)
+                assert torch.equal(a, b), (staged, f0 is None)
+        finally:
+            _set_opt("concat_staged", 1)
+    wa, ia = ops.weight_fit(dev(idx), pool_t, 0.1, return_info=True, utt_offsets=offs)
+    wb, ib = ops.weight_fit(dev(idx), table, 0.1, return_info=True, utt_offsets=offs)
+    assert torch.equal(wa, wb) and torch.equal(ia, ib)
+
+
 def test_merge_topk64_ranks_on_fp64(ops):
     """two fp64 distances that round to the SAME fp32 value: the fp64 merge keeps their order, and
     shards that hold exact duplicates resolve to the lower global index"""
