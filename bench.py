@@ -474,9 +474,12 @@ def run_single_utterance(args, env):
 
 def cfg5_jobs(world, rank, seed=0):
     """(target speaker -> list of (source utterance id, length)) for THIS rank.  Utterance lengths
-    ~U(150, 1500) frames.  Per target pool the (utterance, target) pairs are sorted by
-    length and dealt round-robin over the ranks: every rank gets the same number of pairs (+-1) and
-    of frames (+-1 utterance) per pool, with no communication."""
+    ~U(150, 1500) frames.  All 7038 (utterance, target) pairs are laid out pool by pool
+    (inside a pool in a fixed pseudo-random order, so that every stretch has the same length mix) and
+    the sequence is cut into `world` contiguous pieces of equal FRAME count: a rank gets one to three
+    target pools and batches of several hundred utterances each (batches that small ranks would get
+    from a plain round-robin leave the per-utterance recurrences with a long tail), with no
+    communication."""
     import numpy as np
     rs = np.random.RandomState(seed)
     lens = {}
@@ -487,12 +490,18 @@ def cfg5_jobs(world, rank, seed=0):
     for spk, tgts in CFG5_TARGETS.items():
         for t in tgts:
             per_target.setdefault(t, []).extend((spk, u) for u in range(CFG5_SRC_UTTS[spk]))
-    mine, total_pairs, total_frames = {}, 0, 0
+    seq = []
     for t in sorted(per_target):
-        pairs = sorted(per_target[t], key=lambda su: (-lens[su], su))
-        total_pairs += len(pairs)
-        total_frames += sum(lens[su] for su in pairs)
-        mine[t] = [(su, lens[su]) for su in pairs[rank::world]]
+        pairs = sorted(per_target[t])
+        order = np.random.RandomState(1234).permutation(len(pairs))
+        seq.extend((t, pairs[i]) for i in order)
+    frames = np.cumsum([lens[su] for _, su in seq])
+    total_pairs, total_frames = len(seq), int(frames[-1])
+    lo = int(np.searchsorted(frames, total_frames * rank / world, side="left")) if rank else 0
+    hi = int(np.searchsorted(frames, total_frames * (rank + 1) / world, side="left")) if rank + 1 < world else total_pairs
+    mine = {}
+    for t, su in seq[lo:hi]:
+        mine.setdefault(t, []).append((su, lens[su]))
     return mine, total_pairs, total_frames
 
 
@@ -504,7 +513,8 @@ def run_cfg5(args, env):
     from knn_svc_b200 import ddsp_prematch_dataset as pm
     mine, total_pairs, total_frames = cfg5_jobs(env.world, env.rank)
     assert total_pairs == 7038
-    pools = {t: _pipeline_pool(env, CFG5_POOL_FRAMES, 900 + 10 * j) for j, t in enumerate(sorted(mine))}
+    all_targets = sorted({t for tg in CFG5_TARGETS.values() for t in tg})
+    pools = {t: _pipeline_pool(env, CFG5_POOL_FRAMES, 900 + 10 * all_targets.index(t)) for t in sorted(mine)}
     # every distinct source utterance of this rank: features on the device (the WavLM output), f0 on the host
     utts = {}
     spk_no = {spk: j for j, spk in enumerate(sorted(CFG5_SRC_UTTS))}
@@ -542,8 +552,8 @@ def run_cfg5(args, env):
                 "config": {"workload": "cfg5: OpenSinger_test_to_nus-smc-corpus_48 split shape — 7038 (utterance, target) pairs "
                                        f"({total_frames} query frames, utterances U(150,1500) frames), 4 target pools of "
                                        f"{CFG5_POOL_FRAMES} frames, post_opt_0.2, prioritize_f0, ckpt_type=mix",
-                           "parallelism": f"pairs dealt over {env.world} ranks per target pool (sorted by length, round-robin), "
-                                          "no communication", "batch_utterances": batch,
+                           "parallelism": f"pairs dealt over {env.world} ranks: pool-major sequence cut into contiguous pieces "
+                                          "of equal frame count, no communication", "batch_utterances": batch,
                            "max_pairs_per_rank": counts[0], "max_frames_per_rank": counts[1],
                            "l2": "30k-frame pools (123 MB fp32 + 61 MB fp16) exceed L2 together with the batch"},
                 "roofline": None, "cpu_baseline": None,

@@ -82,6 +82,7 @@ __device__ __forceinline__ void rs_dot2(const float* __restrict__ pa, const floa
 // Refine blocks: rf_rows pool rows each (64 MB of fp32 rows at 1024 dims: half of L2), at most
 // kRefineMaxBlocks of them (the per-(row, segment) offset table has rf_nblk + 1 entries).
 constexpr int kRefineMaxBlocks = 1024;
+constexpr int kRefineSparseAvg = 96;     // logged entries per row up to which the refine walks the logs row-major
 void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk) {
   int64_t rows = (int64_t)(64 << 20) / ((int64_t)dim * 4);
   rows = rows < 256 ? 256 : rows / 256 * 256;
@@ -222,14 +223,20 @@ template <int NV>
 __global__ void __launch_bounds__(256) knn_refine_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int dim, int n_seg, int cap, int rf_nblk, const float* __restrict__ log_val,
-    const int* __restrict__ log_idx, const int* __restrict__ blk_off, const float* __restrict__ row_thr,
-    float* __restrict__ ref_val, int* __restrict__ stats, const int64_t* __restrict__ mask_lo,
-    const int64_t* __restrict__ mask_hi) {
+    const int* __restrict__ log_idx, const int* __restrict__ log_cnt, const int* __restrict__ blk_off,
+    const float* __restrict__ row_thr, float* __restrict__ ref_val, int* __restrict__ stats,
+    const int* __restrict__ total_logged, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t n_groups = ceil_div64(n_query, 32);
-  const int64_t n_units = n_groups * rf_nblk;
+  // Sparse logs (i.i.d.-like data: a few dozen entries per row, a handful above the threshold) gain
+  // nothing from the block-major order — there is no reuse to be had — and would pay for visiting
+  // every (block, group) unit: they are walked row-major, one unit per 32-row group.  The prep kernel
+  // has counted the log entries; the choice is made here, on the device.
+  const bool sparse = (int64_t)*total_logged <= (int64_t)kRefineSparseAvg * n_query;
+  const int nblk_eff = sparse ? 1 : rf_nblk;
+  const int64_t n_units = n_groups * nblk_eff;
   int scored = 0;
   for (int64_t u = warp; u < n_units; u += n_warps) {
     const int b = (int)(u / n_groups);
@@ -239,10 +246,15 @@ __global__ void __launch_bounds__(256) knn_refine_kernel(
     for (int s = 0; s < n_seg; ++s) {
       int o0 = 0, o1 = 0;
       if (my_row < n_query && my_thr < INFINITY) {
-        const int64_t n_slots = n_query * n_seg;
-        const int* off = blk_off + (int64_t)b * n_slots + (my_row * n_seg + s);
-        o0 = off[0];
-        o1 = off[n_slots];
+        if (sparse) {
+          o1 = log_cnt[my_row * n_seg + s];
+          o1 = o1 > cap ? cap : o1;
+        } else {
+          const int64_t n_slots = n_query * n_seg;
+          const int* off = blk_off + (int64_t)b * n_slots + (my_row * n_seg + s);
+          o0 = off[0];
+          o1 = off[n_slots];
+        }
       }
       // lane-parallel pre-check for rows with a handful of entries (sparse data logs ~1 entry per row
       // and block, few of which pass): their entries below the first threshold are settled here and
@@ -328,6 +340,109 @@ __global__ void __launch_bounds__(256) knn_refine_kernel(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, o);
   if (lane == 0 && stats && scored) atomicAdd(stats + 2, scored);
+}
+
+
+// Rows with at most 32 candidates above the first threshold (all of sparse data at small k) are decided
+// by ONE WARP each — candidates in registers, one per lane: the k-th largest refined similarity by
+// rank counting over shuffles, fp64 scores of the survivors (same rs_dot2), final (dist, index) rank.
+// Rows it decides are marked (row_thr = +inf) and skipped by the CTA-per-row kernel that follows.
+__global__ void __launch_bounds__(256) knn_rescore_small_kernel(
+    const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
+    const double* __restrict__ pn, int dim, int k, int n_seg, int cap, const float* __restrict__ ref_val,
+    const int* __restrict__ log_idx, const int* __restrict__ log_cnt, float* __restrict__ row_thr, float refine_window,
+    int64_t index_offset, float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
+    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+  int n_scored = 0;
+  for (int64_t row = warp; row < n_query; row += n_warps) {
+    if (!(row_thr[row] < INFINITY)) continue;          // log overflow: the exact kernel decides (warp-uniform)
+    // gather the candidates above the first threshold, one per lane
+    float myv = -INFINITY;
+    int mycol = -1, n_valid = 0;
+    bool too_many = false;
+    for (int s = 0; s < n_seg && !too_many; ++s) {
+      const int64_t slot = row * n_seg + s;
+      int c = log_cnt[slot];
+      c = c > cap ? cap : c;
+      for (int e0 = 0; e0 < c; e0 += 32) {
+        const int e = e0 + lane;
+        const float v = e < c ? __ldg(ref_val + slot * cap + e) : -INFINITY;
+        const unsigned m = __ballot_sync(0xffffffffu, v > -INFINITY);
+        if (!m) continue;
+        const int add = __popc(m);
+        if (n_valid + add > 32) {
+          too_many = true;
+          break;
+        }
+        const int col = e < c ? log_idx[slot * cap + e] : -1;
+        // lane t in [n_valid, n_valid + add) takes the (t - n_valid)-th set lane of m
+        const int want = lane - n_valid;
+        const int srcl = (want >= 0 && want < add) ? (int)__fns(m, 0, want + 1) : 0;
+        const float tv = __shfl_sync(0xffffffffu, v, srcl);
+        const int tc = __shfl_sync(0xffffffffu, col, srcl);
+        if (want >= 0 && want < add) {
+          myv = tv;
+          mycol = tc;
+        }
+        n_valid += add;
+      }
+    }
+    if (too_many) continue;                             // the CTA-per-row kernel takes this row
+    // tau1 = k-th largest refined similarity (rank counting, ties by lane)
+    int rnk = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float vj = __shfl_sync(0xffffffffu, myv, j);
+      rnk += (j < n_valid) && ((vj > myv) || (vj == myv && j < lane));
+    }
+    const unsigned kth = __ballot_sync(0xffffffffu, lane < n_valid && rnk == k - 1);
+    const float tau1 = kth ? __shfl_sync(0xffffffffu, myv, __ffs(kth) - 1) : -INFINITY;
+    const bool surv = lane < n_valid && myv >= tau1 - refine_window;
+    unsigned sm = __ballot_sync(0xffffffffu, surv);
+    n_scored += __popc(sm);
+    // fp64 scores of the survivors, two per pass
+    const float* qrow = q + row * dim;
+    const double qnorm = qn[row];
+    const int64_t m_lo = mask_lo ? mask_lo[row] : 0, m_hi = mask_lo ? mask_hi[row] : 0;
+    double myd = INFINITY;
+    while (sm) {
+      const int la = __ffs(sm) - 1;
+      sm &= sm - 1;
+      const int lb = sm ? __ffs(sm) - 1 : la;
+      sm &= sm - 1;
+      const int ia = __shfl_sync(0xffffffffu, mycol, la), ib = __shfl_sync(0xffffffffu, mycol, lb);
+      double da, db;
+      if (vec) rs_dot2<true>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, qrow, dim, lane, da, db);
+      else rs_dot2<false>(p + (int64_t)ia * dim, p + (int64_t)ib * dim, qrow, dim, lane, da, db);
+      // (rs_dot2 leaves the full sums in every lane)
+      if (lane == la) myd = (ia >= m_lo && ia < m_hi) ? 1.0 : 1.0 - da / (qnorm * pn[ia]);
+      if (lane == lb && lb != la) myd = (ib >= m_lo && ib < m_hi) ? 1.0 : 1.0 - db / (qnorm * pn[ib]);
+    }
+    // final order by (dist, index) among the survivors
+    int fr = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double dj = __shfl_sync(0xffffffffu, myd, j);
+      const int cj = __shfl_sync(0xffffffffu, mycol, j);
+      const bool sj = (j < n_valid) && dj < INFINITY;
+      fr += sj && rs_less(dj, cj, myd, mycol);
+    }
+    if (surv && fr < k) {
+      out_dist[row * k + fr] = (float)myd;
+      if (out_dist64) out_dist64[row * k + fr] = myd;
+      out_idx[row * k + fr] = (int64_t)mycol + index_offset;
+    }
+    __syncwarp();
+    if (lane == 0) row_thr[row] = INFINITY;             // decided
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_scored += __shfl_xor_sync(0xffffffffu, n_scored, o);
+  if (lane == 0 && stats && n_scored) atomicAdd(stats + 6, n_scored / 1);
 }
 
 // order-preserving map float -> unsigned (larger float <=> larger key) and back
@@ -535,8 +650,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
     if (grid > max_grid) grid = max_grid;
 #define KNN_REFINE_GO(NV)                                                                                          \
   knn_refine_kernel<NV><<<(unsigned)grid, 256, 0, stream>>>(q, qn, n_query, p, pn, dim, pl.n_seg, pl.cap, pl.rf_nblk, \
-                                                            log_val, log_idx, blk_off, row_thr, ref_val, stats,      \
-                                                            mask_lo, mask_hi)
+                                                            log_val, log_idx, log_cnt, blk_off, row_thr, ref_val,    \
+                                                            stats, stats ? stats + 1 : nullptr, mask_lo, mask_hi)
     switch (vec ? dim / 128 : 0) {
       case 1: KNN_REFINE_GO(1); break;
       case 2: KNN_REFINE_GO(2); break;
@@ -551,7 +666,17 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
 #undef KNN_REFINE_GO
     KNN_LAUNCH_CHECK();
   }
-  // 3. fp64 decision among the candidates inside the refined window
+  // 3. fp64 decision among the candidates inside the refined window: rows with <= 32 candidates above the
+  //    first threshold by one warp each, the others by one CTA each
+  {
+    int64_t g2 = ceil_div64(n_query, 8);
+    if (g2 > 148 * 8) g2 = 148 * 8;
+    knn_rescore_small_kernel<<<(unsigned)g2, 256, 0, stream>>>(q, qn, n_query, p, pn, dim, k, pl.n_seg, pl.cap, ref_val,
+                                                             log_idx, log_cnt, row_thr, 2.0f * refine_eps(dim, vec),
+                                                             index_offset, out_dist, out_dist64, out_idx, stats, mask_lo,
+                                                             mask_hi);
+    KNN_LAUNCH_CHECK();
+  }
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, 0, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, ref_val, log_idx, log_cnt, row_thr,
