@@ -127,12 +127,14 @@ int knnsvc_knn_workspace_layout(int64_t n_query, int64_t n_pool, int dim_pad, in
  *   knnsvc_filter_timing_collect   host float[max_n] <- per-call filter durations (ms)
  *                                  since the last collect; returns the count */
 long long knnsvc_launch_count(void);
-/* tuning / experiment switches: "cta_group" = 1|2 (CTAs per tcgen05.mma),
+/* tuning / experiment switches: "cta_group" = 1 (the cta_group::2 filter variant of round 1 was removed),
  * "bf16_operands" = 0|1 (bf16 instead of fp16 tensor-core operands; measurement only,
  * the error window is sized for fp16), "concat_staged" = 1|0 (shared-memory staged K5
  * kernel where the row shape allows it, or the general kernel only),
  * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes),
  * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
+ * "query_group" (chains — query tile x segment — per group of the filter's two-level unit order,
+ * 0 = default 2 x SM count; a value >= the number of chains gives the flat block-major order),
  * "log_cap" (candidate-log slots per row and pool segment, 0 = default 2048; the tests shrink it to
  * drive rows into the overflow -> exact-kernel path with small fixtures),
  * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static

@@ -24,17 +24,7 @@ void set_error(const char* fmt, ...) {
 // Tuning options: process-wide diagnostic switches (knnsvc_set_option).  Each is one relaxed atomic
 // read at launch time, so setting one from another thread is well defined; none of them changes
 // results, only which kernel shape / schedule produces them.
-static std::atomic<int> g_opt_cta_group{0};  // 0 = unset -> env KNNSVC_CTA_GROUP or default
 static std::atomic<int> g_opt_bf16{0};
-int opt_cta_group() {
-  int v = g_opt_cta_group.load(std::memory_order_relaxed);
-  if (v == 0) {
-    const char* e = getenv("KNNSVC_CTA_GROUP");
-    v = (e && e[0] == '2') ? 2 : 1;
-    g_opt_cta_group.store(v, std::memory_order_relaxed);
-  }
-  return v;
-}
 int opt_bf16() { return g_opt_bf16.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_filter_flags{1};
 int opt_filter_flags() { return g_opt_filter_flags.load(std::memory_order_relaxed); }
@@ -47,6 +37,8 @@ int opt_spin_ns() { return g_opt_spin_ns.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_epi_sleep_ns{0};
 int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns.load(std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_query_group{0};
+int opt_query_group() { return g_opt_query_group.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_log_cap{0};
 int opt_log_cap() { return g_opt_log_cap.load(std::memory_order_relaxed); }
 
@@ -265,8 +257,7 @@ long long knnsvc_launch_count(void) { return g_launches.load(); }
 int knnsvc_set_option(const char* name, int value) {
   KNN_CHECK_ARG(name != nullptr, -1, "set_option: null name");
   if (strcmp(name, "cta_group") == 0) {
-    KNN_CHECK_ARG(value == 1 || value == 2, -1, "set_option: cta_group must be 1 or 2");
-    g_opt_cta_group.store(value, std::memory_order_relaxed);
+    KNN_CHECK_ARG(value == 1, -1, "set_option: the cta_group::2 variant was removed (measured slower); only 1 is accepted");
     return 0;
   }
   if (strcmp(name, "spin_sleep_ns") == 0) {
@@ -295,6 +286,11 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "block_tiles") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: block_tiles out of range");
     g_opt_block_tiles.store(value, std::memory_order_relaxed);
+    return 0;
+  }
+  if (strcmp(name, "query_group") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= (1 << 24), -1, "set_option: query_group out of range");
+    g_opt_query_group.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "log_cap") == 0) {

@@ -6,11 +6,11 @@
 namespace knnsvc {
 
 // ---- tuning options (capi.cu): diagnostic switches, see knnsvc_set_option
-int opt_cta_group();   // 1 or 2 CTAs per tcgen05.mma
 int opt_bf16();
 int opt_filter_flags();   // bit0: L2 prefetch of the next unit's query tile, bit2: static unit schedule (bit1 unused)
 int opt_weight_fit_cluster();   // 1 (default): few long utterances are fitted by a cluster of 8 CTAs each
 int opt_log_cap();       // candidate-log slots per (row, segment); 0 = default
+int opt_query_group();   // chains per group of the filter's two-level unit order (0 = default)
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
@@ -33,6 +33,7 @@ int launch_knn_exact_rows(const float* q, const double* qn, int64_t n_query, con
 struct FilterPlan {
   int ctas, n_qtiles, n_ptiles, n_seg, n_blk, n_units, grid, cap;
   int rf_rows, rf_nblk;   // refine blocks (knn_select.cu): pool rows per block, number of blocks
+  int grp;                // chains per group of the filter's two-level unit order
 };
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k);
 void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk);

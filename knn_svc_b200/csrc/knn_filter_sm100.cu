@@ -4,13 +4,11 @@
 // (ddsp_prematch_dataset.py:1196-1206, lib_ongaku_test.py:148-175) without ever
 // writing the [T, Np] distance matrix.
 //
-// Shape of the computation (persistent over work units), two variants:
-//   CTAS = 2 (default): a CTA PAIR on one TPC runs tcgen05.mma.cta_group::2 with
-//     UMMA M = 256 (128 query rows per CTA), N = 256.  Each CTA stages its own
-//     A = 128 query rows x 64 fp16 and HALF of B = 128 pool rows x 64 fp16 per
-//     pipeline stage (32 KB, 6 stages), so shared-memory fill and L2->SM traffic
-//     per FLOP are 2/3 of the single-CTA shape.  The leader CTA issues the MMAs.
-//   CTAS = 1: one CTA, UMMA M = 128, N = 256, A 16 KB + B 32 KB per stage, 4 stages.
+// Shape of the computation (persistent over work units):
+//   one CTA per SM, UMMA M = 128, N = 256, A 16 KB + B 32 KB per stage, 4 stages.
+//   (A cta_group::2 variant — CTA pair, UMMA M = 256, half of B per CTA — was built in round 1 and
+//   measured again in round 2 at the 8-GPU shard size: 1.5-1.8% slower than this shape,
+//   profiles/r2_cta_group_ab_1p25M.jsonl; a pair runs at the pace of its slower SM.  It was removed.)
 //   D = 128 lanes x 256 fp32 columns per CTA in TMEM, double buffered (512 columns)
 //   warp 0 : TMA producer      warp 1 : tcgen05.mma issuer + TMEM owner
 //   warps 2-5 : epilogue, one thread per query row (TMEM lane), tcgen05.ld 32x32b
@@ -53,12 +51,11 @@ constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int kSchedDepth = 4;   // units the producer may run ahead of the slowest consumer warp
 
-template <int CTAS>
 struct Cfg {
-  static constexpr int B_ROWS = BN / CTAS;             // pool rows this CTA stages per tile
+  static constexpr int B_ROWS = BN;                    // pool rows staged per tile
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int STAGES = 4;
   // operand ring first: SWIZZLE_128B wants 1024-byte aligned stage bases
   static constexpr int ring = 0;
   static constexpr int topv = ring + STAGES * STAGE_BYTES;              // float [kMaxK][BM]
@@ -77,21 +74,6 @@ struct Cfg {
 // ----------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -100,10 +82,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// arrive on a barrier that may live in the peer CTA (shared::cluster address from mapa)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -139,22 +117,12 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
     __nanosleep(sleep_ns);
   }
 }
-// TMA tile load; with CTAS == 2 the completion bytes are credited to `bar`, a shared::cluster
-// address that names the LEADER CTA's barrier, whichever CTA of the pair issues the copy.
-template <int CTAS>
+// TMA tile load; the completion bytes are credited to `bar`
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  if constexpr (CTAS == 2) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-            "r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  }
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 // L2 prefetch of one TMA box (no shared-memory destination, no completion to wait for)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
@@ -162,38 +130,19 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// completion of all prior MMAs of this thread -> one arrival on `bar` (in both CTAs of the pair when CTAS == 2)
-template <int CTAS>
+// completion of all prior MMAs of this thread -> one arrival on `bar`
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  if constexpr (CTAS == 2) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
-  } else {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-  }
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-template <int CTAS>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  if constexpr (CTAS == 2) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -221,10 +170,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128*CTAS.
-template <int CTAS>
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N=256, M=128.
 struct InstrDesc {
-  static constexpr uint32_t value = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
+  static constexpr uint32_t value = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
 struct RowState {
@@ -334,16 +282,25 @@ __device__ __forceinline__ RowState filter_insert(RowState st, float v, int col,
   return st;
 }
 
-// Work unit u -> (block, segment, query tile) and the unit's pool-tile range.  Block-major order:
-// all chains' block 0, then all chains' block 1, ...
+// Work unit u -> (block, segment, query tile) and the unit's pool-tile range.  The chains (query tile x
+// segment) are taken in GROUPS of `grp` chains; inside a group the order is block-major (all the group's
+// chains' block 0, then block 1, ...), and the groups follow one another.  With ONE group (the default,
+// see plan_filter) this is the flat block-major order; smaller groups were meant to keep a group's query
+// tiles in L2 while the pool blocks stream past them — measured, they do not (plan_filter).  A unit only
+// ever depends on the same chain's previous block, which has a lower unit index in every order.
 struct Unit {
   int qt, seg, blk, t0, t1;
 };
-__device__ __forceinline__ Unit decode_unit(int u, int n_qtiles, int n_seg, int n_blk, int n_ptiles) {
+__device__ __forceinline__ Unit decode_unit(int u, int n_qtiles, int n_seg, int n_blk, int n_ptiles, int grp) {
   const int n_chains = n_qtiles * n_seg;
+  const int per_group = grp * n_blk;
+  const int g = u / per_group;
+  const int r = u - g * per_group;
+  const int c0 = g * grp;
+  const int in_group = n_chains - c0 < grp ? n_chains - c0 : grp;
   Unit w;
-  w.blk = u / n_chains;
-  const int c = u - w.blk * n_chains;
+  w.blk = r / in_group;
+  const int c = c0 + (r - w.blk * in_group);
   w.seg = c / n_qtiles;
   w.qt = c - w.seg * n_qtiles;
   const int s0 = (int)((int64_t)w.seg * n_ptiles / n_seg), s1 = (int)((int64_t)(w.seg + 1) * n_ptiles / n_seg);
@@ -359,7 +316,7 @@ __device__ __forceinline__ Unit decode_unit(int u, int n_qtiles, int n_seg, int 
 // distance is DEFINED to be 1 (similarity 0) — the offline prematch's self-utterance rule
 // `dists[:, start_index:end_index] = 1` (ddsp_prematch_dataset.py:1623-1624).  The accumulator
 // values of those columns are replaced by 0 before the filter sees them.
-template <int CTAS, bool MASKED>
+template <bool MASKED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                   int64_t n_query, int64_t n_pool, int k_blocks, int k, int n_qtiles, int n_ptiles, int n_seg,
@@ -367,8 +324,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                   float* __restrict__ seg_top, float* __restrict__ seg_kth, int* __restrict__ seg_flag,
                   uint32_t idesc, uint32_t spin_ns, const int64_t* __restrict__ mask_lo,
                   const int64_t* __restrict__ mask_hi, const float* __restrict__ q_err,
-                  const float* __restrict__ p_err, int* __restrict__ unit_counter, int prefetch) {
-  using L = Cfg<CTAS>;
+                  const float* __restrict__ p_err, int* __restrict__ unit_counter, int prefetch, int grp) {
+  using L = Cfg;
   extern __shared__ unsigned char smem_raw_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_unaligned) + 1023) &
                                                          ~(uintptr_t)1023);
@@ -376,12 +333,10 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_units = n_qtiles * n_seg * n_blk;
-  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
-  const bool leader = cta_rank == 0;
-  const int worker = blockIdx.x / CTAS;        // index of this CTA (pair) among the persistent workers
-  const int n_workers = gridDim.x / CTAS;
-  // dynamic unit scheduling (single-CTA shape): units are claimed from a global counter in index order
-  const bool dyn = CTAS == 1 && !(prefetch & 4);
+  const int worker = blockIdx.x;               // index of this CTA among the persistent workers
+  const int n_workers = gridDim.x;
+  // dynamic unit scheduling: units are claimed from a global counter in index order (bit 2: static split)
+  const bool dyn = !(prefetch & 4);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -392,7 +347,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(sbase + L::tmem_full_bar + b * 8, 1);
-      mbar_init(sbase + L::tmem_empty_bar + b * 8, 4 * CTAS);  // one arrive per epilogue warp of the pair
+      mbar_init(sbase + L::tmem_empty_bar + b * 8, 4);  // one arrive per epilogue warp
     }
     for (int i = 0; i < kSchedDepth; ++i) {
       mbar_init(sbase + L::sched_full_bar + i * 8, 1);
@@ -402,21 +357,13 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    if constexpr (CTAS == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L::tmem_ptr),
-                   "n"(TMEM_COLS)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L::tmem_ptr),
-                   "n"(TMEM_COLS)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + L::tmem_ptr),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers must exist before anything signals them
-  else __syncthreads();
+  __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::tmem_ptr);
 
@@ -448,8 +395,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
         }
         if (u < 0) break;
-        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
-        const int q_row = (un.qt * CTAS + (int)cta_rank) * BM;
+        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles, grp);
+        const int q_row = un.qt * BM;
         const int n_t = un.t1 - un.t0;
         // The next unit is claimed four tiles before this one ends (not at its start: CTAs that
         // launch first would grab second units before the last CTAs have taken their first), and
@@ -464,8 +411,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             u_next = claim();
             claimed = true;
             if ((prefetch & 1) && u_next >= 0) {
-              const Unit nx = decode_unit(u_next, n_qtiles, n_seg, n_blk, n_ptiles);
-              if (nx.qt != un.qt) nq_row = (nx.qt * CTAS + (int)cta_rank) * BM;
+              const Unit nx = decode_unit(u_next, n_qtiles, n_seg, n_blk, n_ptiles, grp);
+              if (nx.qt != un.qt) nq_row = nx.qt * BM;
             }
           }
           if (nq_row >= 0) {
@@ -473,20 +420,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             for (int kb = j * k_blocks / a_span; kb < (j + 1) * k_blocks / a_span; ++kb)
               tma_prefetch_2d(&map_q, kb * BK, nq_row);
           }
-          const int p_row = pt * BN + (int)cta_rank * L::B_ROWS;
+          const int p_row = pt * BN;
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait_backoff(sbase + L::empty_bar + stage * 8, phase ^ 1, spin_ns & 0xffffu);
-            const uint32_t full_local = sbase + L::full_bar + stage * 8;
-            uint32_t full = full_local;
-            if constexpr (CTAS == 2) {
-              full = mapa(full_local, 0);                                  // the leader's barrier collects both CTAs' bytes
-              if (leader) mbar_expect_tx(full_local, 2 * L::STAGE_BYTES);
-            } else {
-              mbar_expect_tx(full_local, L::STAGE_BYTES);
-            }
+            const uint32_t full = sbase + L::full_bar + stage * 8;
+            mbar_expect_tx(full, L::STAGE_BYTES);
             const uint32_t a_dst = sbase + L::ring + stage * L::STAGE_BYTES;
-            tma_load_2d<CTAS>(a_dst, &map_q, full, kb * BK, q_row);
-            tma_load_2d<CTAS>(a_dst + A_BYTES, &map_p, full, kb * BK, p_row);
+            tma_load_2d(a_dst, &map_q, full, kb * BK, q_row);
+            tma_load_2d(a_dst + A_BYTES, &map_p, full, kb * BK, p_row);
             if (++stage == L::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -497,8 +438,8 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_n = 0;
@@ -519,7 +460,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           if (u >= n_units) u = -1;
         }
         if (u < 0) break;
-        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
+        const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles, grp);
         for (int pt = un.t0; pt < un.t1; ++pt, ++tile_n) {
           const uint32_t buf = tile_n & 1;
           const uint32_t buf_phase = (tile_n >> 1) & 1;
@@ -535,15 +476,15 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; ++kk) {
               // advancing 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_f16<CTAS>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
+              umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
             }
-            tcgen05_commit<CTAS>(sbase + L::empty_bar + stage * 8);  // smem slot free once these MMAs retire
+            tcgen05_commit(sbase + L::empty_bar + stage * 8);  // smem slot free once these MMAs retire
             if (++stage == L::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tcgen05_commit<CTAS>(sbase + L::tmem_full_bar + buf * 8);  // accumulator ready for the epilogue(s)
+          tcgen05_commit(sbase + L::tmem_full_bar + buf * 8);  // accumulator ready for the epilogue(s)
         }
       }
     }
@@ -572,11 +513,11 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (u >= n_units) u = -1;
       }
       if (u < 0) break;
-      const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles);
+      const Unit un = decode_unit(u, n_qtiles, n_seg, n_blk, n_ptiles, grp);
       const int seg = un.seg, qt = un.qt, t0 = un.t0, t1 = un.t1;
-      const int64_t row = (int64_t)(qt * CTAS + (int)cta_rank) * BM + row_in_tile;
+      const int64_t row = (int64_t)qt * BM + row_in_tile;
       const bool row_ok = row < n_query;
-      const int flag_base = ((qt * CTAS + (int)cta_rank) * 4 + quad) * n_seg;
+      const int flag_base = (qt * 4 + quad) * n_seg;
       const int64_t slot = row * n_seg + seg;
       RowState st;
       if (un.blk > 0) {
@@ -678,8 +619,7 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CTAS == 2) mbar_arrive_cluster(mapa(sbase + L::tmem_empty_bar + buf * 8, 0));
-          else mbar_arrive(sbase + L::tmem_empty_bar + buf * 8);
+          mbar_arrive(sbase + L::tmem_empty_bar + buf * 8);
         }
       }
       if (row_ok) {
@@ -693,18 +633,14 @@ knn_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   }
 
-  // the pair must stay resident until both CTAs are done with each other's shared memory and TMEM
+  // every warp is done with TMEM before its owner frees it
   __syncwarp();
   tcgen05_fence_before();
-  if constexpr (CTAS == 2) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
   tcgen05_fence_after();
   if (warp == 1) {
     __syncwarp();
-    if constexpr (CTAS == 2)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -757,10 +693,10 @@ int num_sms() {
 
 FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   FilterPlan pl;
-  pl.ctas = opt_cta_group();
-  pl.n_qtiles = (int)ceil_div64(n_query, BM * pl.ctas);
+  pl.ctas = 1;   // CTAs per tcgen05.mma (kept in the plan record for the tests / tools that print it)
+  pl.n_qtiles = (int)ceil_div64(n_query, BM);
   pl.n_ptiles = (int)ceil_div64(n_pool, BN);
-  const int workers = num_sms() / pl.ctas;
+  const int workers = num_sms();
   // Blocks of <= blk pool tiles (default 96 tiles = 24576 rows = 48 MB of fp16 operand at 1024 dims).
   // Measured on B200 (tools/block_ab.py, 100k x 2M..10M): speed is flat from 64 tiles up; DRAM
   // traffic per launch has a shallow minimum around 96-192 tiles (larger blocks: fewer query-tile
@@ -780,9 +716,8 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
     const int64_t par = chains < workers ? chains : workers;
     const int64_t units = chains * nb;
     const double tiles = (double)ceil_div64(seg_tiles, nb) + 0.25;  // + state hand-over per unit
-    // dynamic claiming (single-CTA shape): no whole-wave quantisation, about half a unit of tail
-    double rounds = pl.ctas == 1 ? (units > par ? (double)units / (double)par + 0.5 : 1.0)
-                                 : (double)ceil_div64(units, par);
+    // dynamic claiming: no whole-wave quantisation, about half a unit of tail
+    double rounds = units > par ? (double)units / (double)par + 0.5 : 1.0;
     double cost = rounds * tiles * (1.0 + 0.004 * s);
     // with fewer than two chains per CTA the next block of a chain is usually claimed before its
     // predecessor has finished, and the round proceeds at the pace of the slowest SM
@@ -795,8 +730,20 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   }
   pl.n_seg = best_s;
   pl.n_blk = best_nb;
+  // chains per group of the two-level unit order (see decode_unit).  Default: ONE group (flat block-major
+  // order).  Measured on 100k x 2.5M (profiles/r2_filter_traffic_ab.txt): groups of 148 / 296 / 444 / 592
+  // query tiles with 96 / 48 / 32-tile blocks move 58-74 GB per launch against 57-60 GB flat, at the same or
+  // lower speed — L2 does not retain a 38-76 MB query group next to the streaming pool block, so the
+  // re-reads the grouping was meant to remove stay, and a block is additionally read once per group.
+  {
+    const int n_chains = pl.n_qtiles * best_s;
+    int grp = opt_query_group() > 0 ? opt_query_group() : n_chains;
+    if (grp > n_chains) grp = n_chains;
+    if (grp < 1) grp = 1;
+    pl.grp = grp;
+  }
   pl.n_units = pl.n_qtiles * pl.n_seg * pl.n_blk;
-  pl.grid = (pl.n_units < workers ? pl.n_units : workers) * pl.ctas;
+  pl.grid = pl.n_units < workers ? pl.n_units : workers;
   // Candidate-log slots per (row, segment).  Sparse data (i.i.d. rows) logs ~70 entries per row at k = 4;
   // WavLM-like rows (a large shared mean: every pool row within ~0.03 cosine of every other) hold
   // ~800-1200 candidates inside the 2*eps window of the k-th best at 1M-10M pool rows, and a row that
@@ -805,35 +752,28 @@ FilterPlan plan_filter(int64_t n_query, int64_t n_pool, int k) {
   return pl;
 }
 
-size_t filter_flag_count(const FilterPlan& pl) { return (size_t)pl.n_qtiles * pl.ctas * 4 * pl.n_seg; }
+size_t filter_flag_count(const FilterPlan& pl) { return (size_t)pl.n_qtiles * 4 * pl.n_seg; }
 
-template <int CTAS, bool MASKED>
+template <bool MASKED>
 static int launch_variant(const CUtensorMap& map_q, const CUtensorMap& map_p, int64_t n_query, int64_t n_pool,
                           int k_blocks, int k, const FilterPlan& pl, float* log_val, int* log_idx, int* log_cnt,
                           float* seg_top, float* seg_kth, int* seg_flag, const int64_t* mask_lo,
                           const int64_t* mask_hi, const float* q_err, const float* p_err, int* unit_counter,
                           cudaStream_t stream) {
   static PerDevice smem_attr;   // one per template instance
-  KNN_SMEM_ATTR(smem_attr, (knn_filter_kernel<CTAS, MASKED>), Cfg<CTAS>::SMEM_BYTES);
+  KNN_SMEM_ATTR(smem_attr, knn_filter_kernel<MASKED>, Cfg::SMEM_BYTES);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   count_launch();
   // a_format/b_format (bits 7-9, 10-12): 0 = fp16, 1 = bf16
-  const uint32_t idesc = InstrDesc<CTAS>::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
-  KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<CTAS, MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
+  const uint32_t idesc = InstrDesc::value | (opt_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
+  KNN_CUDA(cudaLaunchKernelEx(&cfg, knn_filter_kernel<MASKED>, map_q, map_p, n_query, n_pool, k_blocks, k,
                               pl.n_qtiles, pl.n_ptiles, pl.n_seg, pl.n_blk, pl.cap, log_val, log_idx, log_cnt, seg_top, seg_kth,
                               seg_flag, idesc, (uint32_t)opt_spin_ns() | ((uint32_t)opt_epi_sleep_ns() << 16), mask_lo, mask_hi, q_err, p_err,
-                              unit_counter, opt_filter_flags()));
+                              unit_counter, opt_filter_flags(), pl.grp));
   return 0;
 }
 
@@ -849,18 +789,13 @@ int launch_knn_filter(const void* qh, int64_t n_query, const void* ph, int64_t n
   CUtensorMap map_q, map_p;
   int rc = make_half_map(&map_q, qh, n_query, dim_pad, BM);
   if (rc) return rc;
-  rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN / pl.ctas);
+  rc = make_half_map(&map_p, ph, n_pool, dim_pad, BN);
   if (rc) return rc;
-#define KNN_FILTER_GO(C, M)                                                                                   \
-  return launch_variant<C, M>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top, \
-                              seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, unit_counter, stream)
-  if (pl.ctas == 2) {
-    if (mask_lo) KNN_FILTER_GO(2, true);
-    KNN_FILTER_GO(2, false);
-  }
-  if (mask_lo) KNN_FILTER_GO(1, true);
-  KNN_FILTER_GO(1, false);
-#undef KNN_FILTER_GO
+  if (mask_lo)
+    return launch_variant<true>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
+                                seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, unit_counter, stream);
+  return launch_variant<false>(map_q, map_p, n_query, n_pool, dim_pad / BK, k, pl, log_val, log_idx, log_cnt, seg_top,
+                               seg_kth, seg_flag, mask_lo, mask_hi, q_err, p_err, unit_counter, stream);
 }
 
 }  // namespace knnsvc

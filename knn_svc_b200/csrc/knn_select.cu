@@ -83,6 +83,20 @@ __device__ __forceinline__ void rs_dot2(const float* __restrict__ pa, const floa
 // kRefineMaxBlocks of them (the per-(row, segment) offset table has rf_nblk + 1 entries).
 constexpr int kRefineMaxBlocks = 1024;
 constexpr int kRefineSparseAvg = 96;     // logged entries per row up to which the refine walks the logs row-major
+// Mode of the decision stage, chosen ON THE DEVICE from what the prep kernel counted:
+//   refine  more than kRefineMinAbove candidates per row above the first (fp16-window) threshold — dense
+//           pools of near-duplicates: they are first re-scored in fp32, block-major (knn_refine), and only
+//           the few inside the refined window are scored in fp64;
+//   direct  otherwise: the candidates above the first threshold go straight to the fp64 scoring, one CTA per
+//           row (adjacent rows run side by side on an SM and share their candidates through L1).  Measured
+//           (profiles/r2_dense_search_*.jsonl): with ~30-150 candidates per row the extra pass over the log
+//           costs more than the fp64 arithmetic it saves (100k x 30k, k=32: 5.5 ms direct, 9.2 ms refined),
+//           with ~800-1100 it wins (20k x 1M near-duplicate pool, k=4: 14.3 -> 10.9 ms).
+constexpr int kRefineMinAbove = 400;
+constexpr int kStatAbove = 8;            // stats slot (relative to the stats base) of the prep kernel's count
+__device__ __forceinline__ bool refine_mode(const int* stats, int64_t n_query) {
+  return (int64_t)stats[kStatAbove] > (int64_t)kRefineMinAbove * n_query;
+}
 void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk) {
   int64_t rows = (int64_t)(64 << 20) / ((int64_t)dim * 4);
   rows = rows < 256 ? 256 : rows / 256 * 256;
@@ -115,12 +129,12 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
     int64_t n_query, int k, int n_seg, int cap, int rf_rows, int rf_nblk, const int* __restrict__ log_idx,
     const int* __restrict__ log_cnt, const float* __restrict__ seg_top, float* __restrict__ row_thr,
     int* __restrict__ blk_off, int64_t* __restrict__ flag_list, int* __restrict__ flag_count, int* __restrict__ stats,
-    const float* __restrict__ q_err, const float* __restrict__ p_err, int dim_pad) {
+    const float* __restrict__ log_val, const float* __restrict__ q_err, const float* __restrict__ p_err, int dim_pad) {
   __shared__ float s_top[RP_WARPS][RP_MAXTOP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_top = n_seg * k;
   const float window = 2.0f * filter_eps(q_err, p_err, dim_pad);
-  int logged = 0;
+  int logged = 0, above = 0;
   for (int64_t row = (int64_t)blockIdx.x * RP_WARPS + warp; row < n_query; row += (int64_t)gridDim.x * RP_WARPS) {
     __syncwarp();
     for (int e = lane; e < n_top; e += 32) s_top[warp][e] = seg_top[row * n_top + e];
@@ -160,12 +174,14 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
       const int64_t slot = row * n_seg + s;
       const int c = log_cnt[slot];
       const int* li = log_idx + slot * cap;
+      const float* lvp = log_val + slot * cap;
       // table layout [block][slot]: the refine kernel reads one block's offsets of 32 consecutive rows at once
       const int64_t n_slots = n_query * n_seg;
       int* off = blk_off + slot;
       for (int e0 = 0; e0 < c; e0 += 32) {
         const int e = e0 + lane;
         const int b = e < c ? li[e] / rf_rows : 0;
+        above += (e < c && lvp[e] >= thr) ? 1 : 0;
         int pb = __shfl_up_sync(0xffffffffu, b, 1);
         if (lane == 0) pb = e0 > 0 ? li[e0 - 1] / rf_rows : -1;
         if (e < c)
@@ -178,6 +194,9 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) logged += __shfl_xor_sync(0xffffffffu, logged, o);
   if (lane == 0 && stats && logged) atomicAdd(stats + 1, logged);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  if (lane == 0 && stats && above) atomicAdd(stats + kStatAbove, above);
 }
 
 // fp32 dot products of TWO pool rows with the query row held in registers (NV float4 per lane,
@@ -220,7 +239,7 @@ __device__ __forceinline__ void refine_dot2(const float4 (&qv)[NV], const float*
 // so at any time the whole grid gathers from one or two blocks of the pool.
 //   NV > 0: dim == NV * 128, rows 16-byte aligned: query row in registers.   NV == 0: any dim.
 template <int NV>
-__global__ void __launch_bounds__(256) knn_refine_kernel(
+__global__ void __launch_bounds__(256, 3) knn_refine_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int dim, int n_seg, int cap, int rf_nblk, const float* __restrict__ log_val,
     const int* __restrict__ log_idx, const int* __restrict__ log_cnt, const int* __restrict__ blk_off,
@@ -234,6 +253,7 @@ __global__ void __launch_bounds__(256) knn_refine_kernel(
   // nothing from the block-major order — there is no reuse to be had — and would pay for visiting
   // every (block, group) unit: they are walked row-major, one unit per 32-row group.  The prep kernel
   // has counted the log entries; the choice is made here, on the device.
+  if (!refine_mode(stats, n_query)) return;
   const bool sparse = (int64_t)*total_logged <= (int64_t)kRefineSparseAvg * n_query;
   const int nblk_eff = sparse ? 1 : rf_nblk;
   const int64_t n_units = n_groups * nblk_eff;
@@ -359,6 +379,7 @@ __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
   const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
   int n_scored = 0;
+  if (!refine_mode(stats, n_query)) return;
   for (int64_t row = warp; row < n_query; row += n_warps) {
     if (!(row_thr[row] < INFINITY)) continue;          // log overflow: the exact kernel decides (warp-uniform)
     // gather the candidates above the first threshold, one per lane
@@ -457,10 +478,13 @@ __device__ __forceinline__ float key_float(unsigned key) {
 __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
-    const float* __restrict__ ref_val, const int* __restrict__ log_idx, const int* __restrict__ log_cnt,
-    const float* __restrict__ row_thr, float refine_window, int64_t index_offset, float* __restrict__ out_dist,
-    double* __restrict__ out_dist64, int64_t* __restrict__ out_idx, int* __restrict__ stats,
-    const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
+    const float* __restrict__ ref_val_in, const float* __restrict__ log_val, const int* __restrict__ log_idx,
+    const int* __restrict__ log_cnt, const float* __restrict__ row_thr, float refine_window, int64_t index_offset,
+    float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
+    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
+  // direct mode: the candidates above the FIRST threshold are scored in fp64 right away (no refined values exist)
+  const bool direct = !refine_mode(stats, n_query);
+  const float* __restrict__ ref_val = direct ? log_val : ref_val_in;
   __shared__ double s_dist[RS_LIST];             // exact distances of the survivors in s_cand
   __shared__ int s_cand[RS_LIST];
   __shared__ double s_best_d[kMaxK];             // scratch for the reduction to the best k
@@ -487,7 +511,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     unsigned prefix = 0, prefix_mask = 0;
     int want = k;                  // rank still to find inside the current prefix bucket (1-based, from the top)
     bool have_tau = true;
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < (direct ? 0 : 4); ++pass) {
       const int shift = 24 - 8 * pass;
       for (int i = tid; i < 256; i += RS_THREADS) s_hist[i] = 0;
       __syncthreads();
@@ -540,7 +564,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
       prefix_mask |= 255u << shift;
     }
     const float prev_v = have_tau ? key_float(prefix) : -INFINITY;
-    const float thr = prev_v > -INFINITY ? prev_v - refine_window : -INFINITY;   // block-uniform
+    const float thr = direct ? row_thr[row] : (prev_v > -INFINITY ? prev_v - refine_window : -INFINITY);   // block-uniform
     const double qnorm = qn[row];
     // masked column range: distance defined as 1 (ddsp_prematch_dataset.py:1623-1624)
     const int64_t m_lo = mask_lo ? mask_lo[row] : 0, m_hi = mask_lo ? mask_hi[row] : 0;
@@ -617,7 +641,10 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     score();
     __syncthreads();
     reduce_to_best(true);
-    if (tid == 0 && stats) atomicAdd(stats + 6, s_nsurv);
+    if (tid == 0 && stats) {
+      atomicAdd(stats + 6, s_nsurv);
+      if (direct) atomicAdd(stats + 2, s_nsurv);
+    }
   }
 }
 
@@ -636,8 +663,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
     if (grid > 148 * 16) grid = 148 * 16;
     knn_refine_prep_kernel<<<(unsigned)grid, RP_WARPS * 32, 0, stream>>>(n_query, k, pl.n_seg, pl.cap, pl.rf_rows,
                                                                        pl.rf_nblk, log_idx, log_cnt, seg_top, row_thr,
-                                                                       blk_off, flag_list, flag_count, stats, q_err,
-                                                                       p_err, dim_pad);
+                                                                       blk_off, flag_list, flag_count, stats, log_val,
+                                                                       q_err, p_err, dim_pad);
     KNN_LAUNCH_CHECK();
   }
   // 2. fp32 refine of every candidate above the first threshold, block-major
@@ -679,7 +706,7 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
   }
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, 0, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
-                                                                   pl.cap, ref_val, log_idx, log_cnt, row_thr,
+                                                                   pl.cap, ref_val, log_val, log_idx, log_cnt, row_thr,
                                                                    2.0f * refine_eps(dim, vec), index_offset, out_dist,
                                                                    out_dist64, out_idx, stats, mask_lo, mask_hi);
   KNN_LAUNCH_CHECK();

@@ -546,19 +546,19 @@ def filter_options():
     from knn_svc_b200 import _lib
     lib = _lib.load()
 
-    def set_(block_tiles=0, flags=1, cta_group=1):
+    def set_(block_tiles=0, flags=1, query_group=0):
         _lib.check(lib.knnsvc_set_option(b"block_tiles", block_tiles), "set_option")
         _lib.check(lib.knnsvc_set_option(b"filter_flags", flags), "set_option")
-        _lib.check(lib.knnsvc_set_option(b"cta_group", cta_group), "set_option")
+        _lib.check(lib.knnsvc_set_option(b"query_group", query_group), "set_option")
     yield set_
     set_()
 
 
-@pytest.mark.parametrize("block_tiles,flags,cta_group", [(1, 1, 1), (2, 1, 1), (3, 0, 1), (1, 5, 1), (2, 5, 2), (1, 1, 2)])
-def test_knn_search_block_traversal_changes_nothing(ops, filter_options, small_log, block_tiles, flags, cta_group):
+@pytest.mark.parametrize("block_tiles,flags,query_group", [(1, 1, 0), (2, 1, 0), (3, 0, 0), (1, 5, 0), (2, 1, 2), (1, 1, 5), (3, 5, 1)])
+def test_knn_search_block_traversal_changes_nothing(ops, filter_options, small_log, block_tiles, flags, query_group):
     """The filter walks the pool in L2-sized blocks, handing each row's state (top-k list, candidate
     log) from block to block through global memory, with units claimed dynamically or split statically,
-    by one CTA or a CTA pair.  Tiny blocks (256-768 pool rows) force several hand-overs per chain on sets
+    in the flat block-major order or in groups of a few chains (two-level order).  Tiny blocks (256-768 pool rows) force several hand-overs per chain on sets
     with dense neighbourhoods, exact ties, masked ranges and overflowing logs: results must be
     bit-identical to the default traversal (whose parity with the oracle the tests above establish)."""
     q, p = synth.ar1_frames(700, seed=81, reset_every=250), synth.ar1_frames(20000, seed=82)
@@ -574,11 +574,11 @@ def test_knn_search_block_traversal_changes_nothing(ops, filter_options, small_l
     o_idx, o_val = orc.knn(q, p, 5)
     rows = set_rows(o_val, 4)
     assert np.array_equal(np.sort(ref[4][1].cpu().numpy()[rows], 1), np.sort(o_idx[rows, :4], 1))
-    filter_options(block_tiles, flags, cta_group)
+    filter_options(block_tiles, flags, query_group)
     for k in (4, 32):
         d, i, st = ops.knn_search(qp, pp, k, return_stats=True)
         assert torch.equal(i, ref[k][1]) and torch.equal(d, ref[k][0])
-        n_qtiles = -(-700 // (128 * cta_group))
+        n_qtiles = -(-700 // 128)
         assert int(st[4]) > n_qtiles * int(st[3]), "expected chains of several blocks"
         dm, im = ops.knn_search(qp, pp, k, mask_lo=lo, mask_hi=hi)
         assert torch.equal(im, ref[k, "m"][1]) and torch.equal(dm, ref[k, "m"][0])

@@ -19,7 +19,7 @@ def clocks():
     return out
 
 K = int(os.environ.get("K", 4))
-configs = [("cta1 fp16", 1, 0), ("cta2 fp16", 2, 0), ("cta1 bf16", 1, 1), ("cta2 bf16", 2, 1)]
+configs = [("cta1 fp16", 1, 0), ("cta1 bf16", 1, 1)]      # (the cta_group::2 variant was removed in round 2)
 if os.environ.get("EPI"):      # sweep the epilogue poll back-off instead: EPI=0,100,400
     configs = [(f"cta1 fp16 epi{e}", 1, 0, int(e)) for e in os.environ["EPI"].split(",")]
 if os.environ.get("CONFIGS"):
@@ -29,7 +29,7 @@ steps = int(os.environ.get("STEPS", 4))
 for rep in range(reps):
     for cfg in configs:
         name, cg, bf = cfg[:3]
-        lib.knnsvc_set_option(b"cta_group", cg); lib.knnsvc_set_option(b"bf16_operands", bf)
+        lib.knnsvc_set_option(b"bf16_operands", bf)
         lib.knnsvc_set_option(b"epi_sleep_ns", cfg[3] if len(cfg) > 3 else 0)
         lib.knnsvc_set_option(b"spin_sleep_ns", int(os.environ.get("SPIN", 0)))
         qp, pp = ops.prepare_rows(q, check=False), ops.prepare_rows(p, check=False)
