@@ -135,6 +135,8 @@ long long knnsvc_launch_count(void);
  * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
  * "query_group" (chains — query tile x segment — per group of the filter's two-level unit order,
  * 0 = default 2 x SM count; a value >= the number of chains gives the flat block-major order),
+ * "refine_min_candidates" (candidates per row above the first threshold from which the decision stage
+ * re-scores in fp32 before the fp64 decision, 0 = default; same results either way),
  * "log_cap" (candidate-log slots per row and pool segment, 0 = default 2048; the tests shrink it to
  * drive rows into the overflow -> exact-kernel path with small fixtures),
  * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static

@@ -37,6 +37,8 @@ int opt_spin_ns() { return g_opt_spin_ns.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_epi_sleep_ns{0};
 int opt_epi_sleep_ns() { return g_opt_epi_sleep_ns.load(std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_refine_min{0};
+int opt_refine_min() { return g_opt_refine_min.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_query_group{0};
 int opt_query_group() { return g_opt_query_group.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_log_cap{0};
@@ -286,6 +288,11 @@ int knnsvc_set_option(const char* name, int value) {
   if (strcmp(name, "block_tiles") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: block_tiles out of range");
     g_opt_block_tiles.store(value, std::memory_order_relaxed);
+    return 0;
+  }
+  if (strcmp(name, "refine_min_candidates") == 0) {
+    KNN_CHECK_ARG(value >= 0 && value <= (1 << 20), -1, "set_option: refine_min_candidates out of range");
+    g_opt_refine_min.store(value, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "query_group") == 0) {

@@ -9,6 +9,7 @@ namespace knnsvc {
 int opt_bf16();
 int opt_filter_flags();   // bit0: L2 prefetch of the next unit's query tile, bit2: static unit schedule (bit1 unused)
 int opt_weight_fit_cluster();   // 1 (default): few long utterances are fitted by a cluster of 8 CTAs each
+int opt_refine_min();      // candidates per row above which the decision stage refines in fp32 first (0 = default)
 int opt_log_cap();       // candidate-log slots per (row, segment); 0 = default
 int opt_query_group();   // chains per group of the filter's two-level unit order (0 = default)
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)

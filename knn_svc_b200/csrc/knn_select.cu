@@ -94,8 +94,9 @@ constexpr int kRefineSparseAvg = 96;     // logged entries per row up to which t
 //           with ~800-1100 it wins (20k x 1M near-duplicate pool, k=4: 14.3 -> 10.9 ms).
 constexpr int kRefineMinAbove = 400;
 constexpr int kStatAbove = 8;            // stats slot (relative to the stats base) of the prep kernel's count
+constexpr int kStatMinAbove = 9;         // stats slot holding the threshold in force (written by the prep launch)
 __device__ __forceinline__ bool refine_mode(const int* stats, int64_t n_query) {
-  return (int64_t)stats[kStatAbove] > (int64_t)kRefineMinAbove * n_query;
+  return (int64_t)stats[kStatAbove] > (int64_t)stats[kStatMinAbove] * n_query;
 }
 void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk) {
   int64_t rows = (int64_t)(64 << 20) / ((int64_t)dim * 4);
@@ -129,8 +130,10 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
     int64_t n_query, int k, int n_seg, int cap, int rf_rows, int rf_nblk, const int* __restrict__ log_idx,
     const int* __restrict__ log_cnt, const float* __restrict__ seg_top, float* __restrict__ row_thr,
     int* __restrict__ blk_off, int64_t* __restrict__ flag_list, int* __restrict__ flag_count, int* __restrict__ stats,
-    const float* __restrict__ log_val, const float* __restrict__ q_err, const float* __restrict__ p_err, int dim_pad) {
+    const float* __restrict__ log_val, const float* __restrict__ q_err, const float* __restrict__ p_err, int dim_pad,
+    int min_above) {
   __shared__ float s_top[RP_WARPS][RP_MAXTOP];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && stats) stats[kStatMinAbove] = min_above;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_top = n_seg * k;
   const float window = 2.0f * filter_eps(q_err, p_err, dim_pad);
@@ -328,6 +331,8 @@ __global__ void __launch_bounds__(256, 3) knn_refine_kernel(
             const int lb = m ? __ffs(m) - 1 : la;
             m &= m - 1;                                  // (no-op when m was already 0)
             const int ca = __shfl_sync(0xffffffffu, col, la), cb = __shfl_sync(0xffffffffu, col, lb);
+            // the two pool norms are fetched NOW (lanes 0 and 1), together with the rows, not after the sums
+            const double pnorm = lane < 2 ? pn[lane == 0 ? ca : cb] : 1.0;
             float da, db;
             if (NV > 0) {
               refine_dot2<(NV > 0 ? NV : 1)>(qv, p + (int64_t)ca * dim, p + (int64_t)cb * dim, lane, da, db);
@@ -347,11 +352,9 @@ __global__ void __launch_bounds__(256, 3) knn_refine_kernel(
                 db += __shfl_xor_sync(0xffffffffu, db, o);
               }
             }
-            if (lane == 0) {
-              // masked column range: distance defined as 1 <=> similarity 0 (ddsp_prematch_dataset.py:1623-1624)
-              rv[e0 + la] = (ca >= m_lo && ca < m_hi) ? 0.f : (float)((double)da / (qnorm * pn[ca]));
-              if (lb != la) rv[e0 + lb] = (cb >= m_lo && cb < m_hi) ? 0.f : (float)((double)db / (qnorm * pn[cb]));
-            }
+            // masked column range: distance defined as 1 <=> similarity 0 (ddsp_prematch_dataset.py:1623-1624)
+            if (lane == 0) rv[e0 + la] = (ca >= m_lo && ca < m_hi) ? 0.f : (float)((double)da / (qnorm * pnorm));
+            if (lane == 1 && lb != la) rv[e0 + lb] = (cb >= m_lo && cb < m_hi) ? 0.f : (float)((double)db / (qnorm * pnorm));
           }
         }
       }
@@ -664,7 +667,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
     knn_refine_prep_kernel<<<(unsigned)grid, RP_WARPS * 32, 0, stream>>>(n_query, k, pl.n_seg, pl.cap, pl.rf_rows,
                                                                        pl.rf_nblk, log_idx, log_cnt, seg_top, row_thr,
                                                                        blk_off, flag_list, flag_count, stats, log_val,
-                                                                       q_err, p_err, dim_pad);
+                                                                       q_err, p_err, dim_pad,
+                                                                       opt_refine_min() > 0 ? opt_refine_min() : kRefineMinAbove);
     KNN_LAUNCH_CHECK();
   }
   // 2. fp32 refine of every candidate above the first threshold, block-major

@@ -247,6 +247,39 @@ def test_matcher_match_post_opt_values(ops):
     assert np.abs(out3.cpu().numpy() - orc.gather_mix(p, top4, None)).max() <= 1e-4 * np.abs(want).max()
 
 
+# ----------------------------------------------------------------------------- dense decision route
+@pytest.mark.parametrize("k", [4, 32])
+def test_refine_route_on_a_near_duplicate_pool(ops, k):
+    """a pool of near-duplicates (every row has ~500 copies within 3e-4 cosine) puts > 400 candidates per
+    row inside the fp16 window: the decision stage takes its refine route (fp32 re-score, block-major), which
+    must return exactly what the exact CUDA-core kernel, the direct route and the oracle return — masked
+    ranges included"""
+    rs = np.random.RandomState(5)
+    base = synth.ar1_frames(48, seed=91)
+    pool = (np.tile(base, (500, 1)) + 0.05 * rs.standard_normal((24000, 1024))).astype(np.float32)
+    q = (np.repeat(synth.ar1_frames(48, seed=91), 6, axis=0)[:270] + 0.05 * rs.standard_normal((270, 1024))).astype(np.float32)
+    qp, pp = ops.prepare_rows(dev(q)), ops.prepare_rows(dev(pool))
+    lo = dev(np.full(270, 1000, np.int64)); hi = dev(np.full(270, 9000, np.int64))
+    de, ie = ops.knn_exact(qp, pp, k)
+    d, i, st = ops.knn_search(qp, pp, k, return_stats=True)
+    dm, im = ops.knn_search(qp, pp, k, mask_lo=lo, mask_hi=hi)
+    assert int(st[2]) > 400 * 270, "fixture: the refine route needs > 400 candidates per row"
+    assert int(st[0]) == 0 and int(st[7]) < int(st[2]) // 4, "the fp32 stage must thin the candidates out"
+    assert torch.equal(i, ie) and torch.equal(d, de)
+    # the direct route (threshold raised out of reach) must return the same bits
+    _set_opt("refine_min_candidates", 1 << 20)
+    try:
+        d2, i2, st2 = ops.knn_search(qp, pp, k, return_stats=True)
+    finally:
+        _set_opt("refine_min_candidates", 0)
+    assert int(st2[7]) == int(st2[2]) and torch.equal(i2, i) and torch.equal(d2, d)
+    outs = {1: (d, i, dm, im)}
+    o_idx, o_val = orc.knn(q, pool, k + 1)
+    check_knn_against_oracle(outs[1][1].cpu().numpy(), outs[1][0].cpu().numpy(), o_idx, o_val, k, min_cover=0.0)
+    om_idx, om_val = orc.knn(q, pool, k + 1, np.full(270, 1000), np.full(270, 9000))
+    check_knn_against_oracle(outs[1][3].cpu().numpy(), outs[1][2].cpu().numpy(), om_idx, om_val, k, min_cover=0.0)
+
+
 # ----------------------------------------------------------------------------- sharded row table (one GPU)
 @pytest.mark.parametrize("dim", [1024, 49])
 def test_gather_mix_sharded_equals_contiguous(ops, dim):

@@ -35,6 +35,8 @@ def make(gen, n, seed, seg):
     return torch.randn((n, 1024), device=dev, generator=g)
 
 
+if os.environ.get("REFINE_MIN"):
+    lib.knnsvc_set_option(b"refine_min_candidates", int(os.environ["REFINE_MIN"]))
 lines = []
 for case in args.cases.split(","):
     gen, T, NP, k = case.split(":"); T, NP, k = int(T), int(NP), int(k)
