@@ -173,3 +173,25 @@ def test_bench_reference_arm_runs_on_host_cores():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("cfg4")
+
+
+def test_cfg5_pairs_are_dealt_completely_and_evenly():
+    """bench.py --workload cfg5: every (utterance, target) pair of the split's shape goes to exactly one rank,
+    ranks get equal frame counts (within one utterance) and at most a few target pools each"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (1, 2, 4, 8):
+        seen, frames = set(), []
+        for rank in range(world):
+            mine, total_pairs, total_frames = bench.cfg5_jobs(world, rank)
+            assert total_pairs == 7038
+            for t, jobs in mine.items():
+                for su, n in jobs:
+                    assert (t, su) not in seen
+                    seen.add((t, su))
+            frames.append(sum(n for jobs in mine.values() for _, n in jobs))
+            assert len(mine) <= 3 or world == 1
+        assert len(seen) == 7038 and sum(frames) == total_frames
+        assert max(frames) - min(frames) <= 2 * 1500
