@@ -6,6 +6,7 @@ an op raises.  Build it with `python -m knn_svc_b200.build`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -75,6 +76,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    # diagnostic switches from the environment: KNNSVC_OPTIONS="concat_cluster=0,refine_min_candidates=800"
+    for item in filter(None, os.environ.get("KNNSVC_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        if lib.knnsvc_set_option(name.strip().encode(), int(value)) != 0:
+            raise ValueError(f"KNNSVC_OPTIONS: {lib.knnsvc_last_error().decode(errors='replace')}")
     _lib = lib
     return lib
 

@@ -47,6 +47,9 @@ int opt_log_cap() { return g_opt_log_cap.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_concat_staged{1};
 int opt_concat_staged() { return g_opt_concat_staged.load(std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_concat_cluster{1};
+int opt_concat_cluster() { return g_opt_concat_cluster.load(std::memory_order_relaxed); }
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -72,6 +75,7 @@ struct KnnWorkspace {
   float* seg_kth;
   float* ref_val;   // refined (fp32) similarity of every log entry, -inf below the first threshold
   float* row_thr;   // first threshold of every row (+inf: the row overflowed its log)
+  int* row_mode;    // decision route of every row (1: fp32 refine first, 0: straight to fp64)
   int* blk_off;     // [slots][rf_nblk + 1] start of every refine block inside the (sorted) log
   int* seg_flag;
   size_t seg_flag_bytes;
@@ -99,6 +103,7 @@ KnnWorkspace carve(void* base, int64_t n_query, int64_t n_pool, int k, const Fil
   w.seg_kth = reinterpret_cast<float*>(take(slots * sizeof(float)));
   w.ref_val = reinterpret_cast<float*>(take(slots * pl.cap * sizeof(float)));
   w.row_thr = reinterpret_cast<float*>(take((size_t)n_query * sizeof(float)));
+  w.row_mode = reinterpret_cast<int*>(take((size_t)n_query * sizeof(int)));
   w.blk_off = reinterpret_cast<int*>(take(slots * (size_t)(pl.rf_nblk + 1) * sizeof(int)));
   w.seg_flag_bytes = filter_flag_count(pl) * sizeof(int);
   w.seg_flag = reinterpret_cast<int*>(take(w.seg_flag_bytes));
@@ -239,7 +244,7 @@ int knnsvc_knn_search_full(const float* q, const void* qh, const double* qn, int
   if (rc) return rc;
   if (timed) KNN_CUDA(cudaEventRecord(g_ev[ev_slot][1], stream));
   rc = launch_knn_rescore(q, qn, n_query, p, pn, n_pool, dim, k, pl, w.log_val, w.log_idx, w.log_cnt, w.seg_top,
-                          w.ref_val, w.row_thr, w.blk_off, index_offset, out_dist, out_dist64, out_idx, w.flag_list,
+                          w.ref_val, w.row_thr, w.row_mode, w.blk_off, index_offset, out_dist, out_dist64, out_idx, w.flag_list,
                           w.counters, w.counters + 1, mask_lo, mask_hi, q_err, p_err, stream);
   if (rc) return rc;
   // rows the error window could not decide: exact brute force, count known only on the device
@@ -274,6 +279,10 @@ int knnsvc_set_option(const char* name, int value) {
   }
   if (strcmp(name, "concat_staged") == 0) {
     g_opt_concat_staged.store(value != 0, std::memory_order_relaxed);
+    return 0;
+  }
+  if (strcmp(name, "concat_cluster") == 0) {
+    g_opt_concat_cluster.store(value != 0, std::memory_order_relaxed);
     return 0;
   }
   if (strcmp(name, "filter_flags") == 0) {

@@ -110,6 +110,46 @@ __device__ __forceinline__ void cs_halve(float (&v)[CS_V], bool upper, int xor_m
   }
 }
 
+// ---- the arithmetic of one step, shared by the one-CTA and the cluster kernel.  Every operation is spelled
+// out (explicit fma / mul / add intrinsics: no contraction left to the compiler), so the two kernels give
+// the same bits for the same sums.
+// fp64 sum of the eight per-slice partial sums p[0], p[stride], .. (slice = 128 feature dimensions: a
+// compute warp of the one-CTA kernel, a CTA of the cluster kernel), as a fixed tree
+__device__ __forceinline__ double cs_tree8(const float* p, int stride) {
+  double v[CS_WARPS];
+#pragma unroll
+  for (int w = 0; w < CS_WARPS; ++w) v[w] = (double)p[w * stride];
+  return __dadd_rn(__dadd_rn(__dadd_rn(v[0], v[4]), __dadd_rn(v[2], v[6])),
+                   __dadd_rn(__dadd_rn(v[1], v[5]), __dadd_rn(v[3], v[7])));
+}
+// cosine distance 1 - a.b/(|a||b|) (lib_ongaku_test.py:162-165) from the dot product and carried reciprocal norms
+__device__ __forceinline__ double cs_cos_dist(double dot, double inv_a, double inv_b) {
+  return __fma_rn(-dot, __dmul_rn(inv_a, inv_b), 1.0);
+}
+// the reference's threshold edits of a concatenation cost (lib_ongaku_test.py:318-335)
+__device__ __forceinline__ double cs_edit(double cc, double base, bool use_f0) {
+  if (use_f0) return (base < 0.08 && cc < __dmul_rn(5.0, base)) ? 0.0 : cc;
+  return cc > base ? __fma_rn(1.5, cc, -base) : cc;
+}
+// lower median of 4 = second smallest (torch.median, lib_ongaku_test.py:337,342)
+__device__ __forceinline__ double cs_median4(double c0, double c1, double c2, double c3) {
+  const double lo01 = fmin(c0, c1), hi01 = fmax(c0, c1);
+  const double lo23 = fmin(c2, c3), hi23 = fmax(c2, c3);
+  return fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+}
+__device__ __forceinline__ double cs_total(double w, double med, double match, bool use_f0, double lcand,
+                                           double lsrc) {
+  const double t = __fma_rn(w, med, match);
+  return use_f0 ? __dadd_rn(t, fabs(__dsub_rn(lcand, lsrc))) : t;
+}
+// one float4 column of a row against itself / another row: (x*x' then z*z') + (y*y' then w*w') as two fma chains
+__device__ __forceinline__ float cs_col_dot(const float4& a, const float4& b) {
+  float2 acc = make_float2(0.f, 0.f);
+  acc = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+  acc = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
+  return acc.x + acc.y;
+}
+
 #ifdef KNNSVC_K5_PROFILE
 __device__ long long g_k5_prof[8];
 #define K5_T(i) do { const long long _t = clock64(); prof[i] += _t - t_last; t_last = _t; } while (0)
@@ -313,20 +353,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
       const double base = mt.base;
       if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
       // cross-warp sums in fp64: lane l owns flat entries l and l + 32 (flat = a * 8 + candidate)
-      double p0[CS_WARPS], p1[CS_WARPS];
-#pragma unroll
-      for (int w = 0; w < CS_WARPS; ++w) {
-        p0[w] = (double)sh.part[w][lane];
-        p1[w] = lane < CS_V - 32 ? (double)sh.part[w][lane + 32] : 0.0;
-      }
-#pragma unroll
-      for (int st = CS_WARPS / 2; st > 0; st >>= 1)
-#pragma unroll
-        for (int w = 0; w < st; ++w) {
-          p0[w] += p0[w + st];
-          p1[w] += p1[w + st];
-        }
-      const double t0 = p0[0], t1 = p1[0];
+      const double t0 = cs_tree8(&sh.part[0][lane], CS_V);
+      const double t1 = cs_tree8(&sh.part[0][lane < CS_V - 32 ? lane + 32 : lane], CS_V);
       double q[CS_ACC];   // lane m < 8: the six sums of candidate m
 #pragma unroll
       for (int a = 0; a < 4; ++a) q[a] = __shfl_sync(0xffffffffu, t0, a * CS_C + (lane & 7));
@@ -342,28 +370,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
         const double lcand = lane < CS_K ? mt.lf0_idx[lane] : mt.lf0_spec[slot];
         my_n2 = q[0];
         my_inv = rsqrt(my_n2);
-        // cosine distance 1 - x.c/(|x||c|) (lib_ongaku_test.py:162-165) with carried reciprocal norms
-        const double match = 1.0 - q[1] * (mt.inv_src * my_inv);
+        const double match = cs_cos_dist(q[1], mt.inv_src, my_inv);
         double cc[CS_K];
 #pragma unroll
-        for (int j = 0; j < CS_K; ++j) cc[j] = 1.0 - q[2 + j] * (sh.prev_inv[j] * my_inv);
-        if (use_f0) {
-          if (base < 0.08) {
-#pragma unroll
-            for (int j = 0; j < CS_K; ++j)
-              if (cc[j] < 5.0 * base) cc[j] = 0.0;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CS_K; ++j)
-            if (cc[j] > base) cc[j] = 1.5 * cc[j] - base;
-        }
-        // lower median of 4 = second smallest (torch.median, lib_ongaku_test.py:337,342)
-        const double lo01 = fmin(cc[0], cc[1]), hi01 = fmax(cc[0], cc[1]);
-        const double lo23 = fmin(cc[2], cc[3]), hi23 = fmax(cc[2], cc[3]);
-        const double med = fmin(fmax(lo01, lo23), fmin(hi01, hi23));
-        total = w_sticky * med + match;
-        if (use_f0) total += fabs(lcand - mt.lsrc);
+        for (int j = 0; j < CS_K; ++j) cc[j] = cs_edit(cs_cos_dist(q[2 + j], sh.prev_inv[j], my_inv), base, use_f0);
+        total = cs_total(w_sticky, cs_median4(cc[0], cc[1], cc[2], cc[3]), match, use_f0, lcand, mt.lsrc);
       }
       int rank = 0;
 #pragma unroll
@@ -395,6 +406,305 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster variant: ONE UTTERANCE PER CLUSTER OF 8 CTAs, each CTA owning 128 of the feature dimensions.
+//
+// Measured on the one-CTA kernel (profiles/r2_k5_chain_experiment.txt): a step is bound by moving 13 rows =
+// 53 KB into one SM (~2900-3500 cycles) and by one warp finishing all eight candidates (~1200 cycles).
+// A batch of utterances hides neither — it does not have to, 148 CTAs run side by side — but a single long
+// utterance (BASELINE cfg 2: 3001 frames) waits for every step.  Here
+//   * CTA r fetches only columns [128 r, 128 r + 128) of the 13 rows (6.5 KB per step, TMA bulk copies, the
+//     same three-generation speculative ring as above);
+//   * compute warp m scores CANDIDATE m on the CTA's slice (one float4 column per lane, the six sums
+//     c.c, src.c, prev_j.c, a 5-level warp tree) and sends the six partial sums to warp m of all 8 CTAs with
+//     st.async (remote shared-memory stores that complete a transaction count on the receiver's mbarrier:
+//     no cluster barrier inside the loop);
+//   * warp m of EVERY CTA then adds the 8 slices in fp64 and finishes candidate m's cost (4 lanes = the 4
+//     previous selections, median over shuffles); the producer warp ranks the 8 costs, publishes the
+//     selection to its CTA and issues the next generation.  All 8 CTAs take the same decision from the
+//     same numbers, so nothing else crosses the cluster; rank 0 writes the output.
+// Arithmetic: slice r is exactly what compute warp r of the one-CTA kernel sums, the warp tree has the same
+// levels (16, 8, 4, 2, 1), the cross-slice tree and the cost formulas are the shared functions above —
+// the two kernels return the same bits.
+constexpr int CL_C = 8;                          // CTAs per cluster (portable maximum)
+constexpr int CL_SLICE = CS_MAX_DIM / CL_C;      // feature columns per CTA
+static_assert(CL_C == CS_WARPS, "slice r of the cluster kernel = compute warp r of the one-CTA kernel");
+static_assert(CL_SLICE == 128, "one float4 column per lane");
+
+struct ClShared {
+  float rows[CS_GENS][CS_ROWS][CL_SLICE];
+  float xch[2][CS_C][CL_C][8];     // [step parity][candidate][source CTA]{c.c, src.c, prev0.c, -, prev1.c, prev2.c, prev3.c, -}
+  CsMeta meta[CS_GENS];
+  double cost[CS_C];               // total cost of each candidate of the current step
+  double cinv[CS_C];               // 1/|candidate row|
+  double prev_inv[CS_K];           // 1/|row| of the previous selections
+  unsigned long long full_bar[CS_GENS];
+  unsigned long long xbar[2][CS_C];
+  unsigned long long cbar, sel_bar;
+  int sp[2][CS_K];                 // candidate slot (0..7) of each selection, by step parity
+  int prow[CS_K];                  // row (0..11) of the previous generation holding each selected row
+};
+
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void cl_st_async4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   raddr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+               "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait for a phase completed by peers' st.async (their complete_tx is a release at cluster scope)
+__device__ __forceinline__ void cl_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cl_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) concat_cost_cluster_kernel(
+    const int64_t* __restrict__ idx, const float* __restrict__ src, const __grid_constant__ RowTable pool,
+    int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
+    const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
+    int64_t* __restrict__ out_idx) {
+  __shared__ __align__(128) ClShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int utt = blockIdx.x / CL_C;
+  const int64_t f_begin = utt_offsets[utt], f_end = utt_offsets[utt + 1];
+  const int64_t n = f_end - f_begin;
+  if (n <= 0) return;                                  // (the same decision in all CTAs of the cluster)
+  const bool use_f0 = src_f0 != nullptr;
+  const int64_t n_pool = pool.lo[pool.n];
+  const int s_lo = (int)rank * CL_SLICE;               // first feature column of this CTA
+  const int slice_len = dim - s_lo < 0 ? 0 : (dim - s_lo > CL_SLICE ? CL_SLICE : dim - s_lo);
+  const uint32_t slice_bytes = (uint32_t)slice_len * 4u;
+
+  if (tid == 0) {
+    for (int g = 0; g < CS_GENS; ++g) cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), 1);
+    for (int p = 0; p < 2; ++p)
+      for (int m = 0; m < CS_C; ++m) cs_mbar_init(cs_smem_u32(&sh.xbar[p][m]), 1);
+    cs_mbar_init(cs_smem_u32(&sh.cbar), CS_C);
+    cs_mbar_init(cs_smem_u32(&sh.sel_bar), 1);
+    for (int j = 0; j < CS_K; ++j) {
+      sh.sp[0][j] = j;      // "selection 0" = idx[0] itself, sitting in slots 0..3 of generation 0
+      sh.sp[1][j] = j;
+      sh.prow[j] = j;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  cl_cluster_sync();      // every CTA's barriers are live before a peer sends to them
+
+  if (warp == CS_WARPS) {
+    // ============================ producer / decision warp ============================
+    if (lane < CS_K) {      // generation 0: this CTA's slice of the four rows of idx[0]
+      const int64_t id = idx[f_begin * CS_K + lane];
+      sh.meta[0].idx_g[lane] = id;
+      if (slice_bytes)
+        cs_bulk_row(cs_smem_u32(&sh.rows[0][lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes,
+                    cs_smem_u32(&sh.full_bar[0]));
+    }
+    __syncwarp();
+    if (lane == 0) cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[0]), CS_K * slice_bytes);
+    // what the frame number alone addresses is fetched one generation ahead into registers
+    int64_t next_idx = 0;                       // lanes 8..11: idx[t]
+    double next_base = 0.0, next_n2 = 1.0;      // lane 12: per-frame scalars of the query row
+    float next_f0 = 0.f;
+    if (n > 1) {
+      if (lane >= CS_C && lane < CS_C + CS_K) next_idx = idx[(f_begin + 1) * CS_K + (lane - CS_C)];
+      if (lane == CS_C + CS_K) {
+        next_base = base_all[f_begin + 1];
+        next_n2 = src_n2[f_begin + 1];
+        if (use_f0) next_f0 = __ldg(src_f0 + f_begin + 1);
+      }
+    }
+    // generation t >= 1: rows of idx[t], the query row t and the eight speculative rows cand[t-1] + 1
+    // (c_prev = cand[t-1][lane] in lanes 0..7)
+    auto issue_gen = [&](int64_t t, int64_t c_prev) {
+      const int g = (int)(t % CS_GENS);
+      const uint32_t bar = cs_smem_u32(&sh.full_bar[g]);
+      int64_t id = -1;
+      if (lane < CS_C) {
+        id = c_prev + 1 >= n_pool ? n_pool - 1 : c_prev + 1;   // lib_ongaku_test.py:294-295
+        sh.meta[g].spec_g[lane] = id;
+        if (slice_bytes)
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
+      } else if (lane < CS_C + CS_K) {
+        id = next_idx;
+        sh.meta[g].idx_g[lane - CS_C] = id;
+        if (slice_bytes)
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][lane - CS_C][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
+        if (t + 1 < n) next_idx = idx[(f_begin + t + 1) * CS_K + (lane - CS_C)];
+      } else if (lane == CS_C + CS_K) {
+        if (slice_bytes)
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_ROWS - 1][0]), src + (f_begin + t) * dim + s_lo, slice_bytes, bar);
+        sh.meta[g].base = next_base;
+        sh.meta[g].inv_src = rsqrt(next_n2);
+        sh.meta[g].lsrc = use_f0 ? log2((double)next_f0 + 1e-5) : 0.0;
+        if (t + 1 < n) {
+          next_base = base_all[f_begin + t + 1];
+          next_n2 = src_n2[f_begin + t + 1];
+          if (use_f0) next_f0 = __ldg(src_f0 + f_begin + t + 1);
+        }
+      }
+      if (use_f0 && lane < CS_C + CS_K) {
+        const double lf = log2((double)__ldg(pool_f0 + id) + 1e-5);
+        if (lane < CS_C) sh.meta[g].lf0_spec[lane] = lf;
+        else sh.meta[g].lf0_idx[lane - CS_C] = lf;
+      }
+      __syncwarp();
+      if (lane == 0) cs_mbar_expect_tx(bar, CS_ROWS * slice_bytes);   // release: publishes meta[g] too
+    };
+    int64_t c_cur = lane < CS_C ? idx[f_begin * CS_K + (lane & 3)] : 0;   // "cand[0]": idx[0] twice over
+    if (n > 1) issue_gen(1, c_cur);
+    for (int64_t s = 1; s < n; ++s) {
+      const int g = (int)(s % CS_GENS);
+      // candidate `lane` of step s: known since selection s-1
+      int my_row = lane;
+      if (lane < CS_K) {
+        c_cur = sh.meta[g].idx_g[lane];
+      } else if (lane < CS_C) {
+        const int slot = sh.sp[(s - 1) & 1][lane - CS_K];
+        c_cur = sh.meta[g].spec_g[slot];
+        my_row = CS_K + slot;
+      }
+      if (s + 1 < n) issue_gen(s + 1, c_cur);           // one whole step ahead of its use
+      cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 1) & 1));   // the eight costs of step s
+      const double total = lane < CS_C ? sh.cost[lane] : INFINITY;
+      int rk = 0;
+#pragma unroll
+      for (int j = 0; j < CS_C; ++j) {
+        const double tj = __shfl_sync(0xffffffffu, total, j);
+        rk += (tj < total) || (tj == total && j < lane);
+      }
+      if (lane < CS_C && rk < CS_K) {
+        if (rank == 0) out_idx[(f_begin + s) * CS_K + rk] = c_cur;
+        sh.sp[s & 1][rk] = lane;
+        sh.prow[rk] = my_row;
+        sh.prev_inv[rk] = sh.cinv[lane];
+      }
+      __syncwarp();
+      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.sel_bar));   // release: selection s is published
+    }
+  } else {
+    // ============================ compute warps: warp m scores candidate m ============================
+    const int m = warp;
+    cs_mbar_wait(cs_smem_u32(&sh.full_bar[0]), 0);
+    if (warp < CS_K) {  // |row|^2 of the four initial selections (whole rows, from global memory: once)
+      const int64_t id0 = idx[f_begin * CS_K + warp];
+      const float4* r4 = reinterpret_cast<const float4*>(table_row(pool, id0, dim));
+      const int n4 = dim / 4;
+      double acc = 0.0;
+      for (int c = lane; c < n4; c += 32) {
+        const float4 v = __ldg(r4 + c);
+        float t = v.x * v.x;
+        t = fmaf(v.y, v.y, t);
+        t = fmaf(v.z, v.z, t);
+        t = fmaf(v.w, v.w, t);
+        acc += (double)t;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) sh.prev_inv[warp] = rsqrt(acc);
+      if (rank == 0 && lane == 0) out_idx[f_begin * CS_K + warp] = id0;
+    }
+    cs_compute_sync();
+    const bool has_col = 4 * lane < slice_len;
+    const int j = lane & 3;
+    double w_sticky = (double)concat_weight;
+    for (int64_t s = 1; s < n; ++s) {
+      const int g = (int)(s % CS_GENS), gp = (int)((s - 1) % CS_GENS), par = (int)(s & 1);
+      // generation s was issued a whole step ago; what does not depend on selection s-1 is read first
+      cs_mbar_wait(cs_smem_u32(&sh.full_bar[g]), (uint32_t)((s / CS_GENS) & 1));
+      const uint32_t xb = cs_smem_u32(&sh.xbar[par][m]);
+      if (lane == 0) cs_mbar_expect_tx(xb, CL_C * 32u);
+      float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = sv;
+      if (has_col) {
+        sv = *reinterpret_cast<const float4*>(&sh.rows[g][CS_ROWS - 1][4 * lane]);
+        if (m < CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][m][4 * lane]);
+      }
+      if (s >= 2) cs_mbar_wait(cs_smem_u32(&sh.sel_bar), (uint32_t)((s - 2) & 1));   // selection s-1
+      const int slot = m < CS_K ? 0 : sh.sp[(s - 1) & 1][m - CS_K];
+      int pr[CS_K];
+#pragma unroll
+      for (int jj = 0; jj < CS_K; ++jj) pr[jj] = sh.prow[jj];
+      const double pinv = sh.prev_inv[j];
+      // the six partial sums of candidate m over this CTA's slice: v[0] c.c, v[1] src.c, v[2 + jj] prev_jj.c
+      float v[CS_ACC];
+#pragma unroll
+      for (int a = 0; a < CS_ACC; ++a) v[a] = 0.f;
+      if (has_col) {
+        if (m >= CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][CS_K + slot][4 * lane]);
+        v[0] = cs_col_dot(cv, cv);
+        v[1] = cs_col_dot(sv, cv);
+#pragma unroll
+        for (int jj = 0; jj < CS_K; ++jj)
+          v[2 + jj] = cs_col_dot(*reinterpret_cast<const float4*>(&sh.rows[gp][pr[jj]][4 * lane]), cv);
+      }
+      // warp tree, levels 16, 8, 4, 2, 1 as in the one-CTA kernel: lanes >= 16 end up with sums 3..5
+      const bool upper = (lane & 16) != 0;
+      float r[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float keep = upper ? v[k + 3] : v[k];
+        const float send = upper ? v[k] : v[k + 3];
+        r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+      // to warp m of every CTA of the cluster (this one included)
+      if ((lane & 15) < CL_C) {
+        const uint32_t dst = (uint32_t)(lane & 7);
+        const uint32_t la = cs_smem_u32(&sh.xch[par][m][rank][(lane >> 4) * 4]);
+        cl_st_async4(cl_mapa(la, dst), r[0], r[1], r[2], 0.f, cl_mapa(xb, dst));
+      }
+      cl_mbar_wait_cluster(xb, (uint32_t)(((s - 1) >> 1) & 1));
+      // candidate m's cost: lanes j = 0..3 take one previous selection each (the other lanes repeat them)
+      const CsMeta& mt = sh.meta[g];
+      const double base = mt.base;
+      if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
+      const float* x = &sh.xch[par][m][0][0];
+      const double n2 = cs_tree8(x + 0, 8);
+      const double d_src = cs_tree8(x + 1, 8);
+      const double d_prev = cs_tree8(x + (j == 0 ? 2 : 3 + j), 8);
+      const double my_inv = rsqrt(n2);
+      const double match = cs_cos_dist(d_src, mt.inv_src, my_inv);
+      const double cc = cs_edit(cs_cos_dist(d_prev, pinv, my_inv), base, use_f0);
+      const double c0 = __shfl_sync(0xffffffffu, cc, 0), c1 = __shfl_sync(0xffffffffu, cc, 1);
+      const double c2 = __shfl_sync(0xffffffffu, cc, 2), c3 = __shfl_sync(0xffffffffu, cc, 3);
+      const double lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
+      const double total = cs_total(w_sticky, cs_median4(c0, c1, c2, c3), match, use_f0, lcand, mt.lsrc);
+      if (lane == 0) {
+        sh.cost[m] = total;
+        sh.cinv[m] = my_inv;
+        cl_mbar_arrive(cs_smem_u32(&sh.cbar));      // release
+      }
+    }
+  }
+  __syncwarp();
+  cl_cluster_sync();      // nobody leaves while a peer could still address its shared memory
+}
+
 size_t concat_staged_smem_bytes(int dim) {
   return (size_t)CS_GENS * CS_ROWS * dim * sizeof(float) + sizeof(CsShared);
 }
@@ -403,6 +713,43 @@ bool concat_staged_eligible(const float* src, const RowTable& pool, int dim) {
   bool ok = dim >= 4 && dim % 4 == 0 && dim <= CS_MAX_DIM && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   for (int s = 0; s < pool.n; ++s) ok = ok && (reinterpret_cast<uintptr_t>(pool.base[s]) & 15) == 0;
   return ok;
+}
+
+// The cluster kernel is for a few long utterances: every utterance needs a cluster of 8 SMs of its own,
+// resident at once (a second wave would wait for a whole utterance).
+bool concat_cluster_fits(int n_utt) {
+  static PerDevice cache;           // per device: 0 = not asked yet, else 1 + clusters the device hosts at once
+  std::atomic<int>* slot = cache.slot();
+  int n_clusters = slot ? slot->load(std::memory_order_relaxed) - 1 : -1;
+  if (n_clusters < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL_C);
+    cfg.blockDim = dim3(CS_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL_C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, concat_cost_cluster_kernel, &cfg);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    n_clusters = e == cudaSuccess ? nc : 0;
+    if (slot) slot->store(n_clusters + 1, std::memory_order_relaxed);
+  }
+  return n_utt >= 1 && n_utt <= n_clusters;
+}
+
+int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTable& pool, int dim,
+                               const float* src_f0, const float* pool_f0, float concat_weight,
+                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
+                               int64_t* out_idx, cudaStream_t stream) {
+  concat_cost_cluster_kernel<<<n_utt * CL_C, CS_THREADS, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0,
+                                                                      concat_weight, utt_offsets_dev, base, n2, out_idx);
+  KNN_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_concat_cost_staged(const int64_t* idx, const float* src, const RowTable& pool, int dim,

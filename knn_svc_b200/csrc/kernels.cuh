@@ -14,6 +14,7 @@ int opt_log_cap();       // candidate-log slots per (row, segment); 0 = default
 int opt_query_group();   // chains per group of the filter's two-level unit order (0 = default)
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
+int opt_concat_cluster();  // 1 (default): a few long utterances get a cluster of 8 CTAs each (dimension split)
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
 int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
 
@@ -49,7 +50,7 @@ constexpr int kFlagCap = 1024;  // rows the in-call exact fallback can absorb
 int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, float* ref_val, float* row_thr,
-                       int* blk_off, int64_t index_offset, float* out_dist, double* out_dist64, int64_t* out_idx,
+                       int* row_mode, int* blk_off, int64_t index_offset, float* out_dist, double* out_dist64, int64_t* out_idx,
                        int64_t* flag_list, int* flag_count, int* stats, const int64_t* mask_lo, const int64_t* mask_hi,
                        const float* q_err, const float* p_err, cudaStream_t stream);
 int launch_merge_topk(const float* gd, const int64_t* gi, int n_shards, int64_t n_query, int k, float* out_dist,
@@ -106,6 +107,12 @@ int launch_concat_cost_staged(const int64_t* idx, const float* src, const RowTab
                               const float* src_f0, const float* pool_f0, float concat_weight,
                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                               int64_t* out_idx, cudaStream_t stream);
+
+bool concat_cluster_fits(int n_utt);   // true: every utterance gets a resident cluster of 8 CTAs on this device
+int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTable& pool, int dim,
+                               const float* src_f0, const float* pool_f0, float concat_weight,
+                               const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
+                               int64_t* out_idx, cudaStream_t stream);
 
 // ---- weight_fit.cu
 size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt);

@@ -82,22 +82,22 @@ __device__ __forceinline__ void rs_dot2(const float* __restrict__ pa, const floa
 // Refine blocks: rf_rows pool rows each (64 MB of fp32 rows at 1024 dims: half of L2), at most
 // kRefineMaxBlocks of them (the per-(row, segment) offset table has rf_nblk + 1 entries).
 constexpr int kRefineMaxBlocks = 1024;
-constexpr int kRefineSparseAvg = 96;     // logged entries per row up to which the refine walks the logs row-major
-// Mode of the decision stage, chosen ON THE DEVICE from what the prep kernel counted:
-//   refine  more than kRefineMinAbove candidates per row above the first (fp16-window) threshold — dense
-//           pools of near-duplicates: they are first re-scored in fp32, block-major (knn_refine), and only
-//           the few inside the refined window are scored in fp64;
-//   direct  otherwise: the candidates above the first threshold go straight to the fp64 scoring, one CTA per
-//           row (adjacent rows run side by side on an SM and share their candidates through L1).  Measured
-//           (profiles/r2_dense_search_*.jsonl): with ~30-150 candidates per row the extra pass over the log
-//           costs more than the fp64 arithmetic it saves (100k x 30k, k=32: 5.5 ms direct, 9.2 ms refined),
-//           with ~800-1100 it wins (20k x 1M near-duplicate pool, k=4: 14.3 -> 10.9 ms).
+// Route of the decision stage, chosen ON THE DEVICE, PER QUERY ROW, from what the prep kernel counts:
+//   refine  more than kRefineMinAbove candidates above the row's first (fp16-window) threshold — pools of
+//           near-duplicates: they are first re-scored in fp32, block-major (knn_refine), and only the few
+//           inside the refined window are scored in fp64;
+//   direct  otherwise: the candidates above the first threshold go straight to the fp64 scoring — by one
+//           warp when there are at most 32 of them, else by one CTA per row (adjacent rows run side by side
+//           on an SM and share their candidates through L1).  Measured (profiles/r2_dense_search_*.jsonl):
+//           with ~30-150 candidates per row the extra pass over the log costs more than the fp64
+//           arithmetic it saves (100k x 30k, k=32: 5.5 ms direct, 9.2 ms refined), with ~800-1100 it wins
+//           (20k x 1M near-duplicate pool, k=4: 14.3 -> 9.5 ms).
 constexpr int kRefineMinAbove = 400;
-constexpr int kStatAbove = 8;            // stats slot (relative to the stats base) of the prep kernel's count
-constexpr int kStatMinAbove = 9;         // stats slot holding the threshold in force (written by the prep launch)
-__device__ __forceinline__ bool refine_mode(const int* stats, int64_t n_query) {
-  return (int64_t)stats[kStatAbove] > (int64_t)stats[kStatMinAbove] * n_query;
-}
+ // per-row route codes (row_mode)
+constexpr int kRouteDirectCta = 0;       // > 32 candidates above the first threshold, scored in fp64 by one CTA
+constexpr int kRouteRefine = 1;          // fp32 re-score first
+constexpr int kRouteDirectWarp = 2;      // <= 32 candidates above the first threshold, scored in fp64 by one warp
+constexpr int kStatAbove = 8;            // stats slot (relative to the stats base): number of rows on the refine route
 void plan_refine(int64_t n_query, int64_t n_pool, int dim, int* rf_rows, int* rf_nblk) {
   int64_t rows = (int64_t)(64 << 20) / ((int64_t)dim * 4);
   rows = rows < 256 ? 256 : rows / 256 * 256;
@@ -131,13 +131,12 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
     const int* __restrict__ log_cnt, const float* __restrict__ seg_top, float* __restrict__ row_thr,
     int* __restrict__ blk_off, int64_t* __restrict__ flag_list, int* __restrict__ flag_count, int* __restrict__ stats,
     const float* __restrict__ log_val, const float* __restrict__ q_err, const float* __restrict__ p_err, int dim_pad,
-    int min_above) {
+    int min_above, int* __restrict__ row_mode) {
   __shared__ float s_top[RP_WARPS][RP_MAXTOP];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && stats) stats[kStatMinAbove] = min_above;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_top = n_seg * k;
   const float window = 2.0f * filter_eps(q_err, p_err, dim_pad);
-  int logged = 0, above = 0;
+  int logged = 0, n_refine = 0;
   for (int64_t row = (int64_t)blockIdx.x * RP_WARPS + warp; row < n_query; row += (int64_t)gridDim.x * RP_WARPS) {
     __syncwarp();
     for (int e = lane; e < n_top; e += 32) s_top[warp][e] = seg_top[row * n_top + e];
@@ -168,23 +167,38 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
         flag_list[atomicAdd(flag_count, 1)] = row;
         if (stats) atomicAdd(stats + 0, 1);
         row_thr[row] = INFINITY;
+        row_mode[row] = kRouteDirectCta;
       }
       continue;
     }
-    if (lane == 0) row_thr[row] = thr;
+    // candidates above the first threshold -> the row's route
+    int above = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t slot = row * n_seg + s;
+      const int c = log_cnt[slot];
+      const float* lvp = log_val + slot * cap;
+      for (int e = lane; e < c; e += 32) above += lvp[e] >= thr ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    const bool refine = above > min_above;
+    if (lane == 0) {
+      row_thr[row] = thr;
+      row_mode[row] = refine ? kRouteRefine : (above <= 32 ? kRouteDirectWarp : kRouteDirectCta);
+    }
+    if (!refine) continue;              // direct route: no block offsets needed
+    ++n_refine;
     // block offsets of every (row, segment) log: off[b] = first entry whose column lies in block >= b
     for (int s = 0; s < n_seg; ++s) {
       const int64_t slot = row * n_seg + s;
       const int c = log_cnt[slot];
       const int* li = log_idx + slot * cap;
-      const float* lvp = log_val + slot * cap;
       // table layout [block][slot]: the refine kernel reads one block's offsets of 32 consecutive rows at once
       const int64_t n_slots = n_query * n_seg;
       int* off = blk_off + slot;
       for (int e0 = 0; e0 < c; e0 += 32) {
         const int e = e0 + lane;
         const int b = e < c ? li[e] / rf_rows : 0;
-        above += (e < c && lvp[e] >= thr) ? 1 : 0;
         int pb = __shfl_up_sync(0xffffffffu, b, 1);
         if (lane == 0) pb = e0 > 0 ? li[e0 - 1] / rf_rows : -1;
         if (e < c)
@@ -197,9 +211,7 @@ __global__ void __launch_bounds__(RP_WARPS * 32) knn_refine_prep_kernel(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) logged += __shfl_xor_sync(0xffffffffu, logged, o);
   if (lane == 0 && stats && logged) atomicAdd(stats + 1, logged);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
-  if (lane == 0 && stats && above) atomicAdd(stats + kStatAbove, above);
+  if (lane == 0 && stats && n_refine) atomicAdd(stats + kStatAbove, n_refine);
 }
 
 // fp32 dot products of TWO pool rows with the query row held in registers (NV float4 per lane,
@@ -245,39 +257,30 @@ template <int NV>
 __global__ void __launch_bounds__(256, 3) knn_refine_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int dim, int n_seg, int cap, int rf_nblk, const float* __restrict__ log_val,
-    const int* __restrict__ log_idx, const int* __restrict__ log_cnt, const int* __restrict__ blk_off,
+    const int* __restrict__ log_idx, const int* __restrict__ row_mode, const int* __restrict__ blk_off,
     const float* __restrict__ row_thr, float* __restrict__ ref_val, int* __restrict__ stats,
-    const int* __restrict__ total_logged, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
+    const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t n_groups = ceil_div64(n_query, 32);
-  // Sparse logs (i.i.d.-like data: a few dozen entries per row, a handful above the threshold) gain
-  // nothing from the block-major order — there is no reuse to be had — and would pay for visiting
-  // every (block, group) unit: they are walked row-major, one unit per 32-row group.  The prep kernel
-  // has counted the log entries; the choice is made here, on the device.
-  if (!refine_mode(stats, n_query)) return;
-  const bool sparse = (int64_t)*total_logged <= (int64_t)kRefineSparseAvg * n_query;
-  const int nblk_eff = sparse ? 1 : rf_nblk;
-  const int64_t n_units = n_groups * nblk_eff;
+  if (stats[kStatAbove] == 0) return;      // no row of this search is on the refine route
+  const int64_t n_units = n_groups * rf_nblk;
   int scored = 0;
   for (int64_t u = warp; u < n_units; u += n_warps) {
     const int b = (int)(u / n_groups);
     const int64_t g = u - (int64_t)b * n_groups;
     const int64_t my_row = g * 32 + lane;
     const float my_thr = my_row < n_query ? row_thr[my_row] : INFINITY;
+    const bool my_mode = my_row < n_query && row_mode[my_row] == kRouteRefine;
+    if (!__any_sync(0xffffffffu, my_mode)) continue;
     for (int s = 0; s < n_seg; ++s) {
       int o0 = 0, o1 = 0;
-      if (my_row < n_query && my_thr < INFINITY) {
-        if (sparse) {
-          o1 = log_cnt[my_row * n_seg + s];
-          o1 = o1 > cap ? cap : o1;
-        } else {
-          const int64_t n_slots = n_query * n_seg;
-          const int* off = blk_off + (int64_t)b * n_slots + (my_row * n_seg + s);
-          o0 = off[0];
-          o1 = off[n_slots];
-        }
+      if (my_row < n_query && my_mode) {
+        const int64_t n_slots = n_query * n_seg;
+        const int* off = blk_off + (int64_t)b * n_slots + (my_row * n_seg + s);
+        o0 = off[0];
+        o1 = off[n_slots];
       }
       // lane-parallel pre-check for rows with a handful of entries (sparse data logs ~1 entry per row
       // and block, few of which pass): their entries below the first threshold are settled here and
@@ -367,13 +370,15 @@ __global__ void __launch_bounds__(256, 3) knn_refine_kernel(
 
 
 // Rows with at most 32 candidates above the first threshold (all of sparse data at small k) are decided
-// by ONE WARP each — candidates in registers, one per lane: the k-th largest refined similarity by
-// rank counting over shuffles, fp64 scores of the survivors (same rs_dot2), final (dist, index) rank.
+// by ONE WARP each — candidates in registers, one per lane.  Refine-route rows: the k-th largest refined
+// similarity by rank counting over shuffles, then fp64 scores of the survivors; direct-route rows: fp64
+// scores of all of them (same rs_dot2); final (dist, index) rank.
 // Rows it decides are marked (row_thr = +inf) and skipped by the CTA-per-row kernel that follows.
 __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int dim, int k, int n_seg, int cap, const float* __restrict__ ref_val,
-    const int* __restrict__ log_idx, const int* __restrict__ log_cnt, float* __restrict__ row_thr, float refine_window,
+    const float* __restrict__ log_val, const int* __restrict__ row_mode, const int* __restrict__ log_idx,
+    const int* __restrict__ log_cnt, float* __restrict__ row_thr, float refine_window,
     int64_t index_offset, float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
     int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
   const int lane = threadIdx.x & 31;
@@ -381,10 +386,17 @@ __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
-  int n_scored = 0;
-  if (!refine_mode(stats, n_query)) return;
+  int n_scored = 0, n_direct = 0;
   for (int64_t row = warp; row < n_query; row += n_warps) {
-    if (!(row_thr[row] < INFINITY)) continue;          // log overflow: the exact kernel decides (warp-uniform)
+    const float thr0 = row_thr[row];
+    if (!(thr0 < INFINITY)) continue;                  // log overflow: the exact kernel decides (warp-uniform)
+    const int route = row_mode[row];                   // warp-uniform
+    if (route == kRouteDirectCta) continue;            // known to have more than 32 candidates
+    const bool direct = route != kRouteRefine;
+    // direct route: the approximate similarities against the first threshold; refine route: the refined
+    // values (-inf below the first threshold)
+    const float* __restrict__ vals = direct ? log_val : ref_val;
+    const float cut = direct ? thr0 : -INFINITY;
     // gather the candidates above the first threshold, one per lane
     float myv = -INFINITY;
     int mycol = -1, n_valid = 0;
@@ -395,8 +407,8 @@ __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
       c = c > cap ? cap : c;
       for (int e0 = 0; e0 < c; e0 += 32) {
         const int e = e0 + lane;
-        const float v = e < c ? __ldg(ref_val + slot * cap + e) : -INFINITY;
-        const unsigned m = __ballot_sync(0xffffffffu, v > -INFINITY);
+        const float v = e < c ? __ldg(vals + slot * cap + e) : -INFINITY;
+        const unsigned m = __ballot_sync(0xffffffffu, direct ? (e < c && v >= cut) : v > -INFINITY);
         if (!m) continue;
         const int add = __popc(m);
         if (n_valid + add > 32) {
@@ -425,10 +437,11 @@ __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
       rnk += (j < n_valid) && ((vj > myv) || (vj == myv && j < lane));
     }
     const unsigned kth = __ballot_sync(0xffffffffu, lane < n_valid && rnk == k - 1);
-    const float tau1 = kth ? __shfl_sync(0xffffffffu, myv, __ffs(kth) - 1) : -INFINITY;
-    const bool surv = lane < n_valid && myv >= tau1 - refine_window;
+    const float tau1 = (kth && !direct) ? __shfl_sync(0xffffffffu, myv, __ffs(kth) - 1) : -INFINITY;
+    const bool surv = lane < n_valid && (direct || myv >= tau1 - refine_window);
     unsigned sm = __ballot_sync(0xffffffffu, surv);
     n_scored += __popc(sm);
+    if (direct) n_direct += __popc(sm);
     // fp64 scores of the survivors, two per pass
     const float* qrow = q + row * dim;
     const double qnorm = qn[row];
@@ -464,9 +477,9 @@ __global__ void __launch_bounds__(256) knn_rescore_small_kernel(
     __syncwarp();
     if (lane == 0) row_thr[row] = INFINITY;             // decided
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_scored += __shfl_xor_sync(0xffffffffu, n_scored, o);
-  if (lane == 0 && stats && n_scored) atomicAdd(stats + 6, n_scored / 1);
+  // (both counts are warp-uniform: every lane holds its warp's total)
+  if (lane == 0 && stats && n_scored) atomicAdd(stats + 6, n_scored);
+  if (lane == 0 && stats && n_direct) atomicAdd(stats + 2, n_direct);
 }
 
 // order-preserving map float -> unsigned (larger float <=> larger key) and back
@@ -482,12 +495,10 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
     const float* __restrict__ q, const double* __restrict__ qn, int64_t n_query, const float* __restrict__ p,
     const double* __restrict__ pn, int64_t n_pool, int dim, int k, int n_seg, int cap,
     const float* __restrict__ ref_val_in, const float* __restrict__ log_val, const int* __restrict__ log_idx,
-    const int* __restrict__ log_cnt, const float* __restrict__ row_thr, float refine_window, int64_t index_offset,
-    float* __restrict__ out_dist, double* __restrict__ out_dist64, int64_t* __restrict__ out_idx,
-    int* __restrict__ stats, const int64_t* __restrict__ mask_lo, const int64_t* __restrict__ mask_hi) {
-  // direct mode: the candidates above the FIRST threshold are scored in fp64 right away (no refined values exist)
-  const bool direct = !refine_mode(stats, n_query);
-  const float* __restrict__ ref_val = direct ? log_val : ref_val_in;
+    const int* __restrict__ log_cnt, const float* __restrict__ row_thr, const int* __restrict__ row_mode,
+    float refine_window, int64_t index_offset, float* __restrict__ out_dist, double* __restrict__ out_dist64,
+    int64_t* __restrict__ out_idx, int* __restrict__ stats, const int64_t* __restrict__ mask_lo,
+    const int64_t* __restrict__ mask_hi) {
   __shared__ double s_dist[RS_LIST];             // exact distances of the survivors in s_cand
   __shared__ int s_cand[RS_LIST];
   __shared__ double s_best_d[kMaxK];             // scratch for the reduction to the best k
@@ -500,7 +511,10 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
                    ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
 
   for (int64_t row = blockIdx.x; row < n_query; row += gridDim.x) {
-    if (!(row_thr[row] < INFINITY)) continue;    // log overflow: the exact kernel decides this row (block-uniform)
+    if (!(row_thr[row] < INFINITY)) continue;    // log overflow / decided by the warp kernel (block-uniform)
+    // direct route: the candidates above the FIRST threshold are scored in fp64 right away (no refined values exist)
+    const bool direct = row_mode[row] != kRouteRefine;      // block-uniform
+    const float* __restrict__ ref_val = direct ? log_val : ref_val_in;
     const float* qrow = q + row * dim;
     __syncthreads();
     if (tid == 0) {
@@ -654,7 +668,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_rescore_kernel(
 int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const float* p, const double* pn,
                        int64_t n_pool, int dim, int k, const FilterPlan& pl, const float* log_val,
                        const int* log_idx, const int* log_cnt, const float* seg_top, float* ref_val, float* row_thr,
-                       int* blk_off, int64_t index_offset, float* out_dist, double* out_dist64, int64_t* out_idx,
+                       int* row_mode, int* blk_off, int64_t index_offset, float* out_dist, double* out_dist64, int64_t* out_idx,
                        int64_t* flag_list, int* flag_count, int* stats, const int64_t* mask_lo, const int64_t* mask_hi,
                        const float* q_err, const float* p_err, cudaStream_t stream) {
   if (n_query == 0) return 0;
@@ -668,7 +682,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
                                                                        pl.rf_nblk, log_idx, log_cnt, seg_top, row_thr,
                                                                        blk_off, flag_list, flag_count, stats, log_val,
                                                                        q_err, p_err, dim_pad,
-                                                                       opt_refine_min() > 0 ? opt_refine_min() : kRefineMinAbove);
+                                                                       opt_refine_min() > 0 ? opt_refine_min() : kRefineMinAbove,
+                                                                       row_mode);
     KNN_LAUNCH_CHECK();
   }
   // 2. fp32 refine of every candidate above the first threshold, block-major
@@ -681,8 +696,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
     if (grid > max_grid) grid = max_grid;
 #define KNN_REFINE_GO(NV)                                                                                          \
   knn_refine_kernel<NV><<<(unsigned)grid, 256, 0, stream>>>(q, qn, n_query, p, pn, dim, pl.n_seg, pl.cap, pl.rf_nblk, \
-                                                            log_val, log_idx, log_cnt, blk_off, row_thr, ref_val,    \
-                                                            stats, stats ? stats + 1 : nullptr, mask_lo, mask_hi)
+                                                            log_val, log_idx, row_mode, blk_off, row_thr, ref_val,   \
+                                                            stats, mask_lo, mask_hi)
     switch (vec ? dim / 128 : 0) {
       case 1: KNN_REFINE_GO(1); break;
       case 2: KNN_REFINE_GO(2); break;
@@ -703,7 +718,8 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
     int64_t g2 = ceil_div64(n_query, 8);
     if (g2 > 148 * 8) g2 = 148 * 8;
     knn_rescore_small_kernel<<<(unsigned)g2, 256, 0, stream>>>(q, qn, n_query, p, pn, dim, k, pl.n_seg, pl.cap, ref_val,
-                                                             log_idx, log_cnt, row_thr, 2.0f * refine_eps(dim, vec),
+                                                             log_val, row_mode, log_idx, log_cnt, row_thr,
+                                                             2.0f * refine_eps(dim, vec),
                                                              index_offset, out_dist, out_dist64, out_idx, stats, mask_lo,
                                                              mask_hi);
     KNN_LAUNCH_CHECK();
@@ -711,7 +727,7 @@ int launch_knn_rescore(const float* q, const double* qn, int64_t n_query, const 
   int64_t grid = n_query < 148 * 64 ? n_query : 148 * 64;
   knn_rescore_kernel<<<(unsigned)grid, RS_THREADS, 0, stream>>>(q, qn, n_query, p, pn, n_pool, dim, k, pl.n_seg,
                                                                    pl.cap, ref_val, log_val, log_idx, log_cnt, row_thr,
-                                                                   2.0f * refine_eps(dim, vec), index_offset, out_dist,
+                                                                   row_mode, 2.0f * refine_eps(dim, vec), index_offset, out_dist,
                                                                    out_dist64, out_idx, stats, mask_lo, mask_hi);
   KNN_LAUNCH_CHECK();
   return 0;

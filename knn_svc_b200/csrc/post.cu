@@ -419,9 +419,13 @@ int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& poo
   if (grid > 148 * 16) grid = 148 * 16;
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
-  if (opt_concat_staged() && concat_staged_eligible(src, pool, dim))   // shared-memory staged recurrence (concat_cost_sm100.cu)
+  if (opt_concat_staged() && concat_staged_eligible(src, pool, dim)) {   // shared-memory staged recurrence (concat_cost_sm100.cu)
+    if (opt_concat_cluster() && concat_cluster_fits(n_utt))              // few utterances: 8 SMs each
+      return launch_concat_cost_cluster(idx, src, pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
+                                        base, n2, out_idx, stream);
     return launch_concat_cost_staged(idx, src, pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
                                      base, n2, out_idx, stream);
+  }
   concat_cost_kernel<<<n_utt, CC_WARPS * 32, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0, concat_weight,
                                                       utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();

@@ -286,16 +286,29 @@ def _set_opt(name, value):
     assert _lib.load().knnsvc_set_option(name.encode(), int(value)) == 0
 
 
-@pytest.mark.parametrize("staged", [0, 1])
-def test_concat_cost_both_kernels_match_reference(ops, golden, staged):
-    """the shared-memory staged kernel (concat_cost_sm100.cu) and the general kernel (post.cu)
+K5_KERNELS = {"general": (0, 0), "staged": (1, 0), "cluster": (1, 1)}   # (concat_staged, concat_cluster)
+
+
+class _k5_kernel:
+    """force one of the three K5 kernels: the general one (post.cu), the one-CTA shared-memory staged one, or the
+    cluster kernel (8 CTAs per utterance; the default for launches of a few utterances)"""
+    def __init__(self, name):
+        self.opts = K5_KERNELS[name]
+
+    def __enter__(self):
+        _set_opt("concat_staged", self.opts[0]); _set_opt("concat_cluster", self.opts[1])
+
+    def __exit__(self, *exc):
+        _set_opt("concat_staged", 1); _set_opt("concat_cluster", 1)
+
+
+@pytest.mark.parametrize("kernel", list(K5_KERNELS))
+def test_concat_cost_both_kernels_match_reference(ops, golden, kernel):
+    """the cluster kernel and the one-CTA staged kernel (concat_cost_sm100.cu) and the general kernel (post.cu)
     must each reproduce the reference's selections"""
-    _set_opt("concat_staged", staged)
-    try:
+    with _k5_kernel(kernel):
         test_concat_cost_matches_reference(ops, golden)
         test_concat_cost_batched_utterances(ops)
-    finally:
-        _set_opt("concat_staged", 1)
 
 
 @pytest.mark.parametrize("use_f0", [False, True])
@@ -317,28 +330,25 @@ def test_concat_cost_staged_long_and_ragged(ops, use_f0):
     offsets_sets = [None, [0, 1, 2, 5, 700, 701, 3001], [0, 3001]]
     for offs in offsets_sets:
         outs = []
-        for staged in (0, 1):
-            _set_opt("concat_staged", staged)
-            try:
+        for kernel in K5_KERNELS:
+            with _k5_kernel(kernel):
                 outs.append(ops.concat_cost_reselect(*args, concat_weight=0.2, utt_offsets=offs).cpu().numpy())
-            finally:
-                _set_opt("concat_staged", 1)
         assert np.array_equal(outs[0], outs[1]), f"staged and general kernels disagree (offsets {offs})"
+        assert np.array_equal(outs[1], outs[2]), f"cluster and one-CTA staged kernels disagree (offsets {offs})"
     n_chk = 300
     want = orc.knn_with_concat_cost(idx[:n_chk], q[:n_chk], p, None if f0q is None else f0q[:n_chk], f0p, 0.2)
     assert np.array_equal(outs[1][:n_chk], want)
-    # narrow rows (dim 64) through both kernels
-    q2, p2 = synth.ar1_frames(200, d=64, seed=75), synth.ar1_frames(500, d=64, seed=76)
-    idx2 = rs.randint(0, 500, size=(200, 4)).astype(np.int64)
-    outs = []
-    for staged in (0, 1):
-        _set_opt("concat_staged", staged)
-        try:
-            outs.append(ops.concat_cost_reselect(dev(idx2), dev(q2), dev(p2), concat_weight=0.2).cpu().numpy())
-        finally:
-            _set_opt("concat_staged", 1)
-    assert np.array_equal(outs[0], outs[1])
-    assert np.array_equal(outs[1], orc.knn_with_concat_cost(idx2, q2, p2, concat_weight=0.2))
+    # narrow rows through all kernels: dim 64 (one slice of the cluster kernel, seven empty ones) and dim 328
+    # (two full slices and a partial one)
+    for d in (64, 328):
+        q2, p2 = synth.ar1_frames(200, d=d, seed=75), synth.ar1_frames(500, d=d, seed=76)
+        idx2 = rs.randint(0, 500, size=(200, 4)).astype(np.int64)
+        outs = []
+        for kernel in K5_KERNELS:
+            with _k5_kernel(kernel):
+                outs.append(ops.concat_cost_reselect(dev(idx2), dev(q2), dev(p2), concat_weight=0.2).cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2]), d
+        assert np.array_equal(outs[1], orc.knn_with_concat_cost(idx2, q2, p2, concat_weight=0.2)), d
 
 
 # ----------------------------------------------------------------------------- K6
@@ -678,17 +688,19 @@ def test_edge_branches_match_reference(ops):
     f0q, f0p = synth.f0_track(T, seed=113, unvoiced=0.3), synth.f0_track(Np, seed=114, unvoiced=0.3)
     idx = dev(e["k5e_idx"])
     try:
-        for staged in (1, 0):
+        for staged, clustered in ((1, 1), (1, 0), (0, 0)):
             _lib.check(lib.knnsvc_set_option(b"concat_staged", staged), "set_option")
+            _lib.check(lib.knnsvc_set_option(b"concat_cluster", clustered), "set_option")
             for w, tag in ((0.2, "w0p2"), (0.1, "w0p1"), (0.3, "w0p3")):
                 got = ops.concat_cost_reselect(idx, dev(q), dev(p), concat_weight=w).cpu().numpy()
-                assert np.array_equal(got, e[f"k5e_nof0_{tag}_f64"]), (staged, tag)
+                assert np.array_equal(got, e[f"k5e_nof0_{tag}_f64"]), (staged, clustered, tag)
                 got = ops.concat_cost_reselect(idx, dev(q), dev(p), dev(f0q), dev(f0p), concat_weight=w).cpu().numpy()
-                assert np.array_equal(got, e[f"k5e_f0_{tag}_f64"]), (staged, tag)
+                assert np.array_equal(got, e[f"k5e_f0_{tag}_f64"]), (staged, clustered, tag)
             two = ops.concat_cost_reselect(idx[:2], dev(q[:2]), dev(p), concat_weight=0.2).cpu().numpy()
             assert np.array_equal(two, e["k5e_two_frames"])
     finally:
         lib.knnsvc_set_option(b"concat_staged", 1)
+        lib.knnsvc_set_option(b"concat_cluster", 1)
     prio = ops.f0_rerank(dev(f0q), dev(f0p), dev(e["k4e_nbrs"])).cpu().numpy()
     assert np.array_equal(prio, e["k4e_prio"])
     pool_med = torch.median(torch.log(dev(f0p)[dev(f0p) != 0]))

@@ -280,6 +280,40 @@ def test_refine_route_on_a_near_duplicate_pool(ops, k):
     check_knn_against_oracle(outs[1][3].cpu().numpy(), outs[1][2].cpu().numpy(), om_idx, om_val, k, min_cover=0.0)
 
 
+def test_decision_route_is_chosen_per_row(ops):
+    """one search whose first half of the query rows sits in a pool of near-duplicates (> 400 candidates inside
+    the fp16 window: refine route) and whose second half is i.i.d. (a handful of candidates: direct route,
+    decided by one warp per row): every row takes the route it would take alone — the candidate counts of the
+    mixed search are the sums of the two halves searched separately — and the result is the exact kernel's"""
+    rs = np.random.RandomState(6)
+    base = synth.ar1_frames(48, seed=92)
+    q_iid = rs.standard_normal((135, 1024)).astype(np.float32)
+    # the i.i.d. rows find 8 loose copies of themselves (cosine 0.89 +- 0.014: far wider than the window)
+    pool = np.concatenate([np.tile(base, (500, 1)) + 0.05 * rs.standard_normal((24000, 1024)),
+                           np.repeat(q_iid, 8, axis=0) + 0.5 * rs.standard_normal((1080, 1024)),
+                           rs.standard_normal((6920, 1024))]).astype(np.float32)
+    q_dense = (np.repeat(base, 3, axis=0)[:135] + 0.05 * rs.standard_normal((135, 1024))).astype(np.float32)
+    # interleave in runs of 5 rows so that 32-row groups of the refine kernel hold rows of both routes
+    order = np.argsort(np.concatenate([np.arange(135) // 5 * 2, np.arange(135) // 5 * 2 + 1]), kind="stable")
+    q = np.concatenate([q_dense, q_iid])[order]
+    pp = ops.prepare_rows(dev(pool))
+    k = 4
+    d, i, st = ops.knn_search(ops.prepare_rows(dev(q)), pp, k, return_stats=True)
+    de, ie = ops.knn_exact(ops.prepare_rows(dev(q)), pp, k)
+    assert torch.equal(i, ie) and torch.equal(d, de)
+    _, _, st_a = ops.knn_search(ops.prepare_rows(dev(q_dense)), pp, k, return_stats=True)
+    _, _, st_b = ops.knn_search(ops.prepare_rows(dev(q_iid)), pp, k, return_stats=True)
+    st, st_a, st_b = (x.cpu().numpy().astype(np.int64) for x in (st, st_a, st_b))
+    print("mixed", st[:3], st[7], "dense", st_a[:3], st_a[7], "iid", st_b[:3], st_b[7])
+    assert st[0] == st_a[0] == st_b[0] == 0
+    assert st_a[2] > 400 * 135 and st_a[7] < st_a[2] // 4, "fixture: the dense half must take the refine route"
+    assert st_b[2] <= 32 * 135 and st_b[7] == st_b[2], "fixture: the i.i.d. half must take the direct route"
+    # (the operand error bound eps is the max over the row set, so it can differ by a hair between the three
+    # query sets; the window, and with it the candidate count, is compared with 2% slack)
+    assert abs(int(st[2]) - int(st_a[2] + st_b[2])) <= 0.02 * st[2]
+    assert abs(int(st[7]) - int(st_a[7] + st_b[7])) <= 0.02 * st[7] + 8
+
+
 # ----------------------------------------------------------------------------- sharded row table (one GPU)
 @pytest.mark.parametrize("dim", [1024, 49])
 def test_gather_mix_sharded_equals_contiguous(ops, dim):
@@ -317,16 +351,16 @@ def test_post_opt_stage_on_a_row_table_equals_contiguous(ops):
     idx[250:] = rs.randint(0, 1200, size=(50, 4))
     idx[-1] = 1199                                                   # clamp at the end of the pool
     offs = [0, 120, 121, 300]
-    for staged in (1, 0):
-        _set_opt("concat_staged", staged)
+    for staged, clustered in ((1, 1), (1, 0), (0, 0)):       # cluster kernel, one-CTA staged kernel, general kernel
+        _set_opt("concat_staged", staged); _set_opt("concat_cluster", clustered)
         try:
             for f0 in (None, (dev(f0q), dev(f0p))):
                 args = () if f0 is None else f0
                 a = ops.concat_cost_reselect(dev(idx), dev(q), pool_t, *args, concat_weight=0.2, utt_offsets=offs)
                 b = ops.concat_cost_reselect(dev(idx), dev(q), table, *args, concat_weight=0.2, utt_offsets=offs)
-                assert torch.equal(a, b), (staged, f0 is None)
+                assert torch.equal(a, b), (staged, clustered, f0 is None)
         finally:
-            _set_opt("concat_staged", 1)
+            _set_opt("concat_staged", 1); _set_opt("concat_cluster", 1)
     wa, ia = ops.weight_fit(dev(idx), pool_t, 0.1, return_info=True, utt_offsets=offs)
     wb, ib = ops.weight_fit(dev(idx), table, 0.1, return_info=True, utt_offsets=offs)
     assert torch.equal(wa, wb) and torch.equal(ia, ib)
