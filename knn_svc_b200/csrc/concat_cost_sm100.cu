@@ -153,8 +153,15 @@ __device__ __forceinline__ float cs_col_dot(const float4& a, const float4& b) {
 #ifdef KNNSVC_K5_PROFILE
 __device__ long long g_k5_prof[8];
 #define K5_T(i) do { const long long _t = clock64(); prof[i] += _t - t_last; t_last = _t; } while (0)
+__device__ long long g_k5c_prof[16];
+#define K5C_BEGIN() long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t_last = clock64()
+#define K5C_T(i) do { const long long _t = clock64(); prof[i] += _t - t_last; t_last = _t; } while (0)
+#define K5C_END(base, cnt, cond) do { if (cond) for (int _i = 0; _i < (cnt); ++_i) g_k5c_prof[(base) + _i] = prof[_i]; } while (0)
 #else
 #define K5_T(i) do { } while (0)
+#define K5C_BEGIN() do { } while (0)
+#define K5C_T(i) do { } while (0)
+#define K5C_END(base, cnt, cond) do { } while (0)
 #endif
 
 }  // namespace
@@ -410,24 +417,32 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
 // Cluster variant: ONE UTTERANCE PER CLUSTER OF 8 CTAs, each CTA owning 128 of the feature dimensions.
 //
 // Measured on the one-CTA kernel (profiles/r2_k5_chain_experiment.txt): a step is bound by moving 13 rows =
-// 53 KB into one SM (~2900-3500 cycles) and by one warp finishing all eight candidates (~1200 cycles).
-// A batch of utterances hides neither — it does not have to, 148 CTAs run side by side — but a single long
-// utterance (BASELINE cfg 2: 3001 frames) waits for every step.  Here
-//   * CTA r fetches only columns [128 r, 128 r + 128) of the 13 rows (6.5 KB per step, TMA bulk copies, the
+// 53 KB into one SM and by one warp finishing all eight candidates.  A batch of utterances does not have to
+// hide either — 148 CTAs run side by side — but a single long utterance (BASELINE cfg 2: 3001 frames)
+// waits for every step.  Here
+//   * CTA r holds only columns [128 r, 128 r + 128) of the 13 rows (6.5 KB per step, TMA bulk copies, the
 //     same three-generation speculative ring as above);
 //   * compute warp m scores CANDIDATE m on the CTA's slice (one float4 column per lane, the six sums
 //     c.c, src.c, prev_j.c, a 5-level warp tree) and sends the six partial sums to warp m of all 8 CTAs with
 //     st.async (remote shared-memory stores that complete a transaction count on the receiver's mbarrier:
 //     no cluster barrier inside the loop);
 //   * warp m of EVERY CTA then adds the 8 slices in fp64 and finishes candidate m's cost (4 lanes = the 4
-//     previous selections, median over shuffles); the producer warp ranks the 8 costs, publishes the
-//     selection to its CTA and issues the next generation.  All 8 CTAs take the same decision from the
-//     same numbers, so nothing else crosses the cluster; rank 0 writes the output.
+//     previous selections, median over shuffles), posts it to its CTA, and every compute warp ranks the
+//     eight costs for itself — no decision warp on the chain.  All 8 CTAs take the same decisions from
+//     the same numbers, so nothing else crosses the cluster;
+//   * the fetch of the next generation is spread the same way: warp m issues the ONE speculative row that
+//     follows its own candidate as soon as it has sent its sums; a producer warp fetches what the frame
+//     number alone addresses (rows of idx[t], the query row, per-frame scalars) two steps ahead.  (Per-lane
+//     cp.async.bulk from one warp is serialised by the compiler, ~160 cycles a copy: 13 copies from one warp
+//     were 2200 of a 3100-cycle step in the first version of this kernel, profiles/r2b_k5_cluster.txt.)
+//   * a tenth warp repeats the ranking off the chain, writes the output (rank 0) and tells the producer
+//     which ring buffer is free again.
 // Arithmetic: slice r is exactly what compute warp r of the one-CTA kernel sums, the warp tree has the same
 // levels (16, 8, 4, 2, 1), the cross-slice tree and the cost formulas are the shared functions above —
 // the two kernels return the same bits.
 constexpr int CL_C = 8;                          // CTAs per cluster (portable maximum)
 constexpr int CL_SLICE = CS_MAX_DIM / CL_C;      // feature columns per CTA
+constexpr int CL_THREADS = CS_CT + 64;           // 8 compute warps, producer warp, output warp
 static_assert(CL_C == CS_WARPS, "slice r of the cluster kernel = compute warp r of the one-CTA kernel");
 static_assert(CL_SLICE == 128, "one float4 column per lane");
 
@@ -435,14 +450,15 @@ struct ClShared {
   float rows[CS_GENS][CS_ROWS][CL_SLICE];
   float xch[2][CS_C][CL_C][8];     // [step parity][candidate][source CTA]{c.c, src.c, prev0.c, -, prev1.c, prev2.c, prev3.c, -}
   CsMeta meta[CS_GENS];
-  double cost[CS_C];               // total cost of each candidate of the current step
-  double cinv[CS_C];               // 1/|candidate row|
-  double prev_inv[CS_K];           // 1/|row| of the previous selections
-  unsigned long long full_bar[CS_GENS];
-  unsigned long long xbar[2][CS_C];
-  unsigned long long cbar, sel_bar;
-  int sp[2][CS_K];                 // candidate slot (0..7) of each selection, by step parity
-  int prow[CS_K];                  // row (0..11) of the previous generation holding each selected row
+  double cost[2][CS_C];            // [step parity]: total cost of each candidate
+  double cinv[2][CS_C];            //   1/|candidate row|
+  int64_t cid[2][CS_C];            //   its pool row
+  int crow[2][CS_C];               //   its row (0..11) in the generation's ring buffer
+  double init_inv[CS_K];           // 1/|row| of idx[0]
+  unsigned long long full_bar[CS_GENS];    // 9 arrivals: 8 compute warps (one speculative row each) + the producer
+  unsigned long long empty_bar[CS_GENS];   // output warp -> producer: the buffer's generation has been consumed
+  unsigned long long xbar[2][CS_C];        // [step parity][candidate]: the 8 slices' partial sums have landed
+  unsigned long long cbar;                 // 9 arrivals: 8 costs of a step + the output warp (done with the step before)
 };
 
 __device__ __forceinline__ uint32_t cl_mapa(uint32_t addr, uint32_t cta) {
@@ -477,8 +493,18 @@ __device__ __forceinline__ void cl_mbar_wait_cluster(uint32_t bar, uint32_t pari
 __device__ __forceinline__ void cl_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// rank of candidate (lane & 7) among the eight total costs: ties to the lower candidate slot
+__device__ __forceinline__ int cl_rank8(double total, int lane) {
+  int rk = 0;
+#pragma unroll
+  for (int j = 0; j < CS_C; ++j) {
+    const double tj = __shfl_sync(0xffffffffu, total, j);
+    rk += (tj < total) || (tj == total && j < (lane & 7));
+  }
+  return rk;
+}
 
-__global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) concat_cost_cluster_kernel(
+__global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) concat_cost_cluster_kernel(
     const int64_t* __restrict__ idx, const float* __restrict__ src, const __grid_constant__ RowTable pool,
     int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
     const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
@@ -498,16 +524,13 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
   const uint32_t slice_bytes = (uint32_t)slice_len * 4u;
 
   if (tid == 0) {
-    for (int g = 0; g < CS_GENS; ++g) cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), 1);
+    for (int g = 0; g < CS_GENS; ++g) {
+      cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), CS_WARPS + 1);
+      cs_mbar_init(cs_smem_u32(&sh.empty_bar[g]), 1);
+    }
     for (int p = 0; p < 2; ++p)
       for (int m = 0; m < CS_C; ++m) cs_mbar_init(cs_smem_u32(&sh.xbar[p][m]), 1);
-    cs_mbar_init(cs_smem_u32(&sh.cbar), CS_C);
-    cs_mbar_init(cs_smem_u32(&sh.sel_bar), 1);
-    for (int j = 0; j < CS_K; ++j) {
-      sh.sp[0][j] = j;      // "selection 0" = idx[0] itself, sitting in slots 0..3 of generation 0
-      sh.sp[1][j] = j;
-      sh.prow[j] = j;
-    }
+    cs_mbar_init(cs_smem_u32(&sh.cbar), CS_C + 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -515,8 +538,10 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
   cl_cluster_sync();      // every CTA's barriers are live before a peer sends to them
 
   if (warp == CS_WARPS) {
-    // ============================ producer / decision warp ============================
-    if (lane < CS_K) {      // generation 0: this CTA's slice of the four rows of idx[0]
+    // ============================ producer warp: what the frame number alone addresses ============================
+    // lanes 0..3: the rows of idx[t]; lane 4: the query row t and its scalars.  Global operands of generation
+    // t + 1 are loaded into registers while generation t is issued.
+    if (lane < CS_K) {      // generation 0: this CTA's slice of the four rows of idx[0] (no speculative rows)
       const int64_t id = idx[f_begin * CS_K + lane];
       sh.meta[0].idx_g[lane] = id;
       if (slice_bytes)
@@ -525,90 +550,87 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
     }
     __syncwarp();
     if (lane == 0) cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[0]), CS_K * slice_bytes);
-    // what the frame number alone addresses is fetched one generation ahead into registers
-    int64_t next_idx = 0;                       // lanes 8..11: idx[t]
-    double next_base = 0.0, next_n2 = 1.0;      // lane 12: per-frame scalars of the query row
-    float next_f0 = 0.f;
-    if (n > 1) {
-      if (lane >= CS_C && lane < CS_C + CS_K) next_idx = idx[(f_begin + 1) * CS_K + (lane - CS_C)];
-      if (lane == CS_C + CS_K) {
-        next_base = base_all[f_begin + 1];
-        next_n2 = src_n2[f_begin + 1];
-        if (use_f0) next_f0 = __ldg(src_f0 + f_begin + 1);
+    int64_t next_idx = 0;
+    double next_base = 0.0, next_n2 = 1.0;
+    float next_f0 = 0.f, next_pf0 = 0.f;
+    auto prefetch = [&](int64_t t) {            // operands of generation t -> registers
+      if (t >= n) return;
+      if (lane < CS_K) {
+        next_idx = idx[(f_begin + t) * CS_K + lane];
+        if (use_f0) next_pf0 = __ldg(pool_f0 + next_idx);
+      } else if (lane == CS_K) {
+        next_base = base_all[f_begin + t];
+        next_n2 = src_n2[f_begin + t];
+        if (use_f0) next_f0 = __ldg(src_f0 + f_begin + t);
       }
-    }
-    // generation t >= 1: rows of idx[t], the query row t and the eight speculative rows cand[t-1] + 1
-    // (c_prev = cand[t-1][lane] in lanes 0..7)
-    auto issue_gen = [&](int64_t t, int64_t c_prev) {
+    };
+    prefetch(1);
+    for (int64_t t = 1; t < n; ++t) {
       const int g = (int)(t % CS_GENS);
+      const int64_t id = next_idx;
+      const double b = next_base, n2 = next_n2;
+      const float f0s = next_f0, f0p = next_pf0;
+      prefetch(t + 1);
+      // the ring buffer is free once the step that read generation t-3 as "previous" (step t-2) is decided
+      if (t >= CS_GENS) cs_mbar_wait(cs_smem_u32(&sh.empty_bar[g]), (uint32_t)((t / CS_GENS - 1) & 1));
       const uint32_t bar = cs_smem_u32(&sh.full_bar[g]);
-      int64_t id = -1;
-      if (lane < CS_C) {
-        id = c_prev + 1 >= n_pool ? n_pool - 1 : c_prev + 1;   // lib_ongaku_test.py:294-295
-        sh.meta[g].spec_g[lane] = id;
+      if (lane < CS_K) {
+        sh.meta[g].idx_g[lane] = id;
         if (slice_bytes)
-          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
-      } else if (lane < CS_C + CS_K) {
-        id = next_idx;
-        sh.meta[g].idx_g[lane - CS_C] = id;
-        if (slice_bytes)
-          cs_bulk_row(cs_smem_u32(&sh.rows[g][lane - CS_C][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
-        if (t + 1 < n) next_idx = idx[(f_begin + t + 1) * CS_K + (lane - CS_C)];
-      } else if (lane == CS_C + CS_K) {
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
+        if (use_f0) sh.meta[g].lf0_idx[lane] = log2((double)f0p + 1e-5);
+      } else if (lane == CS_K) {
         if (slice_bytes)
           cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_ROWS - 1][0]), src + (f_begin + t) * dim + s_lo, slice_bytes, bar);
-        sh.meta[g].base = next_base;
-        sh.meta[g].inv_src = rsqrt(next_n2);
-        sh.meta[g].lsrc = use_f0 ? log2((double)next_f0 + 1e-5) : 0.0;
-        if (t + 1 < n) {
-          next_base = base_all[f_begin + t + 1];
-          next_n2 = src_n2[f_begin + t + 1];
-          if (use_f0) next_f0 = __ldg(src_f0 + f_begin + t + 1);
-        }
-      }
-      if (use_f0 && lane < CS_C + CS_K) {
-        const double lf = log2((double)__ldg(pool_f0 + id) + 1e-5);
-        if (lane < CS_C) sh.meta[g].lf0_spec[lane] = lf;
-        else sh.meta[g].lf0_idx[lane - CS_C] = lf;
+        sh.meta[g].base = b;
+        sh.meta[g].inv_src = rsqrt(n2);
+        sh.meta[g].lsrc = use_f0 ? log2((double)f0s + 1e-5) : 0.0;
       }
       __syncwarp();
-      if (lane == 0) cs_mbar_expect_tx(bar, CS_ROWS * slice_bytes);   // release: publishes meta[g] too
-    };
-    int64_t c_cur = lane < CS_C ? idx[f_begin * CS_K + (lane & 3)] : 0;   // "cand[0]": idx[0] twice over
-    if (n > 1) issue_gen(1, c_cur);
+      if (lane == 0) cs_mbar_expect_tx(bar, (CS_K + 1) * slice_bytes);   // release: publishes its part of meta[g]
+    }
+  } else if (warp == CS_WARPS + 1) {
+    // ============================ output warp (off the chain) ============================
     for (int64_t s = 1; s < n; ++s) {
-      const int g = (int)(s % CS_GENS);
-      // candidate `lane` of step s: known since selection s-1
-      int my_row = lane;
-      if (lane < CS_K) {
-        c_cur = sh.meta[g].idx_g[lane];
-      } else if (lane < CS_C) {
-        const int slot = sh.sp[(s - 1) & 1][lane - CS_K];
-        c_cur = sh.meta[g].spec_g[slot];
-        my_row = CS_K + slot;
-      }
-      if (s + 1 < n) issue_gen(s + 1, c_cur);           // one whole step ahead of its use
+      const int par = (int)(s & 1);
+      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.cbar));        // done with the costs of step s-1
       cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 1) & 1));   // the eight costs of step s
-      const double total = lane < CS_C ? sh.cost[lane] : INFINITY;
-      int rk = 0;
-#pragma unroll
-      for (int j = 0; j < CS_C; ++j) {
-        const double tj = __shfl_sync(0xffffffffu, total, j);
-        rk += (tj < total) || (tj == total && j < lane);
-      }
-      if (lane < CS_C && rk < CS_K) {
-        if (rank == 0) out_idx[(f_begin + s) * CS_K + rk] = c_cur;
-        sh.sp[s & 1][rk] = lane;
-        sh.prow[rk] = my_row;
-        sh.prev_inv[rk] = sh.cinv[lane];
-      }
+      const double total = sh.cost[par][lane & 7];
+      const int64_t id = sh.cid[par][lane & 7];
+      const int rk = cl_rank8(total, lane);
+      if (rank == 0 && lane < CS_C && rk < CS_K) out_idx[(f_begin + s) * CS_K + rk] = id;
       __syncwarp();
-      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.sel_bar));   // release: selection s is published
+      // generation s-1 was read for the last time (as the previous one) by step s
+      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.empty_bar[(s - 1) % CS_GENS]));
     }
   } else {
     // ============================ compute warps: warp m scores candidate m ============================
     const int m = warp;
-    cs_mbar_wait(cs_smem_u32(&sh.full_bar[0]), 0);
+    const bool has_col = 4 * lane < slice_len;
+    const int j = lane & 3;
+    // lane 0 fetches the speculative row that follows this warp's candidate: row `c + 1` (clamped) into slot m of
+    // generation t (lib_ongaku_test.py:294-295); spec_publish() completes the generation's meta data and arrives
+    int64_t spec_id = 0;
+    float spec_f0 = 0.f;
+    auto spec_issue = [&](int64_t t, int64_t c) {
+      if (lane == 0) {
+        const int g = (int)(t % CS_GENS);
+        spec_id = c + 1 >= n_pool ? n_pool - 1 : c + 1;
+        if (slice_bytes)
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + m][0]), table_row(pool, spec_id, dim) + s_lo, slice_bytes,
+                      cs_smem_u32(&sh.full_bar[g]));
+        if (use_f0) spec_f0 = __ldg(pool_f0 + spec_id);
+      }
+    };
+    auto spec_publish = [&](int64_t t) {
+      if (lane == 0) {
+        const int g = (int)(t % CS_GENS);
+        sh.meta[g].spec_g[m] = spec_id;
+        if (use_f0) sh.meta[g].lf0_spec[m] = log2((double)spec_f0 + 1e-5);
+        cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[g]), slice_bytes);   // release
+      }
+      __syncwarp();
+    };
     if (warp < CS_K) {  // |row|^2 of the four initial selections (whole rows, from global memory: once)
       const int64_t id0 = idx[f_begin * CS_K + warp];
       const float4* r4 = reinterpret_cast<const float4*>(table_row(pool, id0, dim));
@@ -623,17 +645,30 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
         acc += (double)t;
       }
       acc = warp_sum(acc);
-      if (lane == 0) sh.prev_inv[warp] = rsqrt(acc);
+      if (lane == 0) sh.init_inv[warp] = rsqrt(acc);
       if (rank == 0 && lane == 0) out_idx[f_begin * CS_K + warp] = id0;
     }
+    // "step 0": candidate m is idx[0][m & 3] (the initial selection, twice over)
+    if (n > 1) {
+      spec_issue(1, idx[f_begin * CS_K + (m & 3)]);
+      spec_publish(1);
+    }
+    if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.full_bar[0]));    // generation 0 has no speculative rows
     cs_compute_sync();
-    const bool has_col = 4 * lane < slice_len;
-    const int j = lane & 3;
+    // the previous selection, in registers: candidate slot of each rank, its ring-buffer row, 1/|row| of rank j
+    int sp0 = 0, sp1 = 1, sp2 = 2, sp3 = 3;
+    int pr[CS_K] = {0, 1, 2, 3};
+    double pinv = sh.init_inv[j];
     double w_sticky = (double)concat_weight;
+    // which of the eight exchanged values this lane sums over the slices: lanes 0..3 prev_j.c, 4..7 c.c, 8..11 src.c
+    const int xoff = (lane & 12) == 0 ? (j == 0 ? 2 : 3 + j) : ((lane & 12) == 4 ? 0 : 1);
+    cs_mbar_wait(cs_smem_u32(&sh.full_bar[0]), 0);
+    K5C_BEGIN();
     for (int64_t s = 1; s < n; ++s) {
       const int g = (int)(s % CS_GENS), gp = (int)((s - 1) % CS_GENS), par = (int)(s & 1);
       // generation s was issued a whole step ago; what does not depend on selection s-1 is read first
       cs_mbar_wait(cs_smem_u32(&sh.full_bar[g]), (uint32_t)((s / CS_GENS) & 1));
+      K5C_T(0);
       const uint32_t xb = cs_smem_u32(&sh.xbar[par][m]);
       if (lane == 0) cs_mbar_expect_tx(xb, CL_C * 32u);
       float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = sv;
@@ -641,18 +676,34 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
         sv = *reinterpret_cast<const float4*>(&sh.rows[g][CS_ROWS - 1][4 * lane]);
         if (m < CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][m][4 * lane]);
       }
-      if (s >= 2) cs_mbar_wait(cs_smem_u32(&sh.sel_bar), (uint32_t)((s - 2) & 1));   // selection s-1
-      const int slot = m < CS_K ? 0 : sh.sp[(s - 1) & 1][m - CS_K];
-      int pr[CS_K];
-#pragma unroll
-      for (int jj = 0; jj < CS_K; ++jj) pr[jj] = sh.prow[jj];
-      const double pinv = sh.prev_inv[j];
+      if (s >= 2) {
+        // selection s-1: every compute warp ranks the eight costs of step s-1 for itself
+        cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 2) & 1));
+        K5C_T(1);
+        const int pp = par ^ 1;
+        const double t = sh.cost[pp][lane & 7];
+        const int cr = sh.crow[pp][lane & 7];
+        const double ci = sh.cinv[pp][lane & 7];
+        const int rk = cl_rank8(t, lane);
+        sp0 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 0)) - 1;
+        sp1 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 1)) - 1;
+        sp2 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 2)) - 1;
+        sp3 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 3)) - 1;
+        pr[0] = __shfl_sync(0xffffffffu, cr, sp0);
+        pr[1] = __shfl_sync(0xffffffffu, cr, sp1);
+        pr[2] = __shfl_sync(0xffffffffu, cr, sp2);
+        pr[3] = __shfl_sync(0xffffffffu, cr, sp3);
+        pinv = __shfl_sync(0xffffffffu, ci, j == 0 ? sp0 : (j == 1 ? sp1 : (j == 2 ? sp2 : sp3)));
+      }
+      K5C_T(2);
+      const int slot = m < CS_K ? 0 : (m == 4 ? sp0 : (m == 5 ? sp1 : (m == 6 ? sp2 : sp3)));
+      const int crow = m < CS_K ? m : CS_K + slot;
       // the six partial sums of candidate m over this CTA's slice: v[0] c.c, v[1] src.c, v[2 + jj] prev_jj.c
       float v[CS_ACC];
 #pragma unroll
       for (int a = 0; a < CS_ACC; ++a) v[a] = 0.f;
       if (has_col) {
-        if (m >= CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][CS_K + slot][4 * lane]);
+        if (m >= CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][crow][4 * lane]);
         v[0] = cs_col_dot(cv, cv);
         v[1] = cs_col_dot(sv, cv);
 #pragma unroll
@@ -678,28 +729,37 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CS_THREADS, 1) co
         const uint32_t la = cs_smem_u32(&sh.xch[par][m][rank][(lane >> 4) * 4]);
         cl_st_async4(cl_mapa(la, dst), r[0], r[1], r[2], 0.f, cl_mapa(xb, dst));
       }
-      cl_mbar_wait_cluster(xb, (uint32_t)(((s - 1) >> 1) & 1));
-      // candidate m's cost: lanes j = 0..3 take one previous selection each (the other lanes repeat them)
+      // while the sums travel: this warp's row of the next generation
       const CsMeta& mt = sh.meta[g];
+      const int64_t c_my = m < CS_K ? mt.idx_g[m] : mt.spec_g[slot];
+      if (s + 1 < n) spec_issue(s + 1, c_my);
+      K5C_T(3);
+      cl_mbar_wait_cluster(xb, (uint32_t)(((s - 1) >> 1) & 1));
+      K5C_T(4);
+      // candidate m's cost: lanes 0..3 own one previous selection each, lanes 4..7 |c|^2, lanes 8..11 src.c
       const double base = mt.base;
       if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
-      const float* x = &sh.xch[par][m][0][0];
-      const double n2 = cs_tree8(x + 0, 8);
-      const double d_src = cs_tree8(x + 1, 8);
-      const double d_prev = cs_tree8(x + (j == 0 ? 2 : 3 + j), 8);
+      const double mine = cs_tree8(&sh.xch[par][m][0][xoff], 8);
+      const double n2 = __shfl_sync(0xffffffffu, mine, 4);
+      const double d_src = __shfl_sync(0xffffffffu, mine, 8);
       const double my_inv = rsqrt(n2);
       const double match = cs_cos_dist(d_src, mt.inv_src, my_inv);
-      const double cc = cs_edit(cs_cos_dist(d_prev, pinv, my_inv), base, use_f0);
+      const double cc = cs_edit(cs_cos_dist(mine, pinv, my_inv), base, use_f0);    // meaningful in lanes 0..3
       const double c0 = __shfl_sync(0xffffffffu, cc, 0), c1 = __shfl_sync(0xffffffffu, cc, 1);
       const double c2 = __shfl_sync(0xffffffffu, cc, 2), c3 = __shfl_sync(0xffffffffu, cc, 3);
       const double lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
       const double total = cs_total(w_sticky, cs_median4(c0, c1, c2, c3), match, use_f0, lcand, mt.lsrc);
       if (lane == 0) {
-        sh.cost[m] = total;
-        sh.cinv[m] = my_inv;
+        sh.cost[par][m] = total;
+        sh.cinv[par][m] = my_inv;
+        sh.cid[par][m] = c_my;
+        sh.crow[par][m] = crow;
         cl_mbar_arrive(cs_smem_u32(&sh.cbar));      // release
       }
+      if (s + 1 < n) spec_publish(s + 1);
+      K5C_T(5);
     }
+    K5C_END(0, 6, lane == 0 && warp == 0 && blockIdx.x == 0);
   }
   __syncwarp();
   cl_cluster_sync();      // nobody leaves while a peer could still address its shared memory
@@ -724,7 +784,7 @@ bool concat_cluster_fits(int n_utt) {
   if (n_clusters < 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL_C);
-    cfg.blockDim = dim3(CS_THREADS);
+    cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = 0;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -746,9 +806,18 @@ int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTa
                                const float* src_f0, const float* pool_f0, float concat_weight,
                                const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                                int64_t* out_idx, cudaStream_t stream) {
-  concat_cost_cluster_kernel<<<n_utt * CL_C, CS_THREADS, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0,
+  concat_cost_cluster_kernel<<<n_utt * CL_C, CL_THREADS, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0,
                                                                       concat_weight, utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
+#ifdef KNNSVC_K5_PROFILE
+  {  // debugging aid: cycles of cluster 0 / rank 0 per phase, accumulated over the launch
+    long long h[16] = {0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_k5c_prof, sizeof(h));
+    fprintf(stderr, "[k5 cluster prof] warp0: gen-wait %lld cost-wait %lld rank %lld math+send+issue %lld xchg-wait %lld "
+            "cost+publish %lld\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+  }
+#endif
   return 0;
 }
 
