@@ -427,22 +427,28 @@ __global__ void __launch_bounds__(CS_THREADS, 1) concat_cost_staged_kernel(
 //     st.async (remote shared-memory stores that complete a transaction count on the receiver's mbarrier:
 //     no cluster barrier inside the loop);
 //   * warp m of EVERY CTA then adds the 8 slices in fp64 and finishes candidate m's cost (4 lanes = the 4
-//     previous selections, median over shuffles), posts it to its CTA, and every compute warp ranks the
-//     eight costs for itself — no decision warp on the chain.  All 8 CTAs take the same decisions from
-//     the same numbers, so nothing else crosses the cluster;
-//   * the fetch of the next generation is spread the same way: warp m issues the ONE speculative row that
-//     follows its own candidate as soon as it has sent its sums; a producer warp fetches what the frame
-//     number alone addresses (rows of idx[t], the query row, per-frame scalars) two steps ahead.  (Per-lane
-//     cp.async.bulk from one warp is serialised by the compiler, ~160 cycles a copy: 13 copies from one warp
-//     were 2200 of a 3100-cycle step in the first version of this kernel, profiles/r2b_k5_cluster.txt.)
-//   * a tenth warp repeats the ranking off the chain, writes the output (rank 0) and tells the producer
-//     which ring buffer is free again.
+//     previous selections, median over shuffles), posts it to its CTA, and every warp that needs the
+//     selection ranks the eight costs for itself — no decision warp on the chain.  All 8 CTAs take the same
+//     decisions from the same numbers, so nothing else crosses the cluster;
+//   * a lone warp runs ~4.5 cycles per instruction, so the chain is kept free of everything that is not the
+//     recurrence (profiles/r2b_k5_cluster.txt: with the fetch issued by the warps on the chain a step took
+//     3000-3100 cycles, 2200 of them per-lane cp.async.bulk issue in the first version).  The rows are
+//     fetched by warps of their own: two producer warps run two steps ahead with what the frame number
+//     alone addresses (rows of idx[t], the query row and its scalars; the rows idx[t-1] + 1), four fetch
+//     warps each rank the costs too and fetch the row that follows selection r, and an output warp writes
+//     the result (rank 0) and tells the producers which ring buffer is free again.
 // Arithmetic: slice r is exactly what compute warp r of the one-CTA kernel sums, the warp tree has the same
 // levels (16, 8, 4, 2, 1), the cross-slice tree and the cost formulas are the shared functions above —
 // the two kernels return the same bits.
 constexpr int CL_C = 8;                          // CTAs per cluster (portable maximum)
 constexpr int CL_SLICE = CS_MAX_DIM / CL_C;      // feature columns per CTA
-constexpr int CL_THREADS = CS_CT + 64;           // 8 compute warps, producer warp, output warp
+constexpr int CL_W_PROD_A = CS_WARPS;            // rows of idx[t], query row t
+constexpr int CL_W_PROD_B = CS_WARPS + 1;        // rows idx[t-1] + 1
+constexpr int CL_W_FETCH = CS_WARPS + 2;         // .. + 5: row following selection r
+constexpr int CL_W_OUT = CS_WARPS + 2 + CS_K;    // output
+constexpr int CL_THREADS = (CL_W_OUT + 1) * 32;  // 15 warps
+constexpr int CL_FULL_ARRIVALS = 2 + CS_K;       // per generation: producers A and B, four fetch warps
+constexpr int CL_COST_ARRIVALS = CS_C + 1 + CS_K;   // per step: 8 costs; output warp and fetch warps "done with the step before"
 static_assert(CL_C == CS_WARPS, "slice r of the cluster kernel = compute warp r of the one-CTA kernel");
 static_assert(CL_SLICE == 128, "one float4 column per lane");
 
@@ -450,15 +456,15 @@ struct ClShared {
   float rows[CS_GENS][CS_ROWS][CL_SLICE];
   float xch[2][CS_C][CL_C][8];     // [step parity][candidate][source CTA]{c.c, src.c, prev0.c, -, prev1.c, prev2.c, prev3.c, -}
   CsMeta meta[CS_GENS];
-  double cost[2][CS_C];            // [step parity]: total cost of each candidate
+  alignas(16) double cost[2][CS_C];   // [step parity]: total cost of each candidate (read as double2)
   double cinv[2][CS_C];            //   1/|candidate row|
   int64_t cid[2][CS_C];            //   its pool row
   int crow[2][CS_C];               //   its row (0..11) in the generation's ring buffer
   double init_inv[CS_K];           // 1/|row| of idx[0]
-  unsigned long long full_bar[CS_GENS];    // 9 arrivals: 8 compute warps (one speculative row each) + the producer
-  unsigned long long empty_bar[CS_GENS];   // output warp -> producer: the buffer's generation has been consumed
+  unsigned long long full_bar[CS_GENS];    // CL_FULL_ARRIVALS + bytes: the generation has landed
+  unsigned long long empty_bar[CS_GENS];   // output warp -> producers: the buffer's generation has been consumed
   unsigned long long xbar[2][CS_C];        // [step parity][candidate]: the 8 slices' partial sums have landed
-  unsigned long long cbar;                 // 9 arrivals: 8 costs of a step + the output warp (done with the step before)
+  unsigned long long cbar;                 // CL_COST_ARRIVALS: the eight costs of a step are posted
 };
 
 __device__ __forceinline__ uint32_t cl_mapa(uint32_t addr, uint32_t cta) {
@@ -493,15 +499,20 @@ __device__ __forceinline__ void cl_mbar_wait_cluster(uint32_t bar, uint32_t pari
 __device__ __forceinline__ void cl_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// rank of candidate (lane & 7) among the eight total costs: ties to the lower candidate slot
-__device__ __forceinline__ int cl_rank8(double total, int lane) {
-  int rk = 0;
-#pragma unroll
-  for (int j = 0; j < CS_C; ++j) {
-    const double tj = __shfl_sync(0xffffffffu, total, j);
-    rk += (tj < total) || (tj == total && j < (lane & 7));
-  }
-  return rk;
+// The selection of a step from its eight posted costs, by a whole warp: lane l compares candidate l & 7 with
+// candidates 2 (l >> 3) and 2 (l >> 3) + 1, two shuffle-adds give every lane the rank of candidate l & 7
+// (ties to the lower candidate slot), four ballots the candidate of each rank.
+__device__ __forceinline__ void cl_select(const double* cost, int lane, int& sp0, int& sp1, int& sp2, int& sp3) {
+  const int a = lane & 7, b = (lane >> 3) * 2;
+  const double t = cost[a];
+  const double2 u = *reinterpret_cast<const double2*>(cost + b);
+  int cnt = (int)((u.x < t) || (u.x == t && b < a)) + (int)((u.y < t) || (u.y == t && b + 1 < a));
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+  sp0 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 0)) - 1;
+  sp1 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 1)) - 1;
+  sp2 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 2)) - 1;
+  sp3 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 3)) - 1;
 }
 
 __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) concat_cost_cluster_kernel(
@@ -515,33 +526,33 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int utt = blockIdx.x / CL_C;
   const int64_t f_begin = utt_offsets[utt], f_end = utt_offsets[utt + 1];
-  const int64_t n = f_end - f_begin;
-  if (n <= 0) return;                                  // (the same decision in all CTAs of the cluster)
+  if (f_end - f_begin <= 0) return;                    // (the same decision in all CTAs of the cluster)
+  const int n = (int)(f_end - f_begin);                // (the launcher admits utterances below 2^31 frames)
   const bool use_f0 = src_f0 != nullptr;
   const int64_t n_pool = pool.lo[pool.n];
   const int s_lo = (int)rank * CL_SLICE;               // first feature column of this CTA
   const int slice_len = dim - s_lo < 0 ? 0 : (dim - s_lo > CL_SLICE ? CL_SLICE : dim - s_lo);
   const uint32_t slice_bytes = (uint32_t)slice_len * 4u;
+  auto clamp_next = [&](int64_t c) { return c + 1 >= n_pool ? n_pool - 1 : c + 1; };   // lib_ongaku_test.py:294-295
 
   if (tid == 0) {
     for (int g = 0; g < CS_GENS; ++g) {
-      cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), CS_WARPS + 1);
+      cs_mbar_init(cs_smem_u32(&sh.full_bar[g]), CL_FULL_ARRIVALS);
       cs_mbar_init(cs_smem_u32(&sh.empty_bar[g]), 1);
     }
     for (int p = 0; p < 2; ++p)
       for (int m = 0; m < CS_C; ++m) cs_mbar_init(cs_smem_u32(&sh.xbar[p][m]), 1);
-    cs_mbar_init(cs_smem_u32(&sh.cbar), CS_C + 1);
+    cs_mbar_init(cs_smem_u32(&sh.cbar), CL_COST_ARRIVALS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
   cl_cluster_sync();      // every CTA's barriers are live before a peer sends to them
 
-  if (warp == CS_WARPS) {
-    // ============================ producer warp: what the frame number alone addresses ============================
-    // lanes 0..3: the rows of idx[t]; lane 4: the query row t and its scalars.  Global operands of generation
-    // t + 1 are loaded into registers while generation t is issued.
-    if (lane < CS_K) {      // generation 0: this CTA's slice of the four rows of idx[0] (no speculative rows)
+  if (warp == CL_W_PROD_A) {
+    // ============ producer A: rows of idx[t] (lanes 0..3), query row t and its scalars (lane 4) ============
+    // Global operands of generation t + 1 are loaded into registers while generation t is issued.
+    if (lane < CS_K) {      // generation 0: this CTA's slice of the four rows of idx[0] (no other rows)
       const int64_t id = idx[f_begin * CS_K + lane];
       sh.meta[0].idx_g[lane] = id;
       if (slice_bytes)
@@ -553,7 +564,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
     int64_t next_idx = 0;
     double next_base = 0.0, next_n2 = 1.0;
     float next_f0 = 0.f, next_pf0 = 0.f;
-    auto prefetch = [&](int64_t t) {            // operands of generation t -> registers
+    auto prefetch = [&](int t) {            // operands of generation t -> registers
       if (t >= n) return;
       if (lane < CS_K) {
         next_idx = idx[(f_begin + t) * CS_K + lane];
@@ -565,8 +576,8 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       }
     };
     prefetch(1);
-    for (int64_t t = 1; t < n; ++t) {
-      const int g = (int)(t % CS_GENS);
+    for (int t = 1; t < n; ++t) {
+      const int g = t % CS_GENS;
       const int64_t id = next_idx;
       const double b = next_base, n2 = next_n2;
       const float f0s = next_f0, f0p = next_pf0;
@@ -589,48 +600,93 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       __syncwarp();
       if (lane == 0) cs_mbar_expect_tx(bar, (CS_K + 1) * slice_bytes);   // release: publishes its part of meta[g]
     }
-  } else if (warp == CS_WARPS + 1) {
-    // ============================ output warp (off the chain) ============================
-    for (int64_t s = 1; s < n; ++s) {
-      const int par = (int)(s & 1);
-      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.cbar));        // done with the costs of step s-1
-      cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 1) & 1));   // the eight costs of step s
-      const double total = sh.cost[par][lane & 7];
-      const int64_t id = sh.cid[par][lane & 7];
-      const int rk = cl_rank8(total, lane);
-      if (rank == 0 && lane < CS_C && rk < CS_K) out_idx[(f_begin + s) * CS_K + rk] = id;
+  } else if (warp == CL_W_PROD_B) {
+    // ============ producer B: speculative rows 0..3 of generation t = the rows after idx[t-1] ============
+    // (candidates 0..3 of step t-1 are idx[t-1] whatever is selected; "step 0" has idx[0] in slots 0..3)
+    if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.full_bar[0]));
+    int64_t next_id = 0;
+    float next_pf0 = 0.f;
+    auto prefetch = [&](int t) {
+      if (t >= n || lane >= CS_K) return;
+      next_id = clamp_next(idx[(f_begin + t - 1) * CS_K + lane]);
+      if (use_f0) next_pf0 = __ldg(pool_f0 + next_id);
+    };
+    prefetch(1);
+    for (int t = 1; t < n; ++t) {
+      const int g = t % CS_GENS;
+      const int64_t id = next_id;
+      const float f0p = next_pf0;
+      prefetch(t + 1);
+      if (t >= CS_GENS) cs_mbar_wait(cs_smem_u32(&sh.empty_bar[g]), (uint32_t)((t / CS_GENS - 1) & 1));
+      const uint32_t bar = cs_smem_u32(&sh.full_bar[g]);
+      if (lane < CS_K) {
+        sh.meta[g].spec_g[lane] = id;
+        if (slice_bytes)
+          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
+        if (use_f0) sh.meta[g].lf0_spec[lane] = log2((double)f0p + 1e-5);
+      }
+      __syncwarp();
+      if (lane == 0) cs_mbar_expect_tx(bar, CS_K * slice_bytes);
+    }
+  } else if (warp >= CL_W_FETCH && warp < CL_W_FETCH + CS_K) {
+    // ============ fetch warp r: speculative row 4 + r of generation s + 1 = the row after candidate 4 + r of
+    // step s, which is the row after selection r of step s-1 ============
+    // (generations 0 and 1 need none: step 1 follows the initial selection, whose next rows are producer B's)
+    const int r = warp - CL_W_FETCH;
+    const uint32_t cbar = cs_smem_u32(&sh.cbar);
+    if (lane == 0) {
+      cl_mbar_arrive(cs_smem_u32(&sh.full_bar[0]));
+      if (n > 1) cl_mbar_arrive(cs_smem_u32(&sh.full_bar[1]));
+    }
+    for (int s = 1; s < n; ++s) {
+      const int pp = (s & 1) ^ 1;
+      int64_t sel_id;
+      if (s >= 2) {
+        cs_mbar_wait(cbar, (uint32_t)(s & 1));                            // costs of step s-1 (phase s-2)
+        int sp0, sp1, sp2, sp3;
+        cl_select(sh.cost[pp], lane, sp0, sp1, sp2, sp3);
+        sel_id = sh.cid[pp][(r == 0 ? sp0 : (r == 1 ? sp1 : (r == 2 ? sp2 : sp3))) & 7];
+      } else {
+        sel_id = idx[f_begin * CS_K + r];                                 // selection 0 = idx[0]
+      }
+      __syncwarp();
+      if (lane == 0) {
+        cl_mbar_arrive(cbar);                                             // done with the costs of step s-1
+        if (s + 1 < n) {
+          const int g = (s + 1) % CS_GENS;
+          const int64_t id = clamp_next(clamp_next(sel_id));
+          const uint32_t bar = cs_smem_u32(&sh.full_bar[g]);
+          if (slice_bytes)
+            cs_bulk_row(cs_smem_u32(&sh.rows[g][2 * CS_K + r][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
+          sh.meta[g].spec_g[CS_K + r] = id;
+          if (use_f0) sh.meta[g].lf0_spec[CS_K + r] = log2((double)__ldg(pool_f0 + id) + 1e-5);
+          cs_mbar_expect_tx(bar, slice_bytes);                            // release
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == CL_W_OUT) {
+    // ============ output warp (off the chain) ============
+    if (rank == 0 && lane < CS_K) out_idx[f_begin * CS_K + lane] = idx[f_begin * CS_K + lane];
+    for (int s = 1; s < n; ++s) {
+      const int par = s & 1;
+      if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.cbar));             // done with the costs of step s-1
+      cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 1) & 1));     // the eight costs of step s
+      int sp0, sp1, sp2, sp3;
+      cl_select(sh.cost[par], lane, sp0, sp1, sp2, sp3);
+      if (rank == 0 && lane < CS_K) {
+        const int c = (lane == 0 ? sp0 : (lane == 1 ? sp1 : (lane == 2 ? sp2 : sp3))) & 7;
+        out_idx[(f_begin + s) * CS_K + lane] = sh.cid[par][c];
+      }
       __syncwarp();
       // generation s-1 was read for the last time (as the previous one) by step s
       if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.empty_bar[(s - 1) % CS_GENS]));
     }
   } else {
-    // ============================ compute warps: warp m scores candidate m ============================
+    // ============ compute warps: warp m scores candidate m ============
     const int m = warp;
     const bool has_col = 4 * lane < slice_len;
     const int j = lane & 3;
-    // lane 0 fetches the speculative row that follows this warp's candidate: row `c + 1` (clamped) into slot m of
-    // generation t (lib_ongaku_test.py:294-295); spec_publish() completes the generation's meta data and arrives
-    int64_t spec_id = 0;
-    float spec_f0 = 0.f;
-    auto spec_issue = [&](int64_t t, int64_t c) {
-      if (lane == 0) {
-        const int g = (int)(t % CS_GENS);
-        spec_id = c + 1 >= n_pool ? n_pool - 1 : c + 1;
-        if (slice_bytes)
-          cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + m][0]), table_row(pool, spec_id, dim) + s_lo, slice_bytes,
-                      cs_smem_u32(&sh.full_bar[g]));
-        if (use_f0) spec_f0 = __ldg(pool_f0 + spec_id);
-      }
-    };
-    auto spec_publish = [&](int64_t t) {
-      if (lane == 0) {
-        const int g = (int)(t % CS_GENS);
-        sh.meta[g].spec_g[m] = spec_id;
-        if (use_f0) sh.meta[g].lf0_spec[m] = log2((double)spec_f0 + 1e-5);
-        cs_mbar_expect_tx(cs_smem_u32(&sh.full_bar[g]), slice_bytes);   // release
-      }
-      __syncwarp();
-    };
     if (warp < CS_K) {  // |row|^2 of the four initial selections (whole rows, from global memory: once)
       const int64_t id0 = idx[f_begin * CS_K + warp];
       const float4* r4 = reinterpret_cast<const float4*>(table_row(pool, id0, dim));
@@ -646,49 +702,50 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       }
       acc = warp_sum(acc);
       if (lane == 0) sh.init_inv[warp] = rsqrt(acc);
-      if (rank == 0 && lane == 0) out_idx[f_begin * CS_K + warp] = id0;
     }
-    // "step 0": candidate m is idx[0][m & 3] (the initial selection, twice over)
-    if (n > 1) {
-      spec_issue(1, idx[f_begin * CS_K + (m & 3)]);
-      spec_publish(1);
-    }
-    if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.full_bar[0]));    // generation 0 has no speculative rows
     cs_compute_sync();
     // the previous selection, in registers: candidate slot of each rank, its ring-buffer row, 1/|row| of rank j
     int sp0 = 0, sp1 = 1, sp2 = 2, sp3 = 3;
     int pr[CS_K] = {0, 1, 2, 3};
     double pinv = sh.init_inv[j];
     double w_sticky = (double)concat_weight;
-    // which of the eight exchanged values this lane sums over the slices: lanes 0..3 prev_j.c, 4..7 c.c, 8..11 src.c
-    const int xoff = (lane & 12) == 0 ? (j == 0 ? 2 : 3 + j) : ((lane & 12) == 4 ? 0 : 1);
+    // loop invariants: where this lane's st.async goes (both step parities), which exchanged value it sums
+    const uint32_t dst = (uint32_t)(lane & 7);
+    const int xoff = (lane & 12) == 0 ? (j == 0 ? 2 : 3 + j) : ((lane & 12) == 4 ? 0 : 1);   // lanes 0..3 prev_j.c, 4..7 c.c, 8.. src.c
+    const uint32_t lbar0 = cs_smem_u32(&sh.xbar[0][m]), lbar1 = cs_smem_u32(&sh.xbar[1][m]);
+    const uint32_t rbar0 = cl_mapa(lbar0, dst), rbar1 = cl_mapa(lbar1, dst);
+    const uint32_t rdat0 = cl_mapa(cs_smem_u32(&sh.xch[0][m][rank][(lane >> 4) * 4]), dst);
+    const uint32_t rdat1 = cl_mapa(cs_smem_u32(&sh.xch[1][m][rank][(lane >> 4) * 4]), dst);
+    const float* xsum0 = &sh.xch[0][m][0][xoff];
+    const float* xsum1 = &sh.xch[1][m][0][xoff];
+    const uint32_t cbar = cs_smem_u32(&sh.cbar);
     cs_mbar_wait(cs_smem_u32(&sh.full_bar[0]), 0);
+    int g = 1, gp = 0;
+    uint32_t full_phase = 1u;          // parity to wait for on each ring buffer's barrier (generation 0 is waited for here)
     K5C_BEGIN();
-    for (int64_t s = 1; s < n; ++s) {
-      const int g = (int)(s % CS_GENS), gp = (int)((s - 1) % CS_GENS), par = (int)(s & 1);
-      // generation s was issued a whole step ago; what does not depend on selection s-1 is read first
-      cs_mbar_wait(cs_smem_u32(&sh.full_bar[g]), (uint32_t)((s / CS_GENS) & 1));
+    for (int s = 1; s < n; ++s) {
+      const int par = s & 1;
+      // generation s (issued during step s-1) first: nothing of it may be read before its barrier is seen
+      cs_mbar_wait(cs_smem_u32(&sh.full_bar[g]), (full_phase >> g) & 1u);
+      full_phase ^= 1u << g;
       K5C_T(0);
-      const uint32_t xb = cs_smem_u32(&sh.xbar[par][m]);
-      if (lane == 0) cs_mbar_expect_tx(xb, CL_C * 32u);
+      const uint32_t lbar = par ? lbar1 : lbar0;
+      if (lane == 0) cs_mbar_expect_tx(lbar, CL_C * 32u);
+      const float* rg = &sh.rows[g][0][4 * lane];
+      const float* rgp = &sh.rows[gp][0][4 * lane];
       float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = sv;
-      if (has_col) {
-        sv = *reinterpret_cast<const float4*>(&sh.rows[g][CS_ROWS - 1][4 * lane]);
-        if (m < CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][m][4 * lane]);
+      if (has_col) {      // what does not depend on selection s-1 is read first
+        sv = *reinterpret_cast<const float4*>(rg + (CS_ROWS - 1) * CL_SLICE);
+        if (m < CS_K) cv = *reinterpret_cast<const float4*>(rg + m * CL_SLICE);
       }
       if (s >= 2) {
         // selection s-1: every compute warp ranks the eight costs of step s-1 for itself
-        cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 2) & 1));
+        cs_mbar_wait(cbar, (uint32_t)par);                              // phase s-2
         K5C_T(1);
         const int pp = par ^ 1;
-        const double t = sh.cost[pp][lane & 7];
         const int cr = sh.crow[pp][lane & 7];
         const double ci = sh.cinv[pp][lane & 7];
-        const int rk = cl_rank8(t, lane);
-        sp0 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 0)) - 1;
-        sp1 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 1)) - 1;
-        sp2 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 2)) - 1;
-        sp3 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && rk == 3)) - 1;
+        cl_select(sh.cost[pp], lane, sp0, sp1, sp2, sp3);
         pr[0] = __shfl_sync(0xffffffffu, cr, sp0);
         pr[1] = __shfl_sync(0xffffffffu, cr, sp1);
         pr[2] = __shfl_sync(0xffffffffu, cr, sp2);
@@ -703,12 +760,12 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
 #pragma unroll
       for (int a = 0; a < CS_ACC; ++a) v[a] = 0.f;
       if (has_col) {
-        if (m >= CS_K) cv = *reinterpret_cast<const float4*>(&sh.rows[g][crow][4 * lane]);
+        if (m >= CS_K) cv = *reinterpret_cast<const float4*>(rg + crow * CL_SLICE);
         v[0] = cs_col_dot(cv, cv);
         v[1] = cs_col_dot(sv, cv);
 #pragma unroll
         for (int jj = 0; jj < CS_K; ++jj)
-          v[2 + jj] = cs_col_dot(*reinterpret_cast<const float4*>(&sh.rows[gp][pr[jj]][4 * lane]), cv);
+          v[2 + jj] = cs_col_dot(*reinterpret_cast<const float4*>(rgp + pr[jj] * CL_SLICE), cv);
       }
       // warp tree, levels 16, 8, 4, 2, 1 as in the one-CTA kernel: lanes >= 16 end up with sums 3..5
       const bool upper = (lane & 16) != 0;
@@ -724,39 +781,36 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
 #pragma unroll
         for (int k = 0; k < 3; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
       // to warp m of every CTA of the cluster (this one included)
-      if ((lane & 15) < CL_C) {
-        const uint32_t dst = (uint32_t)(lane & 7);
-        const uint32_t la = cs_smem_u32(&sh.xch[par][m][rank][(lane >> 4) * 4]);
-        cl_st_async4(cl_mapa(la, dst), r[0], r[1], r[2], 0.f, cl_mapa(xb, dst));
-      }
-      // while the sums travel: this warp's row of the next generation
+      if ((lane & 15) < CL_C) cl_st_async4(par ? rdat1 : rdat0, r[0], r[1], r[2], 0.f, par ? rbar1 : rbar0);
+      // while the sums travel: what the cost needs besides them
       const CsMeta& mt = sh.meta[g];
       const int64_t c_my = m < CS_K ? mt.idx_g[m] : mt.spec_g[slot];
-      if (s + 1 < n) spec_issue(s + 1, c_my);
+      const double base = mt.base, inv_src = mt.inv_src;
+      const double lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
+      const double lsrc = mt.lsrc;
+      if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
       K5C_T(3);
-      cl_mbar_wait_cluster(xb, (uint32_t)(((s - 1) >> 1) & 1));
+      cl_mbar_wait_cluster(lbar, (uint32_t)(((s - 1) >> 1) & 1));
       K5C_T(4);
       // candidate m's cost: lanes 0..3 own one previous selection each, lanes 4..7 |c|^2, lanes 8..11 src.c
-      const double base = mt.base;
-      if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
-      const double mine = cs_tree8(&sh.xch[par][m][0][xoff], 8);
+      const double mine = cs_tree8(par ? xsum1 : xsum0, 8);
       const double n2 = __shfl_sync(0xffffffffu, mine, 4);
       const double d_src = __shfl_sync(0xffffffffu, mine, 8);
       const double my_inv = rsqrt(n2);
-      const double match = cs_cos_dist(d_src, mt.inv_src, my_inv);
+      const double match = cs_cos_dist(d_src, inv_src, my_inv);
       const double cc = cs_edit(cs_cos_dist(mine, pinv, my_inv), base, use_f0);    // meaningful in lanes 0..3
       const double c0 = __shfl_sync(0xffffffffu, cc, 0), c1 = __shfl_sync(0xffffffffu, cc, 1);
       const double c2 = __shfl_sync(0xffffffffu, cc, 2), c3 = __shfl_sync(0xffffffffu, cc, 3);
-      const double lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
-      const double total = cs_total(w_sticky, cs_median4(c0, c1, c2, c3), match, use_f0, lcand, mt.lsrc);
+      const double total = cs_total(w_sticky, cs_median4(c0, c1, c2, c3), match, use_f0, lcand, lsrc);
       if (lane == 0) {
         sh.cost[par][m] = total;
         sh.cinv[par][m] = my_inv;
         sh.cid[par][m] = c_my;
         sh.crow[par][m] = crow;
-        cl_mbar_arrive(cs_smem_u32(&sh.cbar));      // release
+        cl_mbar_arrive(cbar);      // release
       }
-      if (s + 1 < n) spec_publish(s + 1);
+      gp = g;
+      g = g == CS_GENS - 1 ? 0 : g + 1;
       K5C_T(5);
     }
     K5C_END(0, 6, lane == 0 && warp == 0 && blockIdx.x == 0);
@@ -764,6 +818,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
   __syncwarp();
   cl_cluster_sync();      // nobody leaves while a peer could still address its shared memory
 }
+
 
 size_t concat_staged_smem_bytes(int dim) {
   return (size_t)CS_GENS * CS_ROWS * dim * sizeof(float) + sizeof(CsShared);
