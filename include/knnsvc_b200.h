@@ -130,13 +130,18 @@ long long knnsvc_launch_count(void);
 /* tuning / experiment switches: "cta_group" = 1 (the cta_group::2 filter variant of round 1 was removed),
  * "bf16_operands" = 0|1 (bf16 instead of fp16 tensor-core operands; measurement only,
  * the error window is sized for fp16), "concat_staged" = 1|0 (shared-memory staged K5
- * kernel where the row shape allows it, or the general kernel only),
+ * kernel where the row shape allows it, or the general kernel only), "concat_cluster" = 1|0 (K5: launches of
+ * few utterances — as many as the device hosts clusters of 8 CTAs at once — run one utterance per cluster,
+ * the feature dimension split over its CTAs; same results as the one-CTA staged kernel, bit for bit),
+ * "concat_f0_table" = 1|0 (the cluster kernel reads log2 f0 of the pool rows from a table built once per
+ * call, for pools up to 4M rows; same results),
  * "spin_sleep_ns" (barrier poll back-off of the filter's producer / MMA lanes),
  * "block_tiles" (pool tiles of 256 rows per L2 block of the filter traversal, 0 = default 96),
  * "query_group" (chains — query tile x segment — per group of the filter's two-level unit order,
  * 0 = default 2 x SM count; a value >= the number of chains gives the flat block-major order),
  * "refine_min_candidates" (candidates per row above the first threshold from which the decision stage
- * re-scores in fp32 before the fp64 decision, 0 = default; same results either way),
+ * re-scores in fp32 before the fp64 decision, 0 = default 400; the route is chosen per query row; same results
+ * either way),
  * "log_cap" (candidate-log slots per row and pool segment, 0 = default 2048; the tests shrink it to
  * drive rows into the overflow -> exact-kernel path with small fixtures),
  * "filter_flags" (bit0: L2 prefetch of the next unit's query tile [default on], bit2: static

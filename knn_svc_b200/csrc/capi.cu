@@ -50,6 +50,9 @@ int opt_concat_staged() { return g_opt_concat_staged.load(std::memory_order_rela
 static std::atomic<int> g_opt_concat_cluster{1};
 int opt_concat_cluster() { return g_opt_concat_cluster.load(std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_concat_f0_table{1};
+int opt_concat_f0_table() { return g_opt_concat_f0_table.load(std::memory_order_relaxed); }
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -285,6 +288,10 @@ int knnsvc_set_option(const char* name, int value) {
     g_opt_concat_cluster.store(value != 0, std::memory_order_relaxed);
     return 0;
   }
+  if (strcmp(name, "concat_f0_table") == 0) {
+    g_opt_concat_f0_table.store(value != 0, std::memory_order_relaxed);
+    return 0;
+  }
   if (strcmp(name, "filter_flags") == 0) {
     KNN_CHECK_ARG(value >= 0 && value <= 7, -1, "set_option: filter_flags out of range");
     g_opt_filter_flags.store(value, std::memory_order_relaxed);
@@ -516,13 +523,21 @@ static int concat_cost_on_table(const int64_t* idx, const float* src, const RowT
   cudaMemPool_t pool_h = nullptr;
   int rc_pool = scratch_pool(&pool_h);
   if (rc_pool) return rc_pool;
+  // (+ for f0 runs of a few utterances against a pool of moderate size: the table of log2 f0 of the cluster kernel)
+  const int64_t n_pool_rows = pool.lo[pool.n];
+  const bool lf0_table = shifted_src_f0 != nullptr && n_utt <= 32 && n_pool_rows <= ((int64_t)1 << 22) &&
+                         opt_concat_f0_table();
+  const size_t frame_bytes = (size_t)2 * (n_frames + 1) * sizeof(double);
   KNN_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&d_ws),
-                                   off_bytes + (size_t)2 * (n_frames + 1) * sizeof(double), pool_h, stream));
+                                   off_bytes + frame_bytes + (lf0_table ? (size_t)n_pool_rows * sizeof(double) : 0),
+                                   pool_h, stream));
   int64_t* d_off = reinterpret_cast<int64_t*>(d_ws);
   KNN_CUDA(cudaMemcpyAsync(d_off, utt_offsets_host, (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            stream));
   int rc = launch_concat_cost(idx, src, pool, dim, shifted_src_f0, pool_f0, concat_weight, d_off, n_utt,
-                              n_frames, reinterpret_cast<double*>(d_ws + off_bytes), out_idx, stream);
+                              n_frames, reinterpret_cast<double*>(d_ws + off_bytes),
+                              lf0_table ? reinterpret_cast<double*>(d_ws + off_bytes + frame_bytes) : nullptr, out_idx,
+                              stream);
   cudaFreeAsync(d_ws, stream);
   return rc;
 }

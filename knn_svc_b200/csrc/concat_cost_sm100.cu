@@ -132,10 +132,14 @@ __device__ __forceinline__ double cs_edit(double cc, double base, bool use_f0) {
   return cc > base ? __fma_rn(1.5, cc, -base) : cc;
 }
 // lower median of 4 = second smallest (torch.median, lib_ongaku_test.py:337,342)
+// (plain compare-and-select: the costs are finite, and fmin / fmax spend half of their instructions on NaNs)
 __device__ __forceinline__ double cs_median4(double c0, double c1, double c2, double c3) {
-  const double lo01 = fmin(c0, c1), hi01 = fmax(c0, c1);
-  const double lo23 = fmin(c2, c3), hi23 = fmax(c2, c3);
-  return fmin(fmax(lo01, lo23), fmin(hi01, hi23));
+  const bool s01 = c0 < c1, s23 = c2 < c3;
+  const double lo01 = s01 ? c0 : c1, hi01 = s01 ? c1 : c0;
+  const double lo23 = s23 ? c2 : c3, hi23 = s23 ? c3 : c2;
+  const double a = lo01 < lo23 ? lo23 : lo01;      // max of the two minima
+  const double b = hi01 < hi23 ? hi01 : hi23;      // min of the two maxima
+  return a < b ? a : b;
 }
 __device__ __forceinline__ double cs_total(double w, double med, double match, bool use_f0, double lcand,
                                            double lsrc) {
@@ -501,23 +505,25 @@ __device__ __forceinline__ void cl_cluster_sync() {
 }
 // The selection of a step from its eight posted costs, by a whole warp: lane l compares candidate l & 7 with
 // candidates 2 (l >> 3) and 2 (l >> 3) + 1, two shuffle-adds give every lane the rank of candidate l & 7
-// (ties to the lower candidate slot), four ballots the candidate of each rank.
-__device__ __forceinline__ void cl_select(const double* cost, int lane, int& sp0, int& sp1, int& sp2, int& sp3) {
+// (ties to the lower candidate slot), and ONE warp-wide OR gathers the four selected candidates: byte r of the
+// result = (candidate slot << 4) | `tag` of the candidate of rank r (tag: 4 bits of the caller's, lanes 0..7).
+__device__ __forceinline__ unsigned cl_select(const double* cost, int lane, int tag) {
   const int a = lane & 7, b = (lane >> 3) * 2;
   const double t = cost[a];
   const double2 u = *reinterpret_cast<const double2*>(cost + b);
   int cnt = (int)((u.x < t) || (u.x == t && b < a)) + (int)((u.y < t) || (u.y == t && b + 1 < a));
   cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
   cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
-  sp0 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 0)) - 1;
-  sp1 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 1)) - 1;
-  sp2 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 2)) - 1;
-  sp3 = __ffs(__ballot_sync(0xffffffffu, lane < CS_C && cnt == 3)) - 1;
+  const unsigned mine = (lane < CS_C && cnt < CS_K) ? (unsigned)((a << 4) | (tag & 15)) << (8 * cnt) : 0u;
+  return __reduce_or_sync(0xffffffffu, mine);
 }
+__device__ __forceinline__ int cl_sel_slot(unsigned packed, int r) { return (int)(packed >> (8 * r + 4)) & 7; }
+__device__ __forceinline__ int cl_sel_tag(unsigned packed, int r) { return (int)(packed >> (8 * r)) & 15; }
 
 __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) concat_cost_cluster_kernel(
     const int64_t* __restrict__ idx, const float* __restrict__ src, const __grid_constant__ RowTable pool,
-    int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0, float concat_weight,
+    int dim, const float* __restrict__ src_f0, const float* __restrict__ pool_f0,
+    const double* __restrict__ lf0_tab, float concat_weight,
     const int64_t* __restrict__ utt_offsets, const double* __restrict__ base_all, const double* __restrict__ src_n2,
     int64_t* __restrict__ out_idx) {
   __shared__ __align__(128) ClShared sh;
@@ -529,6 +535,9 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
   if (f_end - f_begin <= 0) return;                    // (the same decision in all CTAs of the cluster)
   const int n = (int)(f_end - f_begin);                // (the launcher admits utterances below 2^31 frames)
   const bool use_f0 = src_f0 != nullptr;
+  // log2 f0 of the pool rows: from the per-call table when there is one (the compute warps load their candidate's
+  // value themselves), else computed by the warp that fetches the row
+  const bool row_lf0 = use_f0 && lf0_tab == nullptr;
   const int64_t n_pool = pool.lo[pool.n];
   const int s_lo = (int)rank * CL_SLICE;               // first feature column of this CTA
   const int slice_len = dim - s_lo < 0 ? 0 : (dim - s_lo > CL_SLICE ? CL_SLICE : dim - s_lo);
@@ -568,7 +577,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       if (t >= n) return;
       if (lane < CS_K) {
         next_idx = idx[(f_begin + t) * CS_K + lane];
-        if (use_f0) next_pf0 = __ldg(pool_f0 + next_idx);
+        if (row_lf0) next_pf0 = __ldg(pool_f0 + next_idx);
       } else if (lane == CS_K) {
         next_base = base_all[f_begin + t];
         next_n2 = src_n2[f_begin + t];
@@ -589,7 +598,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
         sh.meta[g].idx_g[lane] = id;
         if (slice_bytes)
           cs_bulk_row(cs_smem_u32(&sh.rows[g][lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
-        if (use_f0) sh.meta[g].lf0_idx[lane] = log2((double)f0p + 1e-5);
+        if (row_lf0) sh.meta[g].lf0_idx[lane] = log2((double)f0p + 1e-5);
       } else if (lane == CS_K) {
         if (slice_bytes)
           cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_ROWS - 1][0]), src + (f_begin + t) * dim + s_lo, slice_bytes, bar);
@@ -609,7 +618,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
     auto prefetch = [&](int t) {
       if (t >= n || lane >= CS_K) return;
       next_id = clamp_next(idx[(f_begin + t - 1) * CS_K + lane]);
-      if (use_f0) next_pf0 = __ldg(pool_f0 + next_id);
+      if (row_lf0) next_pf0 = __ldg(pool_f0 + next_id);
     };
     prefetch(1);
     for (int t = 1; t < n; ++t) {
@@ -623,7 +632,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
         sh.meta[g].spec_g[lane] = id;
         if (slice_bytes)
           cs_bulk_row(cs_smem_u32(&sh.rows[g][CS_K + lane][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
-        if (use_f0) sh.meta[g].lf0_spec[lane] = log2((double)f0p + 1e-5);
+        if (row_lf0) sh.meta[g].lf0_spec[lane] = log2((double)f0p + 1e-5);
       }
       __syncwarp();
       if (lane == 0) cs_mbar_expect_tx(bar, CS_K * slice_bytes);
@@ -643,9 +652,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       int64_t sel_id;
       if (s >= 2) {
         cs_mbar_wait(cbar, (uint32_t)(s & 1));                            // costs of step s-1 (phase s-2)
-        int sp0, sp1, sp2, sp3;
-        cl_select(sh.cost[pp], lane, sp0, sp1, sp2, sp3);
-        sel_id = sh.cid[pp][(r == 0 ? sp0 : (r == 1 ? sp1 : (r == 2 ? sp2 : sp3))) & 7];
+        sel_id = sh.cid[pp][cl_sel_slot(cl_select(sh.cost[pp], lane, 0), r)];
       } else {
         sel_id = idx[f_begin * CS_K + r];                                 // selection 0 = idx[0]
       }
@@ -659,7 +666,7 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
           if (slice_bytes)
             cs_bulk_row(cs_smem_u32(&sh.rows[g][2 * CS_K + r][0]), table_row(pool, id, dim) + s_lo, slice_bytes, bar);
           sh.meta[g].spec_g[CS_K + r] = id;
-          if (use_f0) sh.meta[g].lf0_spec[CS_K + r] = log2((double)__ldg(pool_f0 + id) + 1e-5);
+          if (row_lf0) sh.meta[g].lf0_spec[CS_K + r] = log2((double)__ldg(pool_f0 + id) + 1e-5);
           cs_mbar_expect_tx(bar, slice_bytes);                            // release
         }
       }
@@ -672,12 +679,8 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       const int par = s & 1;
       if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.cbar));             // done with the costs of step s-1
       cs_mbar_wait(cs_smem_u32(&sh.cbar), (uint32_t)((s - 1) & 1));     // the eight costs of step s
-      int sp0, sp1, sp2, sp3;
-      cl_select(sh.cost[par], lane, sp0, sp1, sp2, sp3);
-      if (rank == 0 && lane < CS_K) {
-        const int c = (lane == 0 ? sp0 : (lane == 1 ? sp1 : (lane == 2 ? sp2 : sp3))) & 7;
-        out_idx[(f_begin + s) * CS_K + lane] = sh.cid[par][c];
-      }
+      const unsigned sel = cl_select(sh.cost[par], lane, 0);
+      if (rank == 0 && lane < CS_K) out_idx[(f_begin + s) * CS_K + lane] = sh.cid[par][cl_sel_slot(sel, lane)];
       __syncwarp();
       // generation s-1 was read for the last time (as the previous one) by step s
       if (lane == 0) cl_mbar_arrive(cs_smem_u32(&sh.empty_bar[(s - 1) % CS_GENS]));
@@ -743,18 +746,20 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
         cs_mbar_wait(cbar, (uint32_t)par);                              // phase s-2
         K5C_T(1);
         const int pp = par ^ 1;
-        const int cr = sh.crow[pp][lane & 7];
         const double ci = sh.cinv[pp][lane & 7];
-        cl_select(sh.cost[pp], lane, sp0, sp1, sp2, sp3);
-        pr[0] = __shfl_sync(0xffffffffu, cr, sp0);
-        pr[1] = __shfl_sync(0xffffffffu, cr, sp1);
-        pr[2] = __shfl_sync(0xffffffffu, cr, sp2);
-        pr[3] = __shfl_sync(0xffffffffu, cr, sp3);
-        pinv = __shfl_sync(0xffffffffu, ci, j == 0 ? sp0 : (j == 1 ? sp1 : (j == 2 ? sp2 : sp3)));
+        const unsigned sel = cl_select(sh.cost[pp], lane, sh.crow[pp][lane & 7]);
+        sp0 = cl_sel_slot(sel, 0), sp1 = cl_sel_slot(sel, 1), sp2 = cl_sel_slot(sel, 2), sp3 = cl_sel_slot(sel, 3);
+#pragma unroll
+        for (int jj = 0; jj < CS_K; ++jj) pr[jj] = cl_sel_tag(sel, jj);
+        pinv = __shfl_sync(0xffffffffu, ci, cl_sel_slot(sel, j));
       }
       K5C_T(2);
       const int slot = m < CS_K ? 0 : (m == 4 ? sp0 : (m == 5 ? sp1 : (m == 6 ? sp2 : sp3)));
       const int crow = m < CS_K ? m : CS_K + slot;
+      const CsMeta& mt = sh.meta[g];
+      const int64_t c_my = m < CS_K ? mt.idx_g[m] : mt.spec_g[slot];      // the candidate's pool row
+      double lcand = 0.0;
+      if (use_f0 && !row_lf0) lcand = __ldg(lf0_tab + c_my);               // needed at the end of the step only
       // the six partial sums of candidate m over this CTA's slice: v[0] c.c, v[1] src.c, v[2 + jj] prev_jj.c
       float v[CS_ACC];
 #pragma unroll
@@ -783,10 +788,8 @@ __global__ void __cluster_dims__(CL_C, 1, 1) __launch_bounds__(CL_THREADS, 1) co
       // to warp m of every CTA of the cluster (this one included)
       if ((lane & 15) < CL_C) cl_st_async4(par ? rdat1 : rdat0, r[0], r[1], r[2], 0.f, par ? rbar1 : rbar0);
       // while the sums travel: what the cost needs besides them
-      const CsMeta& mt = sh.meta[g];
-      const int64_t c_my = m < CS_K ? mt.idx_g[m] : mt.spec_g[slot];
       const double base = mt.base, inv_src = mt.inv_src;
-      const double lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
+      if (row_lf0) lcand = m < CS_K ? mt.lf0_idx[m] : mt.lf0_spec[slot];
       const double lsrc = mt.lsrc;
       if (use_f0 && !(base < 0.08)) w_sticky = 0.0;  // sticky: persists for all later frames (lib_ongaku_test.py:332)
       K5C_T(3);
@@ -858,10 +861,10 @@ bool concat_cluster_fits(int n_utt) {
 }
 
 int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTable& pool, int dim,
-                               const float* src_f0, const float* pool_f0, float concat_weight,
+                               const float* src_f0, const float* pool_f0, const double* lf0_tab, float concat_weight,
                                const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                                int64_t* out_idx, cudaStream_t stream) {
-  concat_cost_cluster_kernel<<<n_utt * CL_C, CL_THREADS, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0,
+  concat_cost_cluster_kernel<<<n_utt * CL_C, CL_THREADS, 0, stream>>>(idx, src, pool, dim, src_f0, pool_f0, lf0_tab,
                                                                       concat_weight, utt_offsets_dev, base, n2, out_idx);
   KNN_LAUNCH_CHECK();
 #ifdef KNNSVC_K5_PROFILE

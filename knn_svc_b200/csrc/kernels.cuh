@@ -15,6 +15,7 @@ int opt_query_group();   // chains per group of the filter's two-level unit orde
 int opt_block_tiles();   // pool tiles per L2 block of the filter traversal (0 = default)
 int opt_concat_staged();   // 1 (default): shared-memory staged K5 where eligible; 0: general kernel only
 int opt_concat_cluster();  // 1 (default): a few long utterances get a cluster of 8 CTAs each (dimension split)
+int opt_concat_f0_table(); // 1 (default): the cluster kernel reads log2 f0 of pool rows from a per-call table (pools <= 4M rows)
 int opt_epi_sleep_ns();  // nanosleep between the epilogue warps' polls of the accumulator-ready barrier
 int opt_spin_ns();     // nanosleep between barrier polls of the producer / MMA lanes (0 = pure spin)        // 1: bf16 tensor-core operands (experiment only: 8x wider rounding error than fp16)
 
@@ -99,7 +100,8 @@ int launch_f0_rerank(const float* expected_f0, const float* pool_f0, const int64
                      int64_t* out_idx, cudaStream_t stream);
 int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
-                       int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream);
+                       int n_utt, int64_t n_frames, double* frame_ws, double* lf0_ws, int64_t* out_idx,
+                       cudaStream_t stream);   // lf0_ws: optional scratch of one double per pool frame (f0 runs of few utterances)
 
 // ---- concat_cost_sm100.cu
 bool concat_staged_eligible(const float* src, const RowTable& pool, int dim);
@@ -110,7 +112,7 @@ int launch_concat_cost_staged(const int64_t* idx, const float* src, const RowTab
 
 bool concat_cluster_fits(int n_utt);   // true: every utterance gets a resident cluster of 8 CTAs on this device
 int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTable& pool, int dim,
-                               const float* src_f0, const float* pool_f0, float concat_weight,
+                               const float* src_f0, const float* pool_f0, const double* lf0_tab, float concat_weight,
                                const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                                int64_t* out_idx, cudaStream_t stream);
 

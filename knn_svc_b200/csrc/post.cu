@@ -207,6 +207,13 @@ __global__ void __launch_bounds__(256) frame_baseline_kernel(const float* __rest
   }
 }
 
+// log2(f0 + 1e-5) of every pool frame, once per call: the cluster kernel's warps then load a candidate's value
+// instead of running log2 next to the recurrence (lib_ongaku_test.py:322-323 takes the log of both f0 tracks)
+__global__ void __launch_bounds__(256) log_f0_table_kernel(const float* __restrict__ f0, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = log2((double)__ldg(f0 + i) + 1e-5);
+}
+
 // 16 warps: warp w scores candidate (w >> 1) over half (w & 1) of the feature dimension, so one
 // batch of 6 rows x 4 float4 loads per lane covers a 1024-dim row and a step costs about one
 // L2 round trip plus ~600 instructions per warp.
@@ -411,7 +418,8 @@ __global__ void __launch_bounds__(CC_WARPS * 32) concat_cost_kernel(
 
 int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& pool, int dim,
                        const float* src_f0, const float* pool_f0, float concat_weight, const int64_t* utt_offsets_dev,
-                       int n_utt, int64_t n_frames, double* frame_ws, int64_t* out_idx, cudaStream_t stream) {
+                       int n_utt, int64_t n_frames, double* frame_ws, double* lf0_ws, int64_t* out_idx,
+                       cudaStream_t stream) {
   if (n_utt == 0 || n_frames == 0) return 0;
   double* base = frame_ws;
   double* n2 = frame_ws + n_frames;
@@ -420,9 +428,17 @@ int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& poo
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
   if (opt_concat_staged() && concat_staged_eligible(src, pool, dim)) {   // shared-memory staged recurrence (concat_cost_sm100.cu)
-    if (opt_concat_cluster() && concat_cluster_fits(n_utt))              // few utterances: 8 SMs each
-      return launch_concat_cost_cluster(idx, src, pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
-                                        base, n2, out_idx, stream);
+    if (opt_concat_cluster() && concat_cluster_fits(n_utt)) {            // few utterances: 8 SMs each
+      if (src_f0 && lf0_ws) {
+        const int64_t n_pool = pool.lo[pool.n];
+        int64_t g2 = ceil_div64(n_pool, 256);
+        if (g2 > 148 * 8) g2 = 148 * 8;
+        log_f0_table_kernel<<<(unsigned)g2, 256, 0, stream>>>(pool_f0, n_pool, lf0_ws);
+        KNN_LAUNCH_CHECK();
+      }
+      return launch_concat_cost_cluster(idx, src, pool, dim, src_f0, pool_f0, src_f0 ? lf0_ws : nullptr, concat_weight,
+                                        utt_offsets_dev, n_utt, base, n2, out_idx, stream);
+    }
     return launch_concat_cost_staged(idx, src, pool, dim, src_f0, pool_f0, concat_weight, utt_offsets_dev, n_utt,
                                      base, n2, out_idx, stream);
   }

@@ -335,6 +335,13 @@ def test_concat_cost_staged_long_and_ragged(ops, use_f0):
                 outs.append(ops.concat_cost_reselect(*args, concat_weight=0.2, utt_offsets=offs).cpu().numpy())
         assert np.array_equal(outs[0], outs[1]), f"staged and general kernels disagree (offsets {offs})"
         assert np.array_equal(outs[1], outs[2]), f"cluster and one-CTA staged kernels disagree (offsets {offs})"
+        if use_f0:       # the cluster kernel without its per-call log2-f0 table (the path of pools above 4M rows)
+            _set_opt("concat_f0_table", 0)
+            try:
+                no_tab = ops.concat_cost_reselect(*args, concat_weight=0.2, utt_offsets=offs).cpu().numpy()
+            finally:
+                _set_opt("concat_f0_table", 1)
+            assert np.array_equal(no_tab, outs[2]), f"cluster kernel with / without the f0 table disagree (offsets {offs})"
     n_chk = 300
     want = orc.knn_with_concat_cost(idx[:n_chk], q[:n_chk], p, None if f0q is None else f0q[:n_chk], f0p, 0.2)
     assert np.array_equal(outs[1][:n_chk], want)
