@@ -292,6 +292,14 @@ int knnsvc_harmonic_amplitudes(const float* spec, const float* f0, int64_t frame
 /* Offline prematch (per_spk_extract :1672-1675): amp_ratio[t,k] =
  * |spec_utt[t]|_1 / (|spec_pool[idx[t,k]]|_1 + 1e-5).  knnsvc_row_l1: out[r] = sum |x[r,:]|. */
 int knnsvc_row_l1(const float* x, int64_t rows, int dim, float* out, void* stream);
+/* Small result -> PINNED host memory by a kernel (stores over PCIe into the mapped allocation; with unified
+ * addressing every cudaHostAlloc / torch pinned allocation is device-accessible at its host address) instead of
+ * a cudaMemcpy: a blocking device-to-host read waits on the copy engine behind whatever large download another
+ * stream has queued there, this does not.  Extension (no reference counterpart): it is how the matcher hands
+ * the shifted f0 back on the host (ddsp_prematch_dataset.py:1224-1233 computes it there) while a previous
+ * batch's features are still being downloaded.  nbytes a multiple of 4; the caller synchronises the stream. */
+int knnsvc_store_to_host(const void* src_device, void* dst_pinned_host, size_t nbytes, void* stream);
+
 int knnsvc_amp_ratio(const float* l1_query, const float* l1_pool, const int64_t* idx,
                      int64_t n_query, int k, int64_t n_pool, float* out, void* stream);
 

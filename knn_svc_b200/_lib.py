@@ -59,6 +59,7 @@ SIGNATURES = {
     "knnsvc_harmonic_amplitudes": (i32, [vp, vp, i64, i32, i32, i32, vp, vp]),
     "knnsvc_row_l1": (i32, [vp, i64, i32, vp, vp]),
     "knnsvc_amp_ratio": (i32, [vp, vp, vp, i64, i32, i64, vp, vp]),
+    "knnsvc_store_to_host": (i32, [vp, vp, C.c_size_t, vp]),
 }
 
 

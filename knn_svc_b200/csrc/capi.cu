@@ -633,4 +633,11 @@ int knnsvc_amp_ratio(const float* l1_query, const float* l1_pool, const int64_t*
   return launch_amp_ratio(l1_query, l1_pool, idx, n_query, k, n_pool, out, (cudaStream_t)stream);
 }
 
+int knnsvc_store_to_host(const void* src_device, void* dst_pinned_host, size_t nbytes, void* stream) {
+  KNN_CHECK_ARG(nbytes % 4 == 0, -1, "store_to_host: size must be a multiple of 4 bytes");
+  if (nbytes == 0) return 0;
+  KNN_CHECK_ARG(src_device && dst_pinned_host, -1, "store_to_host: null pointer");
+  return launch_store_to_host(src_device, dst_pinned_host, nbytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -116,6 +116,8 @@ int launch_concat_cost_cluster(const int64_t* idx, const float* src, const RowTa
                                const int64_t* utt_offsets_dev, int n_utt, const double* base, const double* n2,
                                int64_t* out_idx, cudaStream_t stream);
 
+int launch_store_to_host(const void* src, void* dst_mapped, size_t nbytes, cudaStream_t stream);   // post.cu
+
 // ---- weight_fit.cu
 size_t weight_fit_workspace_bytes(int64_t n_query, int k, int n_utt);
 int launch_weight_fit(const int64_t* idx, const RowTable& synth, int dim,

@@ -207,6 +207,22 @@ __global__ void __launch_bounds__(256) frame_baseline_kernel(const float* __rest
   }
 }
 
+// words of a small device buffer -> mapped pinned host memory, by stores (no copy engine involved)
+__global__ void __launch_bounds__(256) store_to_host_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                            size_t n_words) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+int launch_store_to_host(const void* src, void* dst_mapped, size_t nbytes, cudaStream_t stream) {
+  const size_t n_words = nbytes / 4;
+  size_t grid = (n_words + 255) / 256;
+  if (grid > 64) grid = 64;      // a few SMs saturate PCIe
+  store_to_host_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(src),
+                                                          reinterpret_cast<uint32_t*>(dst_mapped), n_words);
+  KNN_LAUNCH_CHECK();
+  return 0;
+}
+
 // log2(f0 + 1e-5) of every pool frame, once per call: the cluster kernel's warps then load a candidate's value
 // instead of running log2 next to the recurrence (lib_ongaku_test.py:322-323 takes the log of both f0 tracks)
 __global__ void __launch_bounds__(256) log_f0_table_kernel(const float* __restrict__ f0, int64_t n, double* __restrict__ out) {

@@ -136,8 +136,11 @@ def shift_query_f0_batched(f0_list, matching_f0_median: torch.Tensor):
     logf = torch.log(torch.where(voiced, pad, torch.ones_like(pad)))
     med = _lower_median_rows(logf, voiced)                      # NaN-free even for all-unvoiced rows
     shifted = torch.where(voiced, torch.exp(logf + matching_f0_median.to(pad.dtype) - med[:, None]), pad)
-    keep = torch.arange(L, device=dev)[None, :] < torch.tensor(lens, device=dev)[:, None]
-    return shifted[keep]
+    # the valid entries, row by row — gathered through indices built on the host (a boolean mask would make torch
+    # read the count back: a blocking device-to-host copy in the middle of the batch)
+    import numpy as np
+    take = np.concatenate([np.arange(n, dtype=np.int64) + u * L for u, n in enumerate(lens)]) if U else np.zeros(0, np.int64)
+    return shifted.reshape(-1).index_select(0, torch.from_numpy(take).to(dev))
 
 
 def parse_post_opt(post_opt: str) -> float:
@@ -237,7 +240,10 @@ def match_utterances(query_seqs, query_f0s, pool: MatchingPool, post_opt="no_pos
             t.record_stream(main)
     # the reference hands the shifted f0 back on the device its f0 came from (the host): one copy
     f0_devs = {f.device for f in query_f0s}
-    shifted_host = shifted_f0.to(next(iter(f0_devs))) if len(f0_devs) == 1 else None
+    if len(f0_devs) == 1 and next(iter(f0_devs)).type == "cpu":
+        shifted_host = ops.to_host_small(shifted_f0)      # (not through the copy engine: see ops.to_host_small)
+    else:
+        shifted_host = shifted_f0.to(next(iter(f0_devs))) if len(f0_devs) == 1 else None
     results = []
     for u in range(len(lens)):                      # u: the caller's index; its data sits at position place[u]
         a, b = offs[place[u]], offs[place[u] + 1]

@@ -89,15 +89,64 @@ def prepare_rows(x: torch.Tensor, check: bool = True) -> PreparedRows:
     norms = torch.empty((n,), dtype=torch.float64, device=x.device)
     scal = torch.zeros((2,), dtype=torch.int32, device=x.device)     # [0] bad-row counter, [1] max error (float bits)
     bad, err = scal[0:1], scal[1:2].view(torch.float32)
+    # With `check` the bad-row counter lives in PINNED HOST memory (device-accessible at its host address): the
+    # kernel touches it only when it finds a bad row, and reading it costs a stream synchronisation but no
+    # device-to-host copy — which would wait on the copy engine behind any large download another stream has
+    # queued (a previous batch's features).
+    flag = _pinned_flag() if check else None
+    if flag is not None:
+        flag[0] = 0
     lib = _lib.load()
     if n > 0:
         with torch.cuda.device(x.device):
             _lib.check(lib.knnsvc_prepare_rows(x.data_ptr(), n, dim, dim, half.data_ptr(), dim_pad, norms.data_ptr(),
-                                               bad.data_ptr(), err.data_ptr(), _stream()), "prepare_rows")
-    if check and n > 0 and int(bad.item()) != 0:
-        raise ValueError(f"{int(bad.item())} zero-norm or non-finite feature rows: cosine distance undefined "
-                         "(the reference exits with 'containing nan')")
+                                               (flag if flag is not None else bad).data_ptr(), err.data_ptr(),
+                                               _stream()), "prepare_rows")
+            if flag is not None:
+                torch.cuda.current_stream(x.device).synchronize()
+                n_bad = int(flag[0])
+                if n_bad != 0:
+                    raise ValueError(f"{n_bad} zero-norm or non-finite feature rows: cosine distance undefined "
+                                     "(the reference exits with 'containing nan')")
     return PreparedRows(x, half, norms, err)
+
+
+_host_local = None
+
+
+def _thread_state():
+    global _host_local
+    import threading
+    if _host_local is None:
+        _host_local = threading.local()
+    return _host_local
+
+
+def _pinned_flag() -> torch.Tensor:
+    """one pinned int32 per host thread"""
+    st = _thread_state()
+    if getattr(st, "flag", None) is None:
+        st.flag = torch.zeros((1,), dtype=torch.int32).pin_memory()
+    return st.flag
+
+
+def to_host_small(t: torch.Tensor) -> torch.Tensor:
+    """A small device tensor -> a fresh host tensor WITHOUT the copy engine: a kernel stores it into a pinned staging
+    buffer (grow-only, one per host thread), the stream is synchronised, the staging area is copied out.  A blocking
+    `.cpu()` would queue behind whatever another stream is downloading (knnsvc_store_to_host)."""
+    _dev(t, "tensor")
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0 or nbytes % 4 != 0:
+        return t.cpu()
+    st = _thread_state()
+    if getattr(st, "staging", None) is None or st.staging.numel() < nbytes:
+        st.staging = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8).pin_memory()
+    lib = _lib.load()
+    with torch.cuda.device(t.device):
+        _lib.check(lib.knnsvc_store_to_host(t.data_ptr(), st.staging.data_ptr(), nbytes, _stream()), "store_to_host")
+        torch.cuda.current_stream(t.device).synchronize()
+    return st.staging[:nbytes].clone().view(t.dtype).reshape(t.shape)
 
 
 def cosine_dist(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:

@@ -195,3 +195,27 @@ def test_cfg5_pairs_are_dealt_completely_and_evenly():
             assert len(mine) <= 3 or world == 1
         assert len(seen) == 7038 and sum(frames) == total_frames
         assert max(frames) - min(frames) <= 2 * 1500
+
+
+def test_options_from_the_environment():
+    """KNNSVC_OPTIONS="name=value,..." is applied when the library is loaded (no GPU needed: the switches are
+    host-side atomics); an unknown name fails loudly; every switch the header documents is accepted"""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    code = "from knn_svc_b200 import _lib; _lib.load(); print('loaded')"
+    ok = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
+                        env=dict(os.environ, KNNSVC_OPTIONS="concat_cluster=0, concat_f0_table=0,refine_min_candidates=800"))
+    assert ok.returncode == 0 and "loaded" in ok.stdout, ok.stderr[-2000:]
+    bad = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
+                         env=dict(os.environ, KNNSVC_OPTIONS="no_such_switch=1"))
+    assert bad.returncode != 0 and "unknown option" in bad.stderr
+    from knn_svc_b200 import _lib
+    lib = _lib.load()
+    header = (root / "include" / "knnsvc_b200.h").read_text()
+    for name, value in (("concat_staged", 1), ("concat_cluster", 1), ("concat_f0_table", 1), ("weight_fit_cluster", 1),
+                        ("refine_min_candidates", 0), ("log_cap", 0), ("block_tiles", 0), ("query_group", 0),
+                        ("filter_flags", 1), ("spin_sleep_ns", 40), ("cta_group", 1)):
+        assert f'"{name}"' in header, f"{name} is not documented in the header"
+        assert lib.knnsvc_set_option(name.encode(), value) == 0, name
+    assert lib.knnsvc_set_option(b"cta_group", 2) != 0       # the removed variant is refused, not ignored

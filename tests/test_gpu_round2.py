@@ -400,3 +400,49 @@ def test_merge_topk64_ranks_on_fp64(ops):
     gd = torch.tensor([[[a, 0.9]], [[a, 0.8]]], dtype=torch.float64, device=DEV)
     d, d64, i = ops.merge_topk64(gd, gi)
     assert i.tolist() == [[5, 70]]
+
+
+# ----------------------------------------------------------------------------- host reads that bypass the copy engine
+def test_validation_flag_and_small_downloads_do_not_use_the_copy_engine(ops):
+    """prepare_rows' bad-row counter lives in pinned host memory (the kernel writes it only for a bad row; reading
+    it is a stream synchronisation, not a device-to-host copy), and to_host_small stores a small result into pinned
+    staging memory by a kernel: neither waits behind a large download queued on another stream.  Functionally: bad
+    rows are still refused (zero-norm, NaN, inf), good rows pass, and the download equals .cpu() bit for bit."""
+    x = synth.ar1_frames(300, seed=5)
+    ops.prepare_rows(dev(x))                                        # passes
+    for bad_val, rows in ((0.0, [7]), (np.nan, [0, 299]), (np.inf, [150])):
+        y = x.copy()
+        for r in rows:
+            y[r] = bad_val if bad_val == 0.0 else y[r]
+            if bad_val != 0.0:
+                y[r, 3] = bad_val
+        with pytest.raises(ValueError, match=f"{len(rows)} zero-norm or non-finite"):
+            ops.prepare_rows(dev(y))
+    ops.prepare_rows(dev(x))                                        # the flag is reset for the next call
+    ops.prepare_rows(dev(y), check=False)                           # unchecked: no error, as before
+    g = torch.Generator(device=DEV); g.manual_seed(3)
+    for shape, dtype in (((1,), torch.float32), ((1000, 3), torch.float32), ((262145,), torch.float32),
+                         ((4097,), torch.float64), ((33, 4), torch.int64), ((5,), torch.int32)):
+        t = (torch.randn(shape, device=DEV, generator=g) * 1000).to(dtype)
+        h = ops.to_host_small(t)
+        assert h.device.type == "cpu" and h.dtype == dtype and h.shape == t.shape and torch.equal(h, t.cpu())
+    # while 1 GB is being downloaded on another stream, the small read returns long before that copy ends
+    big = torch.empty((256 << 20,), dtype=torch.float32, device=DEV)
+    big_host = torch.empty((256 << 20,), dtype=torch.float32).pin_memory()
+    side = torch.cuda.Stream()
+    small = torch.arange(1024, device=DEV, dtype=torch.float32)
+    torch.cuda.synchronize()
+    import time
+    done = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        big_host.copy_(big, non_blocking=True)
+        done.record()
+    t0 = time.perf_counter()
+    h = ops.to_host_small(small)
+    t_small = time.perf_counter() - t0
+    still_copying = not done.query()
+    done.synchronize()
+    t_big = time.perf_counter() - t0
+    print(f"small read {1e3 * t_small:.2f} ms while a {1e3 * t_big:.1f} ms download was in flight (still copying: {still_copying})")
+    assert torch.equal(h, small.cpu())
+    assert still_copying and t_small < 0.5 * t_big, "the small read waited for the download"
