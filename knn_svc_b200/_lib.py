@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libknnsvc_b200.so"
+# (KNNSVC_LIB_PATH: another build of the same library, for A/B measurements of two versions on one box)
+LIB_PATH = Path(os.environ["KNNSVC_LIB_PATH"]) if os.environ.get("KNNSVC_LIB_PATH") else _PKG / "libknnsvc_b200.so"
 
 _lib = None
 
