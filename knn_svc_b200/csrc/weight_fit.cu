@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) weight_fit_kernel(const double*
 // two cluster barriers per iteration, nothing touches L2 inside the loop.  Same arithmetic, same
 // reduction order as the one-CTA kernel: results are bit-identical.
 constexpr int WC_C = 8;            // CTAs per cluster (portable maximum)
-constexpr int WC_THREADS = 256;
+constexpr int WC_THREADS = 384;          // 12 warps = the 12 chunks of 32 frames a rank gets of a 3001-frame utterance: one pass per phase
 constexpr int WC_MIN_FRAMES = 512; // every rank gets at least two chunks
 
 __host__ __device__ inline int64_t wc_first_chunk(int64_t n_chunks, int rank) { return n_chunks * rank / WC_C; }
