@@ -444,7 +444,7 @@ int launch_concat_cost(const int64_t* idx, const float* src, const RowTable& poo
   frame_baseline_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, dim, n_frames, base, n2);
   KNN_LAUNCH_CHECK();
   if (opt_concat_staged() && concat_staged_eligible(src, pool, dim)) {   // shared-memory staged recurrence (concat_cost_sm100.cu)
-    if (opt_concat_cluster() && concat_cluster_fits(n_utt)) {            // few utterances: 8 SMs each
+    if (opt_concat_cluster() && concat_cluster_fits(n_utt) && n_frames < ((int64_t)1 << 31)) {   // few utterances: 8 SMs each (32-bit frame counters)
       if (src_f0 && lf0_ws) {
         const int64_t n_pool = pool.lo[pool.n];
         int64_t g2 = ceil_div64(n_pool, 256);
