@@ -1,6 +1,11 @@
-// K5, staged variant: greedy concatenation-cost re-selection with every row the
+// K5, staged variants: greedy concatenation-cost re-selection with every row the
 // recurrence touches resident in shared memory BEFORE the step that needs it.
 // knn_with_concat_cost — lib_ongaku_test.py:270-369, K = 4.
+//
+// Two kernels, same bits: concat_cost_staged_kernel (one CTA per utterance: batches) directly below, and
+// concat_cost_cluster_kernel (one cluster of 8 CTAs per utterance, the feature dimension split over the
+// cluster: launches of up to 15 utterances) further down; the arithmetic of a step lives in the cs_* functions
+// both call.  post.cu holds the general kernel for row shapes neither takes.
 //
 // The recurrence is serial in the frame index, so one CTA walks one utterance and the
 // cost of a step is a latency chain.  The general kernel in post.cu pays an L2 round

@@ -3,7 +3,8 @@
     python tools/sass_summary.py            (no GPU needed: cuobjdump on the built .so)
 
 Counts SASS mnemonics per kernel (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor
-load, UBLKCP = cp.async.bulk, UTMAPF = TMA L2 prefetch, UTCBAR = tcgen05.commit) and the PTX-level
+load, UBLKCP = cp.async.bulk, UTMAPF = TMA L2 prefetch, UTCBAR = tcgen05.commit, STAS = st.async into a peer
+CTA's shared memory, UCGABAR = cluster barrier, SYNCS = mbarrier operations) and the PTX-level
 `tcgen05.` / `cp.async.bulk` strings in the sources."""
 import re
 import subprocess
@@ -14,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "knn_svc_b200" / "libknnsvc_b200.so"
 PAT = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTMAPF", "UTCBAR", "HMMA", "SYNCS",
-       "DFMA", "FFMA2", "REDUX", "MUFU"]
+       "STAS", "UCGABAR", "DFMA", "FFMA2", "REDUX", "MUFU"]
 
 
 def main():
