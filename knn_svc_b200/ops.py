@@ -137,7 +137,7 @@ def to_host_small(t: torch.Tensor) -> torch.Tensor:
     _dev(t, "tensor")
     t = t.contiguous()
     nbytes = t.numel() * t.element_size()
-    if nbytes == 0 or nbytes % 4 != 0:
+    if nbytes == 0 or nbytes % 4 != 0 or t.data_ptr() % 4 != 0:      # (the kernel moves 32-bit words)
         return t.cpu()
     st = _thread_state()
     if getattr(st, "staging", None) is None or st.staging.numel() < nbytes:
